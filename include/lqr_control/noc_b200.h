@@ -1,0 +1,152 @@
+/*
+ * lqr_control/noc_b200.h — C-ABI of libnoc_b200.so, the batched LQR / SLQ solver for NVIDIA B200.
+ *
+ * Drop-in boundary for the hot path of KahnShi/NOC's `lqr_control` package.  The reference snapshot
+ * exports nothing (catkin_package() has no INCLUDE_DIRS/LIBRARIES, lqr_control/CMakeLists.txt:105-110)
+ * and defines no target; the only fixed names are the slots of its CMake template:
+ *     library  ${PROJECT_NAME}            lqr_control/CMakeLists.txt:124-126  -> this library
+ *     headers  include/${PROJECT_NAME}/   lqr_control/CMakeLists.txt:175-179  -> this directory
+ *     node     ${PROJECT_NAME}_node       lqr_control/CMakeLists.txt:136      -> out of scope (no ROS)
+ * Every entry point below says which SURVEY.md §8(a) row it implements; there is no reference
+ * function to cite because none exists.  Arithmetic is specified in DESIGN.md §2.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no C++ types, no exceptions cross this boundary.
+ *   - every data pointer may be a HOST pointer (pageable or pinned) or a DEVICE pointer of the
+ *     context's GPU; the library detects which (cudaPointerGetAttributes).  Device pointers are used
+ *     in place (no copy); host pointers are staged through library-owned device buffers.
+ *   - all matrices are row-major fp64.  Optional outputs may be NULL.
+ *   - return value: 0 = NOC_OK, negative = noc_error (call failed, see noc_last_error()).
+ *     Per-instance numerical outcomes never fail the call; they go to status[] (noc_status).
+ *   - a noc_ctx is bound to one GPU and is single-caller; distinct contexts are independent.
+ *     Calls are synchronous on return unless NOC_FLAG_ASYNC is set (device pointers only).
+ *   - there is NO CPU fallback: without a usable CUDA device noc_create() fails with
+ *     NOC_ERR_NO_DEVICE and nothing else can be called.
+ */
+#ifndef LQR_CONTROL_NOC_B200_H
+#define LQR_CONTROL_NOC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NOC_B200_VERSION_MAJOR 0
+#define NOC_B200_VERSION_MINOR 1
+
+typedef struct noc_ctx noc_ctx; /* opaque: owns streams, scratch device buffers */
+
+typedef enum {
+  NOC_OK = 0,
+  NOC_ERR_BAD_ARG = -1,     /* NULL required pointer, bad sizes, unknown enum */
+  NOC_ERR_UNSUPPORTED = -2, /* (n,m) / model / layout combination without a kernel */
+  NOC_ERR_CUDA = -3,        /* a CUDA runtime call failed; text in noc_last_error() */
+  NOC_ERR_NO_DEVICE = -4,   /* no CUDA device / not sm_100: there is no CPU fallback */
+  NOC_ERR_OOM = -5          /* device allocation failed */
+} noc_error;
+
+/* per-instance outcome, written to status[] */
+typedef enum {
+  NOC_STATUS_OK = 0,        /* LQR: sweep completed.  SLQ: converged (relative decrease < tol) */
+  NOC_STATUS_NOT_PD = 1,    /* LQR: R + B'PB not positive definite at some step; outputs are NaN */
+  NOC_STATUS_MAX_ITER = 2,  /* SLQ: max_iter reached */
+  NOC_STATUS_LS_FAIL = 3,   /* SLQ: no step length in the alpha schedule passed the Armijo test */
+  NOC_STATUS_REG_FAIL = 4   /* SLQ: regularisation exceeded 1e6 */
+} noc_status;
+
+typedef enum {
+  NOC_MODEL_QUAD12 = 0,   /* 12-state / 4-input quadrotor, DESIGN.md §2.1 */
+  NOC_MODEL_DUAL24 = 1,   /* two spring-coupled quadrotors, 24 / 8, DESIGN.md §2.6 */
+  NOC_MODEL_LTV_USER = 2  /* caller supplies A_k, B_k (noc_lqr_solve_batch / noc_dare_solve_batch only) */
+} noc_model;
+
+typedef enum {
+  NOC_LAYOUT_A_THEN_B = 0, /* record k = A_k (n*n, row-major) followed by B_k (n*m, row-major) */
+  NOC_LAYOUT_ROWS_AB = 1   /* record k = n rows of [A_k row i (n) | B_k row i (m)]  ("F = [A B]") */
+} noc_layout;
+
+enum {
+  NOC_FLAG_NONE = 0,
+  NOC_FLAG_ASYNC = 1       /* do not synchronise before returning (all pointers must be device pointers) */
+};
+
+typedef struct {
+  int32_t n, m, N;         /* state dim, input dim, horizon (steps) */
+  int32_t model;           /* noc_model */
+  int32_t layout;          /* noc_layout of AB records */
+  int32_t max_iter;        /* SLQ iterations / DARE iterations cap */
+  int32_t n_alpha;         /* SLQ: number of step lengths alpha_j = 2^-j tried */
+  int32_t flags;           /* NOC_FLAG_* */
+  double dt;               /* Euler step of the built-in models */
+  double tol;              /* SLQ: relative cost decrease; DARE: max|dP|/max|P| */
+  double reg0;             /* SLQ: initial Levenberg-Marquardt mu added to the diagonal of Quu */
+  double armijo;           /* SLQ: sufficient-decrease constant (1e-4) */
+} noc_problem_t;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int noc_create(noc_ctx** out, int device_id);
+void noc_destroy(noc_ctx* ctx);
+const char* noc_last_error(const noc_ctx* ctx);       /* never NULL */
+const char* noc_version(void);
+/* Launch on a caller-owned CUDA stream (cudaStream_t cast to void*); NULL restores the context's own. */
+int noc_set_stream(noc_ctx* ctx, void* cuda_stream);
+int noc_synchronize(noc_ctx* ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int64_t noc_launch_count(const noc_ctx* ctx);
+/* fill defaults: tol 1e-8, max_iter 50, n_alpha 11, armijo 1e-4, dt 0.02, layout A_THEN_B */
+void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N);
+
+/* ---- SURVEY §8(a) a2+a3: backward Riccati recursion, Cholesky, gains -------------------------
+ * Finite-horizon LTV LQR sweep for `batch` independent instances.
+ *   AB        [batch][N][n*n+n*m]   A_k,B_k records (prob->layout)
+ *   QRQf      [n*n + m*m + n*n]     Q, R, Qf shared by the batch, or [batch][...] if qr_per_instance
+ *   x0dev     [batch][n] or NULL    initial deviation; needed only for `cost`
+ *   K         [batch][N][m*n] or NULL   feedback gains u = K x
+ *   K0        [batch][m*n]   or NULL   gains of step 0 only (MPC use)
+ *   P0        [batch][n*n]   or NULL   cost-to-go matrix at step 0
+ *   cost      [batch]        or NULL   0.5 x0' P0 x0
+ *   status    [batch]        or NULL   noc_status                                                  */
+int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* AB,
+                        const double* QRQf, int qr_per_instance, const double* x0dev, double* K,
+                        double* K0, double* P0, double* cost, int32_t* status);
+
+/* ---- time-parallel linearisation ---------------------------------------------
+ *   xbar [batch][N+1][n], ubar [batch][N][m] (NULL = hover input everywhere) -> AB [batch][N][rec]     */
+int noc_linearize_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* xbar,
+                        const double* ubar, double* AB);
+/* open-loop nominal rollout x_{k+1} = x_k + dt f(x_k, u_k): x0 [batch][n] -> xbar [batch][N+1][n]     */
+int noc_rollout_open_loop(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* x0,
+                          const double* ubar, double* xbar);
+
+/* ---- configs 2 / 4 end to end: x0 -> hover-thrust nominal -> linearise -> sweep -----------------
+ * Same outputs as noc_lqr_solve_batch; x0dev = x0 (goal = origin).  The A_k,B_k stream lives in
+ * library scratch (chunked to the free HBM) and never crosses PCIe.                                  */
+int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* x0,
+                          const double* QRQf, double* K, double* K0, double* P0, double* cost,
+                          int32_t* status);
+
+/* ---- infinite-horizon LQR by fixed-point iteration ----------------------------
+ *   AB [batch][n*n+n*m] one LTI record per instance; QR [n*n+m*m] shared.
+ *   Iterates the sweep step from P = Q until max|P'-P| < tol * max|P'| or max_iter.
+ *   P [batch][n*n], K [batch][m*n], iters [batch], status [batch] (MAX_ITER if not converged)        */
+int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* AB,
+                         const double* QR, double* P, double* K, int32_t* iters, int32_t* status);
+
+/* ---- SLQ / iLQR with the built-in nonlinear models ---------------------------
+ *   x0, xgoal [batch][n]; QRQf shared.
+ *   x [batch][N+1][n], u [batch][N][m], K [batch][N][m*n] (NULL ok), cost [batch],
+ *   iters [batch], alpha_idx [batch][max_iter] (accepted j per iteration, -1 beyond), status [batch]  */
+int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* x0,
+                        const double* xgoal, const double* QRQf, double* x, double* u, double* K,
+                        double* cost, int32_t* iters, int32_t* alpha_idx, int32_t* status);
+
+/* ---- "pick the best rollout" on this GPU: index and value of the smallest finite cost ------------
+ * (the cross-GPU step is one all-gather of (cost,index) pairs in the host layer)          */
+int noc_argmin_cost(noc_ctx* ctx, const double* cost, int64_t batch, int64_t* best_index,
+                    double* best_cost);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQR_CONTROL_NOC_B200_H */

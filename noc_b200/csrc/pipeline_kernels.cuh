@@ -1,0 +1,104 @@
+// pipeline_kernels.cuh — the kernels either side of the Riccati sweep:
+//   k_rollout_open_loop  nominal trajectory from x0                 (sequential in k, thread per instance)
+//   k_linearize          A_k, B_k for all (instance, k) at once     (time-parallel)
+//   k_argmin_cost        smallest finite cost of a batch            ("pick the best rollout", §8e)
+// Arithmetic: model.cuh; bit-identical to oracle/noc_oracle.c.
+#pragma once
+#include "common.cuh"
+#include "model.cuh"
+
+namespace noc {
+
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_rollout_open_loop(const double* __restrict__ x0,
+                                                           const double* __restrict__ ubar,  // may be null
+                                                           double* __restrict__ xbar, long long batch, int N,
+                                                           double dt) {
+  constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  double x[n], xn[n], u[m];
+#pragma unroll
+  for (int i = 0; i < n; ++i) x[i] = x0[b * n + i];
+#pragma unroll
+  for (int j = 0; j < m; ++j) u[j] = model::kHover;
+  double* out = xbar + (size_t)b * (N + 1) * n;
+#pragma unroll
+  for (int i = 0; i < n; ++i) out[i] = x[i];
+  for (int k = 0; k < N; ++k) {
+    if (ubar) {
+#pragma unroll
+      for (int j = 0; j < m; ++j) u[j] = ubar[((size_t)b * N + k) * m + j];
+    }
+    model::model_step<MODEL>(x, u, dt, xn);
+#pragma unroll
+    for (int i = 0; i < n; ++i) { x[i] = xn[i]; out[(size_t)(k + 1) * n + i] = xn[i]; }
+  }
+}
+
+// One thread per (instance, k).  The record is zero-filled with 16-byte stores, then the ~70 structural
+// non-zeros are written.  L2 merges the partial sectors before they reach HBM (record = 1536 B, written
+// within one thread).  Layout 0: A then B; layout 1: rows of [A row | B row].
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_linearize(const double* __restrict__ xbar,
+                                                   const double* __restrict__ ubar,  // may be null
+                                                   double* __restrict__ AB, long long batch, int N, double dt,
+                                                   int layout) {
+  constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, rec = n * n + n * m;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= batch * N) return;
+  const long long b = t / N;
+  const int k = (int)(t - b * N);
+  double x[n], u[m];
+  const double* xs = xbar + ((size_t)b * (N + 1) + k) * n;
+#pragma unroll
+  for (int i = 0; i < n; ++i) x[i] = xs[i];
+#pragma unroll
+  for (int j = 0; j < m; ++j) u[j] = ubar ? ubar[((size_t)b * N + k) * m + j] : model::kHover;
+  double* r = AB + (size_t)t * rec;
+  double2* r2 = reinterpret_cast<double2*>(r);
+#pragma unroll 8
+  for (int i = 0; i < rec / 2; ++i) r2[i] = make_double2(0.0, 0.0);
+  if (layout == 0) {
+    model::model_jac_discrete<MODEL>(
+        x, u, dt, [&](int i, int j, double v) { r[i * n + j] = v; },
+        [&](int i, int j, double v) { r[n * n + i * m + j] = v; });
+  } else {
+    model::model_jac_discrete<MODEL>(
+        x, u, dt, [&](int i, int j, double v) { r[i * (n + m) + j] = v; },
+        [&](int i, int j, double v) { r[i * (n + m) + n + j] = v; });
+  }
+}
+
+// Single-CTA argmin over finite costs (NaN = failed instance, skipped).  Ties -> smallest index.
+__global__ void __launch_bounds__(1024) k_argmin_cost(const double* __restrict__ cost, long long batch,
+                                                      long long* __restrict__ best_index,
+                                                      double* __restrict__ best_cost) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  double v = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+  long long idx = -1;
+  for (long long i = threadIdx.x; i < batch; i += blockDim.x) {
+    const double c = cost[i];
+    if (c < v) { v = c; idx = i; }   // false for NaN
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, v, o);
+    const long long oi = __shfl_down_sync(0xffffffffu, idx, o);
+    if (oi >= 0 && (ov < v || (ov == v && (idx < 0 || oi < idx)))) { v = ov; idx = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    v = (threadIdx.x < (blockDim.x >> 5)) ? sv[threadIdx.x] : __longlong_as_double(0x7ff0000000000000LL);
+    idx = (threadIdx.x < (blockDim.x >> 5)) ? si[threadIdx.x] : -1;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, v, o);
+      const long long oi = __shfl_down_sync(0xffffffffu, idx, o);
+      if (oi >= 0 && (ov < v || (ov == v && (idx < 0 || oi < idx)))) { v = ov; idx = oi; }
+    }
+    if (threadIdx.x == 0) { *best_index = idx; *best_cost = idx >= 0 ? v : qnan(); }
+  }
+}
+
+}  // namespace noc

@@ -1,0 +1,57 @@
+"""CPU-only: the product library loads and exports every symbol include/lqr_control/noc_b200.h declares.
+No compute call is made (there is no GPU here and no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "lqr_control", "noc_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from noc_b200 import capi
+    if not os.path.exists(capi.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    return capi.load_library()
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(noc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = _declared()
+    assert len(names) >= 14
+    for nme in names:
+        assert hasattr(lib, nme), f"{nme} declared in the header but not exported"
+
+
+def test_python_export_list_matches_header():
+    from noc_b200 import capi
+    assert sorted(capi.EXPORTS) == _declared()
+
+
+def test_problem_struct_layout(lib):
+    from noc_b200 import capi
+    p = capi.problem(capi.MODEL_QUAD12, 100)
+    assert (p.n, p.m, p.N, p.model, p.layout) == (12, 4, 100, 0, 0)
+    assert (p.max_iter, p.n_alpha) == (50, 11)
+    assert p.dt == 0.02 and p.tol == 1e-8 and p.armijo == 1e-4 and p.reg0 == 0.0
+    p = capi.problem(capi.MODEL_DUAL24, 7)
+    assert (p.n, p.m, p.N) == (24, 8, 7)
+    assert ctypes.sizeof(capi.Problem) == 8 * 4 + 4 * 8
+
+
+def test_version_and_no_gpu_fails_loudly(lib):
+    from noc_b200 import capi
+    assert b"sm_100a" in lib.noc_version()
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(capi.NocError):
+            capi.Solver(0)
