@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — Riccati solves/sec (n=12, m=4, N=100, fp64) on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl noc|reference]
+
+One "step" = one pass of the hot path over one batch: the finite-horizon LTV Riccati sweep of
+BASELINE.json configs[1] (batch 65,536 per GPU, distinct A_k,B_k per instance and step), every gain
+K_k written.  `value` is timed with the A_k,B_k stream resident in HBM (12.6 GB >> 126 MB L2, so no
+L2 flush is needed between steps); `e2e` goes through the C-ABI with HOST buffers (pinned x0 in; K0,
+P0, cost, status out) — nominal rollout, linearisation and sweep all inside the timed region.
+N > 1 (torchrun, one rank per GPU): every rank sweeps its own 65,536 instances (weak scaling, no
+data-path collective), then costs are all-gathered over NCCL and the best rollout picked.
+
+`--impl reference`: the reference publishes no solver source, so this arm times the
+in-repo CPU oracle (kind "port") on all host cores.  bench.py is one of the three places allowed to
+execute oracle/ (tests/, smoke(), and the CPU legs here) — never on the measured GPU path.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "riccati_solves_per_sec_n12_m4_N100_fp64"
+UNIT = "solves/s"
+N_X, N_U, HORIZON = 12, 4, 100
+BATCH_PER_GPU = 65536
+BYTES_PER_STEP = 8 * (N_X * N_X + N_X * N_U) + 8 * N_U * N_X       # read A_k,B_k + write K_k = 1920 B
+FLOPS_PER_STEP_SYM = 9045                                          # SURVEY.md §8d, symmetry-aware count
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), "measured"
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+def fp64_peak_tflops():
+    """DFMA peak measured by tools/ubench on this pool's B200 (profiles/ubench_r01.json)."""
+    p = os.path.join(ROOT, "profiles", "ubench_r01.json")
+    try:
+        return float(json.load(open(p))["dfma_tflops_sustained"])
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f"/tmp/noc_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            c = [t.strip() for t in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2])); power.append(float(c[3]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": max(power)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------ CPU legs
+def cpu_leg(sample: int, threads: int = 0, repeats: int = 1):
+    """Oracle LTV sweep over `sample` synthetic instances of the same workload; returns solves/s."""
+    from noc_b200 import problems as pb
+    from oracle import pyoracle as oracle
+    oracle.build()
+    Q, R, Qf = pb.default_weights()
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(sample, seed=0x4E4F43)
+    AB = oracle.make_ab_batch(0, HORIZON, pb.DT, x0)          # untimed input generation
+    oracle.lqr_batch(N_X, N_U, HORIZON, AB[:min(sample, 256)], qr, x0dev=x0[:min(sample, 256)],
+                     threads=threads)                         # warm-up
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        oracle.lqr_batch(N_X, N_U, HORIZON, AB, qr, x0dev=x0, threads=threads)
+        best = min(best, time.perf_counter() - t0)
+    return sample / best, (threads if threads > 0 else oracle.max_threads()), best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import pyoracle as oracle
+    from noc_b200 import problems as pb
+    oracle.build()
+    sample = args.ref_sample
+    threads = oracle.max_threads()
+    Q, R, Qf = pb.default_weights()
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(sample, seed=0x4E4F43)
+    AB = oracle.make_ab_batch(0, HORIZON, pb.DT, x0)
+    for _ in range(args.warmup):
+        oracle.lqr_batch(N_X, N_U, HORIZON, AB, qr, x0dev=x0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.lqr_batch(N_X, N_U, HORIZON, AB, qr, x0dev=x0)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    sample_txt = (f"{sample} of the {BATCH_PER_GPU} config-2 instances per step (LTV sweep n=12 m=4 N=100, all K_k "
+                  f"written), OpenMP over instances")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "KahnShi/NOC ships no solver source (SURVEY.md §0): this is the in-repo CPU oracle, not the reference",
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(gpus, batch=BATCH_PER_GPU):
+    return {
+        "workload": "configs[1]: finite-horizon LTV LQR Riccati sweep, quadrotor n=12 m=4 N=100, "
+                    f"batch {batch} random initial states per GPU, distinct A_k,B_k per instance and step",
+        "n": N_X, "m": N_U, "N": HORIZON, "batch_per_gpu": batch, "global_batch": batch * gpus,
+        "sharding": f"dp{gpus} (independent instances; NCCL all-gather of costs + argmin only)",
+        "l2": "inputs larger than L2 (A_k,B_k stream 12.6 GB per step vs 126 MB L2); no flush needed",
+    }
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_noc(args):
+    import torch
+    from noc_b200 import capi, problems as pb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libnoc_b200 has no CPU fallback (use --impl reference "
+                         "for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    B, N = args.batch, HORIZON
+    Q, R, Qf = pb.default_weights()
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(B, seed=0x4E4F43 + rank)
+
+    solver = capi.Solver(local)
+    stream = torch.cuda.Stream(device=dev)
+    solver.set_stream(stream.cuda_stream)
+    f64 = dict(dtype=torch.float64, device=dev)
+
+    # ---- inputs resident in HBM: x0 -> hover-thrust nominal -> A_k,B_k stream (our own kernels, untimed)
+    d_x0 = torch.from_numpy(x0).to(dev)
+    d_qr = torch.from_numpy(qr).to(dev)
+    d_xbar = torch.empty(B, N + 1, N_X, **f64)
+    d_AB = torch.empty(B, N, N_X * N_X + N_X * N_U, **f64)
+    d_K = torch.empty(B, N, N_U, N_X, **f64)
+    d_K0 = torch.empty(B, N_U, N_X, **f64)
+    d_cost = torch.empty(B, **f64)
+    d_status = torch.full((B,), -1, dtype=torch.int32, device=dev)
+    d_all_cost = torch.empty(world * B, **f64) if world > 1 else None
+    torch.cuda.synchronize()
+    p_model = capi.problem(capi.MODEL_QUAD12, N, flags=capi.FLAG_ASYNC)
+    p_ltv = capi.problem(capi.MODEL_LTV_USER, N, flags=capi.FLAG_ASYNC)
+    with torch.cuda.stream(stream):
+        solver.rollout_open_loop(p_model, B, d_x0, None, d_xbar)
+        solver.linearize_batch(p_model, B, d_xbar, None, d_AB)
+    stream.synchronize()
+    del d_xbar
+
+    best = {}
+
+    def step():
+        solver.lqr_solve_batch(p_ltv, B, d_AB, d_qr, x0dev=d_x0, K=d_K, K0=d_K0, cost=d_cost, status=d_status)
+        if world > 1:
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(d_all_cost, d_cost)
+            best["idx"], best["cost"] = solver.argmin_cost(d_all_cost, world * B)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = solver.launch_count
+    solver.profile_reset()
+    solver.profile_enable(True)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    solver.profile_enable(False)
+    ric_ms, ric_n = solver.profile_read(capi.KERNEL_RICCATI)
+    launches = solver.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms], **f64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    n_bad = int((d_status != 0).sum().item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- e2e: the same solves through the C-ABI with HOST buffers (pinned), copies inside the timed region
+    h_x0 = torch.from_numpy(x0).pin_memory()
+    h_K0 = torch.empty(B, N_U, N_X, dtype=torch.float64).pin_memory()
+    h_P0 = torch.empty(B, N_X, N_X, dtype=torch.float64).pin_memory()
+    h_cost = torch.empty(B, dtype=torch.float64).pin_memory()
+    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+    p_sync = capi.problem(capi.MODEL_QUAD12, N)
+    h2d = h_x0.numel() * 8 + qr.size * 8
+    d2h = (h_K0.numel() + h_P0.numel() + h_cost.numel()) * 8 + h_status.numel() * 4
+
+    def e2e_step():
+        solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], **f64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * B * args.steps / e2e_s
+    e2e_bad = int((h_status != 0).sum().item())
+
+    if rank == 0:
+        peaks, peaks_kind = measured_peaks()
+        ric_avg_ms = ric_ms / max(ric_n, 1)
+        achieved = B * N * BYTES_PER_STEP / (ric_avg_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("k_lqr12_dram_bytes_per_launch_65536")
+            except Exception:
+                traffic = None
+        fp64_peak = fp64_peak_tflops()
+        fp64_ach = B * N * FLOPS_PER_STEP_SYM / (ric_avg_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, B),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "noc_lqr_solve_from_x0 (host x0 -> nominal rollout -> linearise -> sweep -> host K0,P0,cost,status)",
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_kind,
+                         "kernel": "k_lqr12", "kernel_ms": ric_avg_ms, "kernel_launches": ric_n,
+                         "algorithmic_bytes_per_launch": B * N * BYTES_PER_STEP,
+                         "kernel_share_of_step": ric_ms / ms if world == 1 else None,
+                         "fp64": {"achieved_tflops_symmetric_count": fp64_ach, "peak_tflops_measured_dfma": fp64_peak,
+                                  "frac": (fp64_ach / fp64_peak) if fp64_peak else None}},
+            "clocks": clocks,
+            "status_not_ok": n_bad + e2e_bad,
+        }
+        if world > 1:
+            line["best_rollout"] = {"index": best.get("idx"), "cost": best.get("cost")}
+        if world == 1 and not args.no_cpu:
+            v, cores, secs = cpu_leg(args.cpu_sample)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"{args.cpu_sample} of the {B} instances, one pass, {secs:.2f} s wall on {cores} threads "
+                          "(in-repo C oracle, OpenMP over instances; the reference has no solver source)"}
+        print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="noc", choices=["noc", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU (default: config 2)")
+    ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--ref-sample", type=int, default=8192)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "noc":
+        log("note: fewer than 3 warm-up steps requested")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "noc" and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), __file__] + sys.argv[1:]
+        return subprocess.call(cmd)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_noc(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -94,6 +94,21 @@ int noc_set_stream(noc_ctx* ctx, void* cuda_stream);
 int noc_synchronize(noc_ctx* ctx);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t noc_launch_count(const noc_ctx* ctx);
+/* Per-kernel device time, measured with CUDA events on the launching stream (bench.py's roofline).
+ * Off by default; while on, every launch of the library is bracketed by an event pair. */
+typedef enum {
+  NOC_KERNEL_SETUP = 0,      /* weight packing */
+  NOC_KERNEL_ROLLOUT = 1,    /* open-loop nominal rollout */
+  NOC_KERNEL_LINEARIZE = 2,  /* time-parallel A_k,B_k */
+  NOC_KERNEL_RICCATI = 3,    /* backward sweep (LQR, DARE and the SLQ backward pass) */
+  NOC_KERNEL_FORWARD = 4,    /* SLQ closed-loop rollouts + line search */
+  NOC_KERNEL_ARGMIN = 5,
+  NOC_KERNEL_COUNT = 6
+} noc_kernel_id;
+int noc_profile_enable(noc_ctx* ctx, int on);
+/* total device milliseconds and launch count of one kernel id since the last reset (synchronises) */
+int noc_profile_read(noc_ctx* ctx, int kernel_id, double* total_ms, int64_t* launches);
+int noc_profile_reset(noc_ctx* ctx);
 /* fill defaults: tol 1e-8, max_iter 50, n_alpha 11, armijo 1e-4, dt 0.02, layout A_THEN_B */
 void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N);
 

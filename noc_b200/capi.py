@@ -28,8 +28,9 @@ EXPORTS = [
     "noc_create", "noc_destroy", "noc_last_error", "noc_version", "noc_set_stream", "noc_synchronize",
     "noc_launch_count", "noc_problem_defaults", "noc_lqr_solve_batch", "noc_linearize_batch",
     "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_dare_solve_batch", "noc_slq_solve_batch",
-    "noc_argmin_cost",
+    "noc_argmin_cost", "noc_profile_enable", "noc_profile_read", "noc_profile_reset",
 ]
+KERNEL_SETUP, KERNEL_ROLLOUT, KERNEL_LINEARIZE, KERNEL_RICCATI, KERNEL_FORWARD, KERNEL_ARGMIN = range(6)
 
 
 class Problem(C.Structure):
@@ -79,6 +80,9 @@ def load_library():
     lib.noc_dare_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp]
     lib.noc_slq_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_argmin_cost.argtypes = [vp, dp, i64, C.POINTER(i64), C.POINTER(C.c_double)]
+    lib.noc_profile_enable.argtypes = [vp, C.c_int]
+    lib.noc_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
+    lib.noc_profile_reset.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -147,6 +151,18 @@ class Solver:
     @property
     def launch_count(self):
         return int(self._lib.noc_launch_count(self._h))
+
+    def profile_enable(self, on=True):
+        self._check(self._lib.noc_profile_enable(self._h, int(on)))
+
+    def profile_reset(self):
+        self._check(self._lib.noc_profile_reset(self._h))
+
+    def profile_read(self, kernel_id):
+        """(total device ms, launches) of one kernel id since the last reset."""
+        ms, cnt = C.c_double(), C.c_int64()
+        self._check(self._lib.noc_profile_read(self._h, kernel_id, C.byref(ms), C.byref(cnt)))
+        return ms.value, cnt.value
 
     @staticmethod
     def version():

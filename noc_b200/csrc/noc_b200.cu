@@ -37,6 +37,13 @@ struct noc_ctx {
   int sm_count = 0;
   std::vector<DevBuf> in_slots, out_slots, scratch;
   std::vector<PendingCopy> pending;
+  // per-kernel device timing (noc_profile_*): event pairs recorded around launches of each kernel id
+  bool profiling = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+  std::vector<std::pair<int, size_t>> ev_used;  // (kernel id, pool index)
+  size_t ev_next = 0;
+  double prof_ms[NOC_KERNEL_COUNT] = {0};
+  int64_t prof_launches[NOC_KERNEL_COUNT] = {0};
 };
 
 namespace {
@@ -51,6 +58,31 @@ using namespace noc;
       return (e_ == cudaErrorMemoryAllocation) ? NOC_ERR_OOM : NOC_ERR_CUDA;                     \
     }                                                                                            \
   } while (0)
+
+// RAII bracket around one kernel launch: counts it and, when profiling, records an event pair on the
+// launching stream (noc_profile_read turns the pairs into per-kernel device time).
+struct LaunchScope {
+  noc_ctx* c;
+  cudaEvent_t stop = nullptr;
+  LaunchScope(noc_ctx* ctx, int kid) : c(ctx) {
+    c->launches++;
+    c->prof_launches[kid]++;
+    if (!c->profiling) return;
+    if (c->ev_next == c->ev_pool.size()) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      c->ev_pool.push_back({a, b});
+    }
+    auto& pr = c->ev_pool[c->ev_next];
+    c->ev_used.push_back({kid, c->ev_next});
+    c->ev_next++;
+    cudaEventRecord(pr.first, c->stream);
+    stop = pr.second;
+  }
+  ~LaunchScope() {
+    if (stop) cudaEventRecord(stop, c->stream);
+  }
+};
 
 int fail(noc_ctx* ctx, int code, const std::string& msg) {
   if (ctx) ctx->err = msg;
@@ -158,8 +190,10 @@ int launch_lqr12(noc_ctx* ctx, const Lqr12Args& a) {
   }
   const long long per_cta = 2 * LQR12_WARPS;
   const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
-  kern<<<grid, LQR12_WARPS * 32, smem, ctx->stream>>>(a);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+    kern<<<grid, LQR12_WARPS * 32, smem, ctx->stream>>>(a);
+  }
   NOC_CUDA(ctx, cudaGetLastError());
   return NOC_OK;
 }
@@ -170,8 +204,10 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   void* w = nullptr;
   int rc = scratch(ctx, SCR_W, sizeof(double) * (16 * 16 + 144), &w);
   if (rc) return rc;
-  k_build_w<<<1, 256, 0, ctx->stream>>>(dQRQf, (double*)w, 12, 4);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_SETUP);
+    k_build_w<<<1, 256, 0, ctx->stream>>>(dQRQf, (double*)w, 12, 4);
+  }
   NOC_CUDA(ctx, cudaGetLastError());
   Lqr12Args a;
   a.AB = dAB; a.W = (const double*)w; a.Qf = (const double*)w + 256; a.x0 = dx0;
@@ -229,6 +265,7 @@ void noc_destroy(noc_ctx* ctx) {
   for (auto* v : {&ctx->in_slots, &ctx->out_slots, &ctx->scratch})
     for (auto& b : *v)
       if (b.p) cudaFree(b.p);
+  for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -248,6 +285,43 @@ int noc_synchronize(noc_ctx* ctx) {
 }
 
 int64_t noc_launch_count(const noc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int noc_profile_enable(noc_ctx* ctx, int on) {
+  if (!ctx) return NOC_ERR_BAD_ARG;
+  ctx->profiling = on != 0;
+  return NOC_OK;
+}
+
+static int profile_collect(noc_ctx* ctx) {
+  if (ctx->ev_used.empty()) return NOC_OK;
+  NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (auto& u : ctx->ev_used) {
+    float ms = 0.f;
+    NOC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev_pool[u.second].first, ctx->ev_pool[u.second].second));
+    ctx->prof_ms[u.first] += ms;
+  }
+  ctx->ev_used.clear();
+  ctx->ev_next = 0;
+  return NOC_OK;
+}
+
+int noc_profile_read(noc_ctx* ctx, int kernel_id, double* total_ms, int64_t* launches) {
+  if (!ctx) return NOC_ERR_BAD_ARG;
+  if (kernel_id < 0 || kernel_id >= NOC_KERNEL_COUNT) return fail(ctx, NOC_ERR_BAD_ARG, "unknown kernel id");
+  int rc = profile_collect(ctx);
+  if (rc) return rc;
+  if (total_ms) *total_ms = ctx->prof_ms[kernel_id];
+  if (launches) *launches = ctx->prof_launches[kernel_id];
+  return NOC_OK;
+}
+
+int noc_profile_reset(noc_ctx* ctx) {
+  if (!ctx) return NOC_ERR_BAD_ARG;
+  int rc = profile_collect(ctx);
+  if (rc) return rc;
+  for (int i = 0; i < NOC_KERNEL_COUNT; ++i) { ctx->prof_ms[i] = 0; ctx->prof_launches[i] = 0; }
+  return NOC_OK;
+}
 
 int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* AB, const double* QRQf,
                         int qr_per_instance, const double* x0dev, double* K, double* K0, double* P0, double* cost,
@@ -292,11 +366,13 @@ int noc_rollout_open_loop(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
   if ((rc = stage_in(ctx, 1, ubar, sizeof(double) * B * N * m, &du))) return rc;
   if ((rc = stage_out(ctx, 0, xbar, sizeof(double) * B * (N + 1) * n, &dx))) return rc;
   const unsigned grid = (unsigned)((batch + 127) / 128);
-  if (p->model == NOC_MODEL_QUAD12)
-    k_rollout_open_loop<0><<<grid, 128, 0, ctx->stream>>>((const double*)dx0, (const double*)du, (double*)dx, batch, p->N, p->dt);
-  else
-    k_rollout_open_loop<1><<<grid, 128, 0, ctx->stream>>>((const double*)dx0, (const double*)du, (double*)dx, batch, p->N, p->dt);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
+    if (p->model == NOC_MODEL_QUAD12)
+      k_rollout_open_loop<0><<<grid, 128, 0, ctx->stream>>>((const double*)dx0, (const double*)du, (double*)dx, batch, p->N, p->dt);
+    else
+      k_rollout_open_loop<1><<<grid, 128, 0, ctx->stream>>>((const double*)dx0, (const double*)du, (double*)dx, batch, p->N, p->dt);
+  }
   NOC_CUDA(ctx, cudaGetLastError());
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
@@ -317,11 +393,13 @@ int noc_linearize_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if ((rc = stage_out(ctx, 0, AB, sizeof(double) * B * N * rec, &dAB))) return rc;
   const long long total = (long long)batch * p->N;
   const unsigned grid = (unsigned)((total + 127) / 128);
-  if (p->model == NOC_MODEL_QUAD12)
-    k_linearize<0><<<grid, 128, 0, ctx->stream>>>((const double*)dx, (const double*)du, (double*)dAB, batch, p->N, p->dt, p->layout);
-  else
-    k_linearize<1><<<grid, 128, 0, ctx->stream>>>((const double*)dx, (const double*)du, (double*)dAB, batch, p->N, p->dt, p->layout);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+    if (p->model == NOC_MODEL_QUAD12)
+      k_linearize<0><<<grid, 128, 0, ctx->stream>>>((const double*)dx, (const double*)du, (double*)dAB, batch, p->N, p->dt, p->layout);
+    else
+      k_linearize<1><<<grid, 128, 0, ctx->stream>>>((const double*)dx, (const double*)du, (double*)dAB, batch, p->N, p->dt, p->layout);
+  }
   NOC_CUDA(ctx, cudaGetLastError());
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
@@ -362,12 +440,16 @@ int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
   for (size_t off = 0; off < B; off += chunk) {
     const long long cb = (long long)std::min(chunk, B - off);
     const double* x0c = (const double*)dx0 + off * n;
-    k_rollout_open_loop<0><<<(unsigned)((cb + 127) / 128), 128, 0, ctx->stream>>>(x0c, nullptr, (double*)dxbar, cb, p->N, p->dt);
-    ctx->launches++;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
+      k_rollout_open_loop<0><<<(unsigned)((cb + 127) / 128), 128, 0, ctx->stream>>>(x0c, nullptr, (double*)dxbar, cb, p->N, p->dt);
+    }
     NOC_CUDA(ctx, cudaGetLastError());
     const long long total = cb * p->N;
-    k_linearize<0><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout);
-    ctx->launches++;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+      k_linearize<0><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout);
+    }
     NOC_CUDA(ctx, cudaGetLastError());
     rc = lqr12_device(ctx, &q, cb, (const double*)dAB, (const double*)dQ, x0c,
                       dK ? (double*)dK + off * N * m * n : nullptr, dK0 ? (double*)dK0 + off * m * n : nullptr,
@@ -401,8 +483,10 @@ int noc_argmin_cost(noc_ctx* ctx, const double* cost, int64_t batch, int64_t* be
   if ((rc = stage_in(ctx, 0, cost, sizeof(double) * (size_t)batch, &dc))) return rc;
   void* s;
   if ((rc = scratch(ctx, SCR_ARGMIN, 16, &s))) return rc;
-  k_argmin_cost<<<1, 1024, 0, ctx->stream>>>((const double*)dc, batch, (long long*)s, (double*)s + 1);
-  ctx->launches++;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_ARGMIN);
+    k_argmin_cost<<<1, 1024, 0, ctx->stream>>>((const double*)dc, batch, (long long*)s, (double*)s + 1);
+  }
   NOC_CUDA(ctx, cudaGetLastError());
   long long hi;
   double hv;

@@ -468,6 +468,28 @@ void noc_oracle_lqr_from_x0_batch(int model, int N, double dt, int64_t batch, co
   }
 }
 
+/* synthetic A_k,B_k streams for a batch of initial states (hover-thrust nominal), OpenMP over instances */
+void noc_oracle_make_ab_batch(int model, int N, double dt, int64_t batch, const double* x0, int layout,
+                              double* AB, int threads) {
+  int n, m;
+  noc_oracle_model_dims(model, &n, &m);
+  const size_t rec = (size_t)n * n + (size_t)n * m;
+#pragma omp parallel num_threads(threads > 0 ? threads : noc_oracle_max_threads())
+  {
+    double* xbar = (double*)malloc((size_t)(N + 1) * n * sizeof(double));
+    double* ubar = (double*)malloc((size_t)N * m * sizeof(double));
+    double uh[MMAX];
+    noc_oracle_hover_input(model, uh);
+    for (int k = 0; k < N; ++k) memcpy(ubar + (size_t)k * m, uh, (size_t)m * sizeof(double));
+#pragma omp for schedule(static)
+    for (int64_t b = 0; b < batch; ++b) {
+      noc_oracle_rollout_open_loop(model, N, dt, x0 + (size_t)b * n, ubar, xbar);
+      noc_oracle_linearize_traj(model, N, dt, xbar, ubar, layout, AB + (size_t)b * N * rec);
+    }
+    free(xbar); free(ubar);
+  }
+}
+
 /* ---------------------------------------------------------------- DARE fixed point */
 int noc_oracle_dare(int n, int m, const double* A, const double* B, const double* Q, const double* R,
                     double tol, int max_iter, double* P, double* K) {

@@ -61,6 +61,10 @@ void noc_oracle_lqr_from_x0_batch(int model, int N, double dt, int64_t batch, co
                                   const double* QRQf, double* K0, double* P0, double* cost,
                                   int32_t* status, int threads);
 
+/* AB[B][N][rec] along the hover-thrust nominal from each x0[B][n] (bench / test input generator) */
+void noc_oracle_make_ab_batch(int model, int N, double dt, int64_t batch, const double* x0, int layout,
+                              double* AB, int threads);
+
 /* -- infinite horizon ------------------------------------------------------ */
 /* iterate the sweep step from P=Q until max|P'-P|/max|P'| < tol. returns iterations used (<= max_iter),
  * negative on Cholesky failure. */

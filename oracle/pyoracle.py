@@ -166,6 +166,15 @@ def lqr_from_x0_batch(model, N, dt, x0, QRQf, threads=0, want_P0=True):
     return dict(K0=K0, P0=P0, cost=cost, status=status)
 
 
+def make_ab_batch(model, N, dt, x0, layout=LAYOUT_A_THEN_B, threads=0):
+    n, m = dims(model)
+    x0 = _c(x0)
+    B = x0.shape[0]
+    AB = np.empty((B, N, n * n + n * m))
+    lib().noc_oracle_make_ab_batch(model, N, C.c_double(dt), C.c_int64(B), _p(x0), layout, _p(AB), threads)
+    return AB
+
+
 def dare(A, B, Q, R, tol=1e-12, max_iter=10000):
     A, B, Q, R = _c(A), _c(B), _c(Q), _c(R)
     n, m = B.shape
