@@ -12,6 +12,7 @@
 
 #include "pipeline_kernels.cuh"
 #include "riccati12.cuh"
+#include "slq_kernels.cuh"
 
 namespace {
 
@@ -145,19 +146,25 @@ int scratch(noc_ctx* ctx, int slot, size_t bytes, void** out) {
   return NOC_OK;
 }
 
-enum { SCR_W = 0, SCR_XBAR = 1, SCR_AB = 2, SCR_ARGMIN = 3 };
+enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
+       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U };
 
-// W = blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by Qf (n*n)
-__global__ void k_build_w(const double* __restrict__ qrqf, double* __restrict__ w, int n, int m) {
+// W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
+// Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
+// DESIGN.md §2.3); qf_off selects Qf (n*n+m*m) or, for the DARE iteration, Q itself (0).
+__global__ void k_build_w(const double* __restrict__ qrqf, double* __restrict__ w, int n, int m, int qf_off) {
   const int nm = n + m;
   for (int e = threadIdx.x; e < nm * nm; e += blockDim.x) {
     const int i = e / nm, j = e % nm;
     double v = 0.0;
-    if (i < n && j < n) v = qrqf[i * n + j];
-    else if (i >= n && j >= n) v = qrqf[n * n + (i - n) * m + (j - n)];
+    if (i < n && j < n) v = qrqf[min(i, j) * n + max(i, j)];
+    else if (i >= n && j >= n) v = qrqf[n * n + (max(i, j) - n) * m + (min(i, j) - n)];
     w[e] = v;
   }
-  for (int e = threadIdx.x; e < n * n; e += blockDim.x) w[nm * nm + e] = qrqf[n * n + m * m + e];
+  for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+    const int i = e / n, j = e % n;
+    w[nm * nm + e] = qrqf[qf_off + min(i, j) * n + max(i, j)];
+  }
 }
 
 int check_prob(noc_ctx* ctx, const noc_problem_t* p, int64_t batch) {
@@ -175,45 +182,64 @@ int check_prob(noc_ctx* ctx, const noc_problem_t* p, int64_t batch) {
   return NOC_OK;
 }
 
-constexpr int LQR12_WARPS = 4;
-constexpr int LQR12_MIN_CTAS = 5;
+bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
 
-template <int LAYOUT>
-int launch_lqr12(noc_ctx* ctx, const Lqr12Args& a) {
-  auto kern = k_lqr12<LAYOUT, LQR12_WARPS, LQR12_MIN_CTAS>;
-  const size_t smem = lqr12_smem_bytes(LQR12_WARPS);
-  static bool attr_set[2] = {false, false};
-  if (!attr_set[LAYOUT]) {
+// kernel configurations: 8 instances per warp; LQR/DARE 2 CTAs x 4 warps per SM,
+// SLQ backward pass 1 CTA x 7 warps (its per-instance shared-memory slice is larger)
+template <int MODE> struct RicCfg { static constexpr int warps = 4, min_ctas = 2; };
+template <> struct RicCfg<RIC_AFFINE> { static constexpr int warps = 7, min_ctas = 1; };
+
+template <int LAYOUT, int MODE>
+int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
+  constexpr int W = RicCfg<MODE>::warps;
+  auto kern = k_ric12<LAYOUT, MODE, W, RicCfg<MODE>::min_ctas>;
+  const size_t smem = ric12_smem_bytes<MODE>(W);
+  static bool attr_set = false;  // one flag per template instantiation
+  if (!attr_set) {
     NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set[LAYOUT] = true;
+    attr_set = true;
   }
-  const long long per_cta = 2 * LQR12_WARPS;
+  const long long per_cta = 8LL * W;
   const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
   {
     LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
-    kern<<<grid, LQR12_WARPS * 32, smem, ctx->stream>>>(a);
+    kern<<<grid, W * 32, smem, ctx->stream>>>(a);
   }
   NOC_CUDA(ctx, cudaGetLastError());
+  return NOC_OK;
+}
+
+template <int MODE>
+int launch_ric12_layout(noc_ctx* ctx, int layout, const Ric12Args& a) {
+  return layout == NOC_LAYOUT_A_THEN_B ? launch_ric12<0, MODE>(ctx, a) : launch_ric12<1, MODE>(ctx, a);
+}
+
+// packs the weights for the n=12 kernels into scratch: W[256] | Qf[144]
+int build_w12(noc_ctx* ctx, const double* dQRQf, bool dare, const double** W, const double** Qf) {
+  void* w = nullptr;
+  int rc = scratch(ctx, SCR_W, sizeof(double) * (16 * 16 + 144), &w);
+  if (rc) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_SETUP);
+    k_build_w<<<1, 256, 0, ctx->stream>>>(dQRQf, (double*)w, 12, 4, dare ? 0 : 12 * 12 + 4 * 4);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  *W = (const double*)w;
+  *Qf = (const double*)w + 256;
   return NOC_OK;
 }
 
 // device-pointer core of the n=12 sweep
 int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* dAB, const double* dQRQf,
                  const double* dx0, double* dK, double* dK0, double* dP0, double* dcost, int32_t* dstatus) {
-  void* w = nullptr;
-  int rc = scratch(ctx, SCR_W, sizeof(double) * (16 * 16 + 144), &w);
+  Ric12Args a{};
+  int rc = build_w12(ctx, dQRQf, false, &a.W, &a.Qf);
   if (rc) return rc;
-  {
-    LaunchScope ls(ctx, NOC_KERNEL_SETUP);
-    k_build_w<<<1, 256, 0, ctx->stream>>>(dQRQf, (double*)w, 12, 4);
-  }
-  NOC_CUDA(ctx, cudaGetLastError());
-  Lqr12Args a;
-  a.AB = dAB; a.W = (const double*)w; a.Qf = (const double*)w + 256; a.x0 = dx0;
+  a.AB = dAB; a.x0 = dx0;
   a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
   a.batch = batch; a.N = p->N;
-  return p->layout == NOC_LAYOUT_A_THEN_B ? launch_lqr12<0>(ctx, a) : launch_lqr12<1>(ctx, a);
+  return launch_ric12_layout<RIC_LQR>(ctx, p->layout, a);
 }
 
 }  // namespace
@@ -332,6 +358,7 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if (batch == 0) return NOC_OK;
   if (qr_per_instance) return fail(ctx, NOC_ERR_UNSUPPORTED, "per-instance Q/R/Qf not implemented yet");
   if (!(p->n == 12 && p->m == 4)) return fail(ctx, NOC_ERR_UNSUPPORTED, "only n=12, m=4 has a sweep kernel");
+  if (misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned (TMA bulk copies)");
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const int n = p->n, m = p->m, N = p->N;
   const size_t rec = (size_t)n * n + (size_t)n * m, B = (size_t)batch;
@@ -396,9 +423,9 @@ int noc_linearize_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   {
     LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
     if (p->model == NOC_MODEL_QUAD12)
-      k_linearize<0><<<grid, 128, 0, ctx->stream>>>((const double*)dx, (const double*)du, (double*)dAB, batch, p->N, p->dt, p->layout);
+      k_linearize<0><<<grid, 128, 0, ctx->stream>>>((const double*)dx, (const double*)du, (double*)dAB, batch, p->N, p->dt, p->layout, nullptr);
     else
-      k_linearize<1><<<grid, 128, 0, ctx->stream>>>((const double*)dx, (const double*)du, (double*)dAB, batch, p->N, p->dt, p->layout);
+      k_linearize<1><<<grid, 128, 0, ctx->stream>>>((const double*)dx, (const double*)du, (double*)dAB, batch, p->N, p->dt, p->layout, nullptr);
   }
   NOC_CUDA(ctx, cudaGetLastError());
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
@@ -448,7 +475,7 @@ int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
     const long long total = cb * p->N;
     {
       LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
-      k_linearize<0><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout);
+      k_linearize<0><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout, nullptr);
     }
     NOC_CUDA(ctx, cudaGetLastError());
     rc = lqr12_device(ctx, &q, cb, (const double*)dAB, (const double*)dQ, x0c,
@@ -460,18 +487,120 @@ int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
 
-int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*, const double*, double*,
-                         double*, int32_t*, int32_t*) {
+int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* AB, const double* QR,
+                         double* P, double* K, int32_t* iters, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
-  return fail(ctx, NOC_ERR_UNSUPPORTED, "noc_dare_solve_batch: not implemented yet");
+  if (!AB || !QR) return fail(ctx, NOC_ERR_BAD_ARG, "AB and QR are required");
+  if (p->max_iter < 1) return fail(ctx, NOC_ERR_BAD_ARG, "max_iter must be >= 1");
+  if (batch == 0) return NOC_OK;
+  if (!(p->n == 12 && p->m == 4)) return fail(ctx, NOC_ERR_UNSUPPORTED, "only n=12, m=4 has a DARE kernel");
+  if (misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned");
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t B = (size_t)batch, n = 12, m = 4;
+  const void *dAB, *dQ;
+  void *dP, *dK, *dit, *dst;
+  if ((rc = stage_in(ctx, 0, AB, sizeof(double) * B * 192, &dAB))) return rc;
+  if ((rc = stage_in(ctx, 1, QR, sizeof(double) * (n * n + m * m), &dQ))) return rc;
+  if ((rc = stage_out(ctx, 0, P, sizeof(double) * B * n * n, &dP))) return rc;
+  if ((rc = stage_out(ctx, 1, K, sizeof(double) * B * m * n, &dK))) return rc;
+  if ((rc = stage_out(ctx, 2, iters, sizeof(int32_t) * B, &dit))) return rc;
+  if ((rc = stage_out(ctx, 3, status, sizeof(int32_t) * B, &dst))) return rc;
+  Ric12Args a{};
+  if ((rc = build_w12(ctx, (const double*)dQ, true, &a.W, &a.Qf))) { ctx->pending.clear(); return rc; }
+  a.AB = (const double*)dAB; a.K = (double*)dK; a.P0 = (double*)dP; a.iters = (int32_t*)dit; a.status = (int32_t*)dst;
+  a.tol = p->tol; a.max_iter = p->max_iter; a.batch = batch; a.N = 1;
+  rc = launch_ric12_layout<RIC_DARE>(ctx, p->layout, a);
+  if (rc) { ctx->pending.clear(); return rc; }
+  return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
 
-int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*, const double*,
-                        const double*, double*, double*, double*, double*, int32_t*, int32_t*, int32_t*) {
+int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
+                        const double* QRQf, double* x, double* u, double* K, double* cost, int32_t* iters,
+                        int32_t* alpha_idx, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
-  return fail(ctx, NOC_ERR_UNSUPPORTED, "noc_slq_solve_batch: not implemented yet");
+  if (p->model != NOC_MODEL_QUAD12) return fail(ctx, NOC_ERR_UNSUPPORTED, "noc_slq_solve_batch: only NOC_MODEL_QUAD12 so far");
+  if (!x0 || !xgoal || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0, xgoal and QRQf are required");
+  if (p->max_iter < 1 || p->n_alpha < 1 || p->n_alpha > 32)
+    return fail(ctx, NOC_ERR_BAD_ARG, "need max_iter >= 1 and 1 <= n_alpha <= 32");
+  if (batch > 0x7fffffffLL) return fail(ctx, NOC_ERR_BAD_ARG, "batch too large for 32-bit work lists");
+  if (batch == 0) return NOC_OK;
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t B = (size_t)batch, n = 12, m = 4, N = p->N, rec = 192;
+  const void *dx0, *dxg, *dQ;
+  void *dx, *du, *dK, *dJ, *dit, *dai, *dst;
+  if ((rc = stage_in(ctx, 0, x0, sizeof(double) * B * n, &dx0))) return rc;
+  if ((rc = stage_in(ctx, 1, xgoal, sizeof(double) * B * n, &dxg))) return rc;
+  if ((rc = stage_in(ctx, 2, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
+  // outputs double as the solver's working state; the ones the caller does not want live in scratch
+  auto out_or_scratch = [&](int oslot, int sslot, void* host, size_t bytes, void** dev) -> int {
+    if (host) return stage_out(ctx, oslot, host, bytes, dev);
+    return scratch(ctx, sslot, bytes, dev);
+  };
+  if ((rc = out_or_scratch(0, SCR_X, x, sizeof(double) * B * (N + 1) * n, &dx))) return rc;
+  if ((rc = out_or_scratch(1, SCR_U, u, sizeof(double) * B * N * m, &du))) return rc;
+  if ((rc = out_or_scratch(2, SCR_K, K, sizeof(double) * B * N * m * n, &dK))) return rc;
+  if ((rc = out_or_scratch(3, SCR_J, cost, sizeof(double) * B, &dJ))) return rc;
+  if ((rc = out_or_scratch(4, SCR_ITERS, iters, sizeof(int32_t) * B, &dit))) return rc;
+  if ((rc = stage_out(ctx, 5, alpha_idx, sizeof(int32_t) * B * p->max_iter, &dai))) return rc;
+  if ((rc = out_or_scratch(6, SCR_STATUS, status, sizeof(int32_t) * B, &dst))) return rc;
+  void *dAB, *dkff, *ddV, *dmu, *dbst, *didx0, *didx1, *dcount;
+  if ((rc = scratch(ctx, SCR_AB, sizeof(double) * B * N * rec, &dAB))) return rc;
+  if ((rc = scratch(ctx, SCR_KFF, sizeof(double) * B * N * m, &dkff))) return rc;
+  if ((rc = scratch(ctx, SCR_DV, sizeof(double) * B * 2, &ddV))) return rc;
+  if ((rc = scratch(ctx, SCR_MU, sizeof(double) * B, &dmu))) return rc;
+  if ((rc = scratch(ctx, SCR_BSTATUS, sizeof(int32_t) * B, &dbst))) return rc;
+  if ((rc = scratch(ctx, SCR_IDX0, sizeof(int32_t) * B, &didx0))) return rc;
+  if ((rc = scratch(ctx, SCR_IDX1, sizeof(int32_t) * B, &didx1))) return rc;
+  if ((rc = scratch(ctx, SCR_COUNT, 64, &dcount))) return rc;
+  const size_t wbytes = sizeof(double) * (2 * n * n + m * m);
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
+    k_slq_init<0><<<(unsigned)((batch + 127) / 128), 128, wbytes, ctx->stream>>>(
+        (const double*)dx0, (const double*)dxg, (const double*)dQ, (double*)dx, (double*)du, (double*)dJ, (double*)dmu,
+        (int32_t*)dst, (int32_t*)dit, (int32_t*)dai, (int32_t*)didx0, batch, p->N, p->dt, p->reg0, p->max_iter);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  Ric12Args ra{};
+  if ((rc = build_w12(ctx, (const double*)dQ, false, &ra.W, &ra.Qf))) { ctx->pending.clear(); return rc; }
+  int count = (int)batch;
+  int32_t* cur = (int32_t*)didx0;
+  int32_t* nxt = (int32_t*)didx1;
+  for (int it = 0; it < p->max_iter && count > 0; ++it) {
+    {  // a1: time-parallel linearisation of the active instances
+      const long long total = (long long)count * p->N;
+      LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+      k_linearize<0><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
+          (const double*)dx, (const double*)du, (double*)dAB, count, p->N, p->dt, NOC_LAYOUT_A_THEN_B, cur);
+    }
+    NOC_CUDA(ctx, cudaGetLastError());
+    // a2+a3: affine backward pass (regularisation retries in-kernel)
+    ra.AB = (const double*)dAB; ra.idx = cur; ra.xbar = (const double*)dx; ra.ubar = (const double*)du;
+    ra.xgoal = (const double*)dxg; ra.K = (double*)dK; ra.kff = (double*)dkff; ra.dV = (double*)ddV;
+    ra.mu = (double*)dmu; ra.status = (int32_t*)dbst; ra.batch = count; ra.N = p->N;
+    if ((rc = launch_ric12<0, RIC_AFFINE>(ctx, ra))) { ctx->pending.clear(); return rc; }
+    // a4: candidate rollouts, line search, acceptance, convergence, next work list
+    NOC_CUDA(ctx, cudaMemsetAsync(dcount, 0, 4, ctx->stream));
+    SlqFwdArgs fa{};
+    fa.idx = cur; fa.next_idx = nxt; fa.next_count = (int32_t*)dcount; fa.xgoal = (const double*)dxg;
+    fa.qrqf = (const double*)dQ; fa.x = (double*)dx; fa.u = (double*)du; fa.K = (const double*)dK;
+    fa.kff = (const double*)dkff; fa.dV = (const double*)ddV; fa.J = (double*)dJ; fa.bstatus = (const int32_t*)dbst;
+    fa.status = (int32_t*)dst; fa.iters = (int32_t*)dit; fa.alpha_idx = (int32_t*)dai; fa.count = count; fa.N = p->N;
+    fa.iter = it; fa.max_iter = p->max_iter; fa.n_alpha = p->n_alpha; fa.dt = p->dt; fa.tol = p->tol;
+    fa.armijo = p->armijo;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+      k_slq_forward<0><<<(unsigned)((count + 3) / 4), 128, wbytes, ctx->stream>>>(fa);
+    }
+    NOC_CUDA(ctx, cudaGetLastError());
+    int32_t hc = 0;
+    NOC_CUDA(ctx, cudaMemcpyAsync(&hc, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    count = hc;
+    std::swap(cur, nxt);
+  }
+  return flush_out(ctx, false);
 }
 
 int noc_argmin_cost(noc_ctx* ctx, const double* cost, int64_t batch, int64_t* best_index, double* best_cost) {

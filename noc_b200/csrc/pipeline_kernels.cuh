@@ -36,19 +36,21 @@ __global__ void __launch_bounds__(128) k_rollout_open_loop(const double* __restr
   }
 }
 
-// One thread per (instance, k).  The record is zero-filled with 16-byte stores, then the ~70 structural
+// One thread per (work item, k); `batch` counts work items (= instances unless idx is given).  The record is zero-filled with 16-byte stores, then the ~70 structural
 // non-zeros are written.  L2 merges the partial sectors before they reach HBM (record = 1536 B, written
 // within one thread).  Layout 0: A then B; layout 1: rows of [A row | B row].
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_linearize(const double* __restrict__ xbar,
                                                    const double* __restrict__ ubar,  // may be null
                                                    double* __restrict__ AB, long long batch, int N, double dt,
-                                                   int layout) {
+                                                   int layout, const int32_t* __restrict__ idx) {
   constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, rec = n * n + n * m;
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= batch * N) return;
-  const long long b = t / N;
-  const int k = (int)(t - b * N);
+  const long long tw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tw >= batch * N) return;
+  const long long item = tw / N;
+  const int k = (int)(tw - item * N);
+  const long long b = idx ? (long long)idx[item] : item;   // SLQ: only the instances still iterating
+  const long long t = b * N + k;
   double x[n], u[m];
   const double* xs = xbar + ((size_t)b * (N + 1) + k) * n;
 #pragma unroll

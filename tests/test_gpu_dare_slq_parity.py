@@ -1,0 +1,137 @@
+"""Ring 2 for the infinite-horizon LQR (row a5) and SLQ / iLQR (rows a1-a4) paths: CUDA vs the CPU
+oracle through the C-ABI.  Bit-exact values; iteration counts, accepted step indices and statuses identical.
+Parity statement: "kernel vs in-repo oracle, oracle vs scipy" (parity unpinned — the reference has no source)."""
+import numpy as np
+import pytest
+
+from noc_b200 import problems as pb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from noc_b200 import capi
+    s = capi.Solver(0)
+    yield s
+    s.close()
+
+
+def _hover_AB(oracle, batch, rng, layout=0):
+    """LTI records: linearisation at hover with a random yaw and small random attitude per instance."""
+    recs = []
+    for _ in range(batch):
+        x = np.zeros(12)
+        x[6:8] = rng.uniform(-0.2, 0.2, 2)
+        x[8] = rng.uniform(-np.pi, np.pi)
+        A, B = oracle.linearize(0, x, pb.hover_input(), 0.02)
+        if layout == 0:
+            recs.append(np.concatenate([A.ravel(), B.ravel()]))
+        else:
+            recs.append(np.concatenate([A, B], axis=1).ravel())
+    return np.stack(recs)
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+def test_dare_bitexact_and_iteration_counts(oracle, solver, layout):
+    from noc_b200 import capi
+    rng = np.random.default_rng(11)
+    batch = 21
+    Q, R, _ = pb.default_weights()
+    AB = _hover_AB(oracle, batch, rng, layout)
+    qr = np.concatenate([Q.ravel(), R.ravel()])
+    prob = capi.problem(capi.MODEL_LTV_USER, 1, layout=layout, tol=1e-12, max_iter=10000)
+    P = np.empty((batch, 12, 12)); K = np.empty((batch, 4, 12))
+    iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    solver.dare_solve_batch(prob, batch, AB, qr, P, K, iters, status)
+    for b in range(batch):
+        if layout == 0:
+            A, B = AB[b, :144].reshape(12, 12), AB[b, 144:].reshape(12, 4)
+        else:
+            F = AB[b].reshape(12, 16); A, B = F[:, :12].copy(), F[:, 12:].copy()
+        Pr, Kr, it = oracle.dare(A, B, Q, R, tol=1e-12, max_iter=10000)
+        assert status[b] == 0 and iters[b] == it
+        assert np.array_equal(P[b], Pr) and np.array_equal(K[b], Kr)
+    assert 150 < iters.min() and iters.max() < 400   # 218 at exact hover
+
+
+def test_dare_max_iter_status(oracle, solver):
+    from noc_b200 import capi
+    rng = np.random.default_rng(12)
+    batch = 5
+    Q, R, _ = pb.default_weights()
+    AB = _hover_AB(oracle, batch, rng)
+    qr = np.concatenate([Q.ravel(), R.ravel()])
+    prob = capi.problem(capi.MODEL_LTV_USER, 1, tol=1e-12, max_iter=17)
+    P = np.empty((batch, 12, 12)); K = np.empty((batch, 4, 12))
+    iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    solver.dare_solve_batch(prob, batch, AB, qr, P, K, iters, status)
+    assert np.all(status == 2) and np.all(iters == 17)
+    for b in range(batch):
+        Pr, Kr, it = oracle.dare(AB[b, :144].reshape(12, 12), AB[b, 144:].reshape(12, 4), Q, R, tol=1e-12, max_iter=17)
+        assert it == 17 and np.array_equal(P[b], Pr) and np.array_equal(K[b], Kr)
+
+
+def _slq_compare(oracle, solver, batch, N, x0, xg, qr, **kw):
+    from noc_b200 import capi
+    prob = capi.problem(capi.MODEL_QUAD12, N, **kw)
+    x = np.empty((batch, N + 1, 12)); u = np.empty((batch, N, 4)); K = np.empty((batch, N, 4, 12))
+    cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    aidx = np.full((batch, prob.max_iter), -7, dtype=np.int32)
+    solver.slq_solve_batch(prob, batch, x0, xg, qr, x=x, u=u, K=K, cost=cost, iters=iters, alpha_idx=aidx, status=status)
+    opts = oracle.slq_opts(0, N, dt=prob.dt, tol=prob.tol, max_iter=prob.max_iter, n_alpha=prob.n_alpha,
+                           reg0=prob.reg0, armijo=prob.armijo)
+    ref = oracle.slq_batch(opts, x0, xg, qr, want_traj=True, want_K=True)
+    assert np.array_equal(status, ref["status"])
+    assert np.array_equal(iters, ref["iters"])          # iteration counts identical (north_star)
+    assert np.array_equal(aidx, ref["alpha_idx"])       # accepted line-search indices identical
+    assert np.array_equal(cost, ref["cost"])
+    assert np.array_equal(x, ref["x"]) and np.array_equal(u, ref["u"])
+    # K of the last backward pass of every instance
+    assert np.array_equal(K, ref["K"])
+    return dict(status=status, iters=iters, aidx=aidx, cost=cost)
+
+
+def test_slq_waypoints_bitexact(oracle, solver):
+    """Config-3 style: hover start, waypoint goals; every instance converges."""
+    batch, N = 40, 60
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.hover_state(batch); xg = pb.sample_goals(batch, seed=5)
+    out = _slq_compare(oracle, solver, batch, N, x0, xg, qr)
+    assert np.all(out["status"] == 0) and out["iters"].min() >= 2
+    assert len(set(out["iters"].tolist())) > 1           # instances leave the work list at different iterations
+
+
+def test_slq_backtracking_and_max_iter(oracle, solver):
+    """Aggressive starts force alpha < 1; a small max_iter leaves some instances at MAX_ITER."""
+    batch, N = 24, 40
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    rng = np.random.default_rng(9)
+    x0 = pb.sample_x0(batch, seed=123)
+    x0[:, 6:8] = rng.uniform(-0.9, 0.9, (batch, 2))
+    xg = pb.sample_goals(batch, seed=6) * 2.0
+    out = _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=6)
+    assert np.any(out["aidx"] > 0)
+    assert np.any(out["status"] == 2)
+
+
+def test_slq_regularisation_retry(oracle, solver):
+    """A negative R makes Quu indefinite at mu = 0: the backward pass must raise mu exactly like the oracle."""
+    batch, N = 10, 20
+    Q, R, Qf = pb.default_weights()
+    R = R.copy(); R[1, 1] = -0.5
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(batch, seed=31); xg = pb.sample_goals(batch, seed=7)
+    _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=5)
+
+
+def test_slq_optional_outputs(oracle, solver):
+    from noc_b200 import capi
+    batch, N = 12, 30
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.hover_state(batch); xg = pb.sample_goals(batch, seed=8)
+    prob = capi.problem(capi.MODEL_QUAD12, N)
+    cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32)
+    solver.slq_solve_batch(prob, batch, x0, xg, qr, cost=cost, iters=iters)
+    ref = oracle.slq_batch(oracle.slq_opts(0, N), x0, xg, qr, want_traj=False)
+    assert np.array_equal(cost, ref["cost"]) and np.array_equal(iters, ref["iters"])

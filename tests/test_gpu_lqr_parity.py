@@ -176,3 +176,20 @@ def test_large_batch_properties(solver):
     sel = np.arange(0, batch, 331)
     ref = oracle.lqr_from_x0_batch(0, N, 0.02, x0[sel], qr)
     assert np.array_equal(K0[sel], ref["K0"]) and np.array_equal(P0[sel], ref["P0"]) and np.array_equal(cost[sel], ref["cost"])
+
+
+def test_lqr_tail_and_big_mixed(oracle, solver):
+    """Batch sizes that are not a multiple of the 8 instances a warp owns / the 32 a CTA owns."""
+    from noc_b200 import capi
+    Q, R, Qf = pb.default_weights()
+    qr = pb.pack_qrqf(Q, R, Qf)
+    for batch, N in [(7, 9), (9, 3), (33, 17), (257, 11)]:
+        x0 = pb.sample_x0(batch, seed=77 + batch)
+        AB = oracle.make_ab_batch(0, N, 0.02, x0)
+        ref = oracle.lqr_batch(12, 4, N, AB, qr, x0dev=x0)
+        K = np.empty((batch, N, 4, 12)); P0 = np.empty((batch, 12, 12)); cost = np.empty(batch)
+        status = np.full(batch, -1, dtype=np.int32)
+        solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, N), batch, AB, qr, x0dev=x0, K=K, P0=P0, cost=cost,
+                               status=status)
+        assert np.all(status == 0)
+        assert np.array_equal(K, ref["K"]) and np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
