@@ -307,7 +307,7 @@ def run_noc(args):
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("k_lqr12_dram_bytes_per_launch_65536")
+                traffic = json.load(open(tp)).get("k_ric12_dram_bytes_per_launch_65536")
             except Exception:
                 traffic = None
         fp64_peak = fp64_peak_tflops()
@@ -322,7 +322,7 @@ def run_noc(args):
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_kind,
-                         "kernel": "k_lqr12", "kernel_ms": ric_avg_ms, "kernel_launches": ric_n,
+                         "kernel": "k_ric12<LAYOUT_A_THEN_B,RIC_LQR>", "kernel_ms": ric_avg_ms, "kernel_launches": ric_n,
                          "algorithmic_bytes_per_launch": B * N * BYTES_PER_STEP,
                          "kernel_share_of_step": ric_ms / ms if world == 1 else None,
                          "fp64": {"achieved_tflops_symmetric_count": fp64_ach, "peak_tflops_measured_dfma": fp64_peak,
