@@ -161,6 +161,11 @@ int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, 
 int noc_argmin_cost(noc_ctx* ctx, const double* cost, int64_t batch, int64_t* best_index,
                     double* best_cost);
 
+/* ---- diagnostics -----------------------------------------------------------------------------------
+ * The pivots' reciprocals inside the sweep use a branch-free correctly-rounded sequence valid on
+ * (1e-280, 1e280); this runs it next to the IEEE division on n values so tests can compare the bits. */
+int noc_selftest_rcp(noc_ctx* ctx, const double* x, double* y_fast, double* y_ieee, int64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,7 @@ EXPORTS = [
     "noc_create", "noc_destroy", "noc_last_error", "noc_version", "noc_set_stream", "noc_synchronize",
     "noc_launch_count", "noc_problem_defaults", "noc_lqr_solve_batch", "noc_linearize_batch",
     "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_dare_solve_batch", "noc_slq_solve_batch",
-    "noc_argmin_cost", "noc_profile_enable", "noc_profile_read", "noc_profile_reset",
+    "noc_argmin_cost", "noc_profile_enable", "noc_profile_read", "noc_profile_reset", "noc_selftest_rcp",
 ]
 KERNEL_SETUP, KERNEL_ROLLOUT, KERNEL_LINEARIZE, KERNEL_RICCATI, KERNEL_FORWARD, KERNEL_ARGMIN = range(6)
 
@@ -83,6 +83,7 @@ def load_library():
     lib.noc_profile_enable.argtypes = [vp, C.c_int]
     lib.noc_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     lib.noc_profile_reset.argtypes = [vp]
+    lib.noc_selftest_rcp.argtypes = [vp, dp, dp, dp, i64]
     _lib = lib
     return lib
 
@@ -194,6 +195,12 @@ class Solver:
         self._check(self._lib.noc_slq_solve_batch(self._h, C.byref(prob), batch, _ptr(x0), _ptr(xgoal), _ptr(QRQf),
                                                   _ptr(x), _ptr(u), _ptr(K), _ptr(cost), _ptr(iters),
                                                   _ptr(alpha_idx), _ptr(status)))
+
+    def selftest_rcp(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        fast, ieee = np.empty_like(x), np.empty_like(x)
+        self._check(self._lib.noc_selftest_rcp(self._h, _ptr(x), _ptr(fast), _ptr(ieee), x.size))
+        return fast, ieee
 
     def argmin_cost(self, cost, batch):
         idx, val = C.c_int64(), C.c_double()

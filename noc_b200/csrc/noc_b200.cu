@@ -167,6 +167,15 @@ __global__ void k_build_w(const double* __restrict__ qrqf, double* __restrict__ 
   }
 }
 
+// diagnostics: the branch-free reciprocal of the factorisation next to the IEEE division
+__global__ void k_selftest_rcp(const double* __restrict__ x, double* __restrict__ fast, double* __restrict__ ieee,
+                               long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fast[i] = rcp_rn_normal(x[i]);
+  ieee[i] = 1.0 / x[i];
+}
+
 int check_prob(noc_ctx* ctx, const noc_problem_t* p, int64_t batch) {
   if (!ctx) return NOC_ERR_BAD_ARG;
   if (!p) return fail(ctx, NOC_ERR_BAD_ARG, "problem descriptor is NULL");
@@ -600,6 +609,24 @@ int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
     count = hc;
     std::swap(cur, nxt);
   }
+  return flush_out(ctx, false);
+}
+
+int noc_selftest_rcp(noc_ctx* ctx, const double* x, double* y_fast, double* y_ieee, int64_t n) {
+  if (!ctx) return NOC_ERR_BAD_ARG;
+  if (!x || !y_fast || !y_ieee || n < 1) return fail(ctx, NOC_ERR_BAD_ARG, "x, outputs and n>=1 required");
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const void* dx;
+  void *df, *di;
+  int rc;
+  if ((rc = stage_in(ctx, 0, x, sizeof(double) * (size_t)n, &dx))) return rc;
+  if ((rc = stage_out(ctx, 0, y_fast, sizeof(double) * (size_t)n, &df))) return rc;
+  if ((rc = stage_out(ctx, 1, y_ieee, sizeof(double) * (size_t)n, &di))) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_SETUP);
+    k_selftest_rcp<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const double*)dx, (double*)df, (double*)di, n);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
   return flush_out(ctx, false);
 }
 

@@ -281,7 +281,7 @@ typedef struct {
   double Hxx[NMAX * NMAX];  /* upper triangle valid */
   double Hux[MMAX * NMAX];
   double Huu[MMAX * MMAX];  /* lower triangle valid */
-  double L[MMAX * MMAX], d[MMAX];
+  double L[MMAX * MMAX], D[MMAX], d[MMAX]; /* unit-lower L, pivots D, d = 1/D */
 } step_ws;
 
 /* G = P F ; Hxx (upper) = Q + A^T G_A ; Hux = B^T G_A ; Huu (lower) = R + B^T G_B (+mu on diag) */
@@ -314,38 +314,47 @@ static void form_H(step_ws* w, const double* P, const double* F, const double* Q
     }
 }
 
-/* lower Cholesky, left-looking, with reciprocal diagonal. returns 0 or NOT_PD */
+/* Square-root-free Cholesky Huu = L D L^T (L unit lower, D diagonal), left-looking:
+ *   w_l = L[j][l] * D[l]                       (plain products, l < j)
+ *   D[j] = Huu[j][j] - sum_l L[j][l] w_l       (fma chain, ascending l); r[j] = 1 / D[j]
+ *   L[i][j] = (Huu[i][j] - sum_l L[i][l] w_l) * r[j]
+ * Huu is positive definite iff every pivot D[j] > 0; pivots outside (1e-280, 1e280) also count as failure,
+ * so that 1/D[j] never leaves the normal range.  returns 0 or NOT_PD */
+#define PIVOT_MIN 1e-280
+#define PIVOT_MAX 1e280
 static int chol_lower(step_ws* w) {
   const int m = w->m;
+  double v[MMAX];
   for (int j = 0; j < m; ++j) {
+    for (int l = 0; l < j; ++l) v[l] = w->L[j * m + l] * w->D[l];
     double s = w->Huu[j * m + j];
-    for (int l = 0; l < j; ++l) s = fma(-w->L[j * m + l], w->L[j * m + l], s);
-    if (!(s > 0.0)) return NOC_O_NOT_PD;
-    const double ljj = sqrt(s);
-    w->L[j * m + j] = ljj;
-    w->d[j] = 1.0 / ljj;
+    for (int l = 0; l < j; ++l) s = fma(-w->L[j * m + l], v[l], s);
+    if (!(s > PIVOT_MIN) || !(s < PIVOT_MAX)) return NOC_O_NOT_PD;
+    w->D[j] = s;
+    w->d[j] = 1.0 / s;
+    w->L[j * m + j] = 1.0;
     for (int i = j + 1; i < m; ++i) {
       double t = w->Huu[i * m + j];
-      for (int l = 0; l < j; ++l) t = fma(-w->L[i * m + l], w->L[j * m + l], t);
+      for (int l = 0; l < j; ++l) t = fma(-w->L[i * m + l], v[l], t);
       w->L[i * m + j] = t * w->d[j];
     }
   }
   return NOC_O_OK;
 }
 
-/* out = -(L L^T)^{-1} rhs for one right-hand side of length m (stride between elements = rs) */
+/* out = -(L D L^T)^{-1} rhs for one right-hand side of length m (stride between elements = rs) */
 static void chol_solve_neg(const step_ws* w, const double* rhs, int rs, double* out, int os) {
   const int m = w->m;
   double y[MMAX], z[MMAX];
   for (int i = 0; i < m; ++i) {
     double s = rhs[i * rs];
     for (int l = 0; l < i; ++l) s = fma(-w->L[i * m + l], y[l], s);
-    y[i] = s * w->d[i];
+    y[i] = s;
   }
   for (int i = m - 1; i >= 0; --i) {
-    double s = y[i];
+    double s = y[i] * w->d[i];
     for (int l = i + 1; l < m; ++l) s = fma(-w->L[l * m + i], z[l], s);
-    z[i] = s * w->d[i];
+    z[i] = s;
   }
   for (int i = 0; i < m; ++i) out[i * os] = -z[i];
 }
