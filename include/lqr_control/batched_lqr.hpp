@@ -1,0 +1,218 @@
+// lqr_control/batched_lqr.hpp — C++ host-side facade over the C-ABI of libnoc_b200.so.
+//
+// This is the "controller class" slot of the reference package: KahnShi/NOC's lqr_control scaffolds a library
+// built from src/${PROJECT_NAME}/lqr_control.cpp with headers in include/${PROJECT_NAME}/
+// (lqr_control/CMakeLists.txt:124-126, :175-179) and defines nothing in it, so the names
+// below are this repo's.  Header-only C++17; the only thing that crosses the library boundary is the C-ABI in
+// noc_b200.h (exceptions are thrown on this side of it).
+//
+// Pointers follow the C-ABI rule: host or device, detected by the library; outputs may be nullptr.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "noc_b200.h"
+
+namespace lqr_control {
+
+class NocError : public std::runtime_error {
+ public:
+  NocError(int code, const std::string& what) : std::runtime_error(what), code_(code) {}
+  int code() const { return code_; }
+
+ private:
+  int code_;
+};
+
+// One GPU context (noc_ctx).  Single caller; create one per device / per host thread.
+class Context {
+ public:
+  explicit Context(int device = 0) : device_(device) {
+    const int rc = noc_create(&h_, device);
+    if (rc != NOC_OK)
+      throw NocError(rc, "noc_create(device " + std::to_string(device) +
+                             ") failed: no usable sm_100 CUDA device (libnoc_b200 has no CPU fallback)");
+  }
+  ~Context() { noc_destroy(h_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  noc_ctx* handle() const { return h_; }
+  int device() const { return device_; }
+  void check(int rc) const {
+    if (rc != NOC_OK) throw NocError(rc, std::string("libnoc_b200: ") + noc_last_error(h_));
+  }
+  void setStream(void* cuda_stream) { check(noc_set_stream(h_, cuda_stream)); }
+  void synchronize() { check(noc_synchronize(h_)); }
+  int64_t launchCount() const { return noc_launch_count(h_); }
+
+ private:
+  noc_ctx* h_ = nullptr;
+  int device_;
+};
+
+// Q (n*n), R (m*m), Qf (n*n) packed the way the C-ABI wants them
+struct Weights {
+  int n = 12, m = 4;
+  std::vector<double> qrqf;
+  Weights() = default;
+  Weights(int n_, int m_, const double* Q, const double* R, const double* Qf) : n(n_), m(m_) {
+    qrqf.insert(qrqf.end(), Q, Q + n * n);
+    qrqf.insert(qrqf.end(), R, R + m * m);
+    qrqf.insert(qrqf.end(), Qf, Qf + n * n);
+  }
+  // the benchmark weights: Q = diag(10,10,10,1,1,1,5,5,5,.1,.1,.1) per vehicle, R = 0.1 I, Qf = 10 Q
+  static Weights quadrotorDefault(int vehicles = 1) {
+    const double q[12] = {10, 10, 10, 1, 1, 1, 5, 5, 5, 0.1, 0.1, 0.1};
+    const int n = 12 * vehicles, m = 4 * vehicles;
+    std::vector<double> Q((size_t)n * n, 0.0), R((size_t)m * m, 0.0), Qf((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) { Q[(size_t)i * n + i] = q[i % 12]; Qf[(size_t)i * n + i] = 10.0 * q[i % 12]; }
+    for (int i = 0; i < m; ++i) R[(size_t)i * m + i] = 0.1;
+    return Weights(n, m, Q.data(), R.data(), Qf.data());
+  }
+};
+
+// Finite-horizon batched LQR.
+class BatchedLqr {
+ public:
+  BatchedLqr(std::shared_ptr<Context> ctx, int horizon, int model = NOC_MODEL_QUAD12) : ctx_(std::move(ctx)) {
+    noc_problem_defaults(&prob_, model, horizon);
+    weights_ = Weights::quadrotorDefault(model == NOC_MODEL_DUAL24 ? 2 : 1);
+  }
+  noc_problem_t& problem() { return prob_; }
+  void setWeights(const Weights& w) { weights_ = w; }
+  void setTimeStep(double dt) { prob_.dt = dt; }
+
+  // caller-supplied A_k,B_k records: AB[batch][N][n*n+n*m] in problem().layout
+  void solve(int64_t batch, const double* AB, const double* x0dev, double* K, double* K0, double* P0, double* cost,
+             int32_t* status) {
+    noc_problem_t p = prob_;
+    p.model = NOC_MODEL_LTV_USER;
+    ctx_->check(noc_lqr_solve_batch(ctx_->handle(), &p, batch, AB, weights_.qrqf.data(), 0, x0dev, K, K0, P0, cost,
+                                    status));
+  }
+  // built-in model: x0 -> hover-thrust nominal -> linearise -> sweep
+  void solveFromInitialStates(int64_t batch, const double* x0, double* K, double* K0, double* P0, double* cost,
+                              int32_t* status) {
+    ctx_->check(noc_lqr_solve_from_x0(ctx_->handle(), &prob_, batch, x0, weights_.qrqf.data(), K, K0, P0, cost,
+                                      status));
+  }
+  void linearize(int64_t batch, const double* xbar, const double* ubar, double* AB) {
+    ctx_->check(noc_linearize_batch(ctx_->handle(), &prob_, batch, xbar, ubar, AB));
+  }
+  void rolloutOpenLoop(int64_t batch, const double* x0, const double* ubar, double* xbar) {
+    ctx_->check(noc_rollout_open_loop(ctx_->handle(), &prob_, batch, x0, ubar, xbar));
+  }
+  // "pick the best rollout" on this GPU
+  std::pair<int64_t, double> argminCost(const double* cost, int64_t batch) {
+    int64_t idx = -1;
+    double val = 0.0;
+    ctx_->check(noc_argmin_cost(ctx_->handle(), cost, batch, &idx, &val));
+    return {idx, val};
+  }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+  noc_problem_t prob_{};
+  Weights weights_;
+};
+
+// Infinite-horizon LQR by fixed-point iteration (row a5): one LTI record [A|B] per instance.
+class InfiniteHorizonLqr {
+ public:
+  explicit InfiniteHorizonLqr(std::shared_ptr<Context> ctx, double tol = 1e-12, int max_iter = 10000)
+      : ctx_(std::move(ctx)) {
+    noc_problem_defaults(&prob_, NOC_MODEL_LTV_USER, 1);
+    prob_.tol = tol;
+    prob_.max_iter = max_iter;
+    weights_ = Weights::quadrotorDefault();
+  }
+  noc_problem_t& problem() { return prob_; }
+  void setWeights(const Weights& w) { weights_ = w; }
+  void solve(int64_t batch, const double* AB, double* P, double* K, int32_t* iters, int32_t* status) {
+    // the C-ABI takes Q | R only; they are the leading part of the packed weights
+    ctx_->check(noc_dare_solve_batch(ctx_->handle(), &prob_, batch, AB, weights_.qrqf.data(), P, K, iters, status));
+  }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+  noc_problem_t prob_{};
+  Weights weights_;
+};
+
+// SLQ / iLQR with the built-in nonlinear models (rows a1-a4).
+class BatchedSlq {
+ public:
+  BatchedSlq(std::shared_ptr<Context> ctx, int horizon, int model = NOC_MODEL_QUAD12) : ctx_(std::move(ctx)) {
+    noc_problem_defaults(&prob_, model, horizon);
+    weights_ = Weights::quadrotorDefault(model == NOC_MODEL_DUAL24 ? 2 : 1);
+  }
+  noc_problem_t& problem() { return prob_; }
+  void setWeights(const Weights& w) { weights_ = w; }
+  void solve(int64_t batch, const double* x0, const double* xgoal, double* x, double* u, double* K, double* cost,
+             int32_t* iters, int32_t* alpha_idx, int32_t* status) {
+    ctx_->check(noc_slq_solve_batch(ctx_->handle(), &prob_, batch, x0, xgoal, weights_.qrqf.data(), x, u, K, cost,
+                                    iters, alpha_idx, status));
+  }
+
+ private:
+  std::shared_ptr<Context> ctx_;
+  noc_problem_t prob_{};
+  Weights weights_;
+};
+
+// contiguous slice [begin, end) of `batch` owned by shard g of G
+inline std::pair<int64_t, int64_t> shardSlice(int64_t batch, int g, int G) {
+  const int64_t base = batch / G, rem = batch % G;
+  const int64_t begin = g * base + std::min<int64_t>(g, rem);
+  return {begin, begin + base + (g < rem ? 1 : 0)};
+}
+
+// One host process driving several GPUs of a box: the batch is cut into contiguous slices, one host thread and
+// one Context per device, no data-path collective (instances are independent).  HOST pointers only; every
+// device writes its slice of the output arrays, so the "gather" is the host arrays themselves.
+class ShardedBatchedLqr {
+ public:
+  ShardedBatchedLqr(const std::vector<int>& devices, int horizon, int model = NOC_MODEL_QUAD12) {
+    for (int d : devices) shards_.emplace_back(std::make_shared<Context>(d), horizon, model);
+  }
+  size_t shards() const { return shards_.size(); }
+  void setWeights(const Weights& w) { for (auto& s : shards_) s.setWeights(w); }
+  // returns (index, cost) of the best instance over all shards
+  std::pair<int64_t, double> solveFromInitialStates(int64_t batch, const double* x0, double* K0, double* P0,
+                                                    double* cost, int32_t* status, int n = 12, int m = 4) {
+    const int G = (int)shards_.size();
+    std::vector<std::thread> th;
+    std::vector<std::string> err(G);
+    for (int g = 0; g < G; ++g)
+      th.emplace_back([&, g] {
+        const auto sl = shardSlice(batch, g, G);
+        const int64_t cnt = sl.second - sl.first, o = sl.first;
+        if (cnt == 0) return;
+        try {
+          shards_[g].solveFromInitialStates(cnt, x0 + o * n, nullptr, K0 ? K0 + o * m * n : nullptr,
+                                            P0 ? P0 + o * n * n : nullptr, cost ? cost + o : nullptr,
+                                            status ? status + o : nullptr);
+        } catch (const std::exception& e) { err[g] = e.what(); }
+      });
+    for (auto& t : th) t.join();
+    for (auto& e : err)
+      if (!e.empty()) throw NocError(NOC_ERR_CUDA, e);
+    int64_t best = -1;
+    double bv = 0.0;
+    if (cost)
+      for (int64_t i = 0; i < batch; ++i)
+        if (cost[i] == cost[i] && (best < 0 || cost[i] < bv)) { best = i; bv = cost[i]; }
+    return {best, bv};
+  }
+
+ private:
+  std::vector<BatchedLqr> shards_;
+};
+
+}  // namespace lqr_control

@@ -1,0 +1,112 @@
+// C++ host-side test of the lqr_control facade (include/lqr_control/batched_lqr.hpp) against the CPU oracle.
+// Built and run by tests/test_cpp_facade.py.  Exit codes: 0 = all checks passed, 3 = no usable GPU (the facade
+// must fail loudly: there is no CPU fallback), 1 = mismatch.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "lqr_control/batched_lqr.hpp"
+extern "C" {
+#include "../../oracle/noc_oracle.h"
+}
+
+using namespace lqr_control;
+
+static unsigned long long rng_state = 0x4E4F43ULL;
+static double urand(double lo, double hi) {
+  rng_state = rng_state * 6364136223846793005ULL + 1442695040888963407ULL;
+  return lo + (hi - lo) * ((rng_state >> 11) * (1.0 / 9007199254740992.0));
+}
+static std::vector<double> sample_x0(int64_t B) {
+  std::vector<double> x((size_t)B * 12);
+  for (int64_t b = 0; b < B; ++b) {
+    double* p = &x[(size_t)b * 12];
+    for (int i = 0; i < 3; ++i) p[i] = urand(-2, 2);
+    for (int i = 3; i < 6; ++i) p[i] = urand(-1, 1);
+    p[6] = urand(-0.3, 0.3); p[7] = urand(-0.3, 0.3); p[8] = urand(-3.14, 3.14);
+    for (int i = 9; i < 12; ++i) p[i] = urand(-0.2, 0.2);
+  }
+  return x;
+}
+static bool same(const std::vector<double>& a, const std::vector<double>& b) {
+  return a.size() == b.size() && std::memcmp(a.data(), b.data(), a.size() * sizeof(double)) == 0;
+}
+#define CHECK(c)                                                   \
+  do {                                                             \
+    if (!(c)) { std::printf("CHECK FAILED line %d: %s\n", __LINE__, #c); return 1; } \
+  } while (0)
+
+int main() {
+  std::shared_ptr<Context> ctx;
+  try {
+    ctx = std::make_shared<Context>(0);
+  } catch (const NocError& e) {
+    std::printf("NO DEVICE: %s (code %d)\n", e.what(), e.code());
+    return 3;
+  }
+  const Weights w = Weights::quadrotorDefault();
+
+  {  // finite-horizon LQR from initial states, single context and two shards
+    const int64_t B = 45;
+    const int N = 30;
+    auto x0 = sample_x0(B);
+    std::vector<double> K0(B * 48), P0(B * 144), cost(B), rK0(B * 48), rP0(B * 144), rcost(B);
+    std::vector<int32_t> st(B, -1), rst(B, -1);
+    BatchedLqr lqr(ctx, N);
+    lqr.solveFromInitialStates(B, x0.data(), nullptr, K0.data(), P0.data(), cost.data(), st.data());
+    noc_oracle_lqr_from_x0_batch(NOC_O_MODEL_QUAD12, N, 0.02, B, x0.data(), w.qrqf.data(), rK0.data(), rP0.data(),
+                                 rcost.data(), rst.data(), 0);
+    CHECK(same(K0, rK0) && same(P0, rP0) && same(cost, rcost) && st == rst);
+    auto best = lqr.argminCost(cost.data(), B);
+    int64_t rb = 0;
+    for (int64_t i = 1; i < B; ++i) if (rcost[i] < rcost[rb]) rb = i;
+    CHECK(best.first == rb && best.second == rcost[rb]);
+
+    ShardedBatchedLqr sh({0, 0, 0}, N);   // three shards (contexts) on one GPU: exercises the slicing
+    std::vector<double> sK0(B * 48), sP0(B * 144), scost(B);
+    std::vector<int32_t> sst(B, -1);
+    auto sbest = sh.solveFromInitialStates(B, x0.data(), sK0.data(), sP0.data(), scost.data(), sst.data());
+    CHECK(same(sK0, rK0) && same(sP0, rP0) && same(scost, rcost) && sst == rst);
+    CHECK(sbest.first == rb && sbest.second == rcost[rb]);
+    auto s0 = shardSlice(10, 0, 3), s1 = shardSlice(10, 1, 3), s2 = shardSlice(10, 2, 3);
+    CHECK(s0.first == 0 && s0.second == 4 && s1.first == 4 && s1.second == 7 && s2.first == 7 && s2.second == 10);
+  }
+  {  // infinite-horizon LQR at hover
+    double x[12] = {0}, u[4], A[144], Bm[48], P[144], K[48], rP[144], rK[48];
+    noc_oracle_hover_input(NOC_O_MODEL_QUAD12, u);
+    noc_oracle_linearize(NOC_O_MODEL_QUAD12, x, u, 0.02, A, Bm);
+    std::vector<double> rec(192);
+    std::memcpy(rec.data(), A, sizeof(A));
+    std::memcpy(rec.data() + 144, Bm, sizeof(Bm));
+    int32_t it = 0, st = -1;
+    InfiniteHorizonLqr dare(ctx);
+    dare.solve(1, rec.data(), P, K, &it, &st);
+    const int rit = noc_oracle_dare(12, 4, A, Bm, w.qrqf.data(), w.qrqf.data() + 144, 1e-12, 10000, rP, rK);
+    CHECK(st == 0 && it == rit && std::memcmp(P, rP, sizeof(P)) == 0 && std::memcmp(K, rK, sizeof(K)) == 0);
+    std::printf("hover DARE: %d iterations\n", it);
+  }
+  {  // SLQ to waypoints
+    const int64_t B = 6;
+    const int N = 40;
+    std::vector<double> x0(B * 12, 0.0), xg(B * 12, 0.0);
+    for (int64_t b = 0; b < B; ++b) { xg[b * 12 + 0] = urand(-2, 2); xg[b * 12 + 1] = urand(-2, 2); xg[b * 12 + 2] = urand(-2, 2); }
+    std::vector<double> x(B * (N + 1) * 12), u(B * N * 4), cost(B), rx(x.size()), ru(u.size()), rcost(B);
+    std::vector<int32_t> iters(B), st(B), aidx(B * 50), riters(B), rst(B), raidx(B * 50);
+    BatchedSlq slq(ctx, N);
+    slq.solve(B, x0.data(), xg.data(), x.data(), u.data(), nullptr, cost.data(), iters.data(), aidx.data(), st.data());
+    noc_oracle_slq_opts o{NOC_O_MODEL_QUAD12, N, 50, 11, 0.02, 1e-8, 0.0, 1e-4};
+    noc_oracle_slq_batch(&o, B, x0.data(), xg.data(), w.qrqf.data(), rx.data(), ru.data(), nullptr, rcost.data(),
+                         riters.data(), raidx.data(), rst.data(), 0);
+    CHECK(same(x, rx) && same(u, ru) && same(cost, rcost) && iters == riters && st == rst && aidx == raidx);
+  }
+  {  // errors surface as exceptions with the library's message
+    BatchedLqr lqr(ctx, 10);
+    bool threw = false;
+    try { lqr.solveFromInitialStates(4, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr); }
+    catch (const NocError& e) { threw = e.code() == NOC_ERR_BAD_ARG; }
+    CHECK(threw);
+  }
+  std::printf("FACADE OK\n");
+  return 0;
+}
