@@ -8,10 +8,12 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "pipeline_kernels.cuh"
 #include "riccati12.cuh"
+#include "riccati24.cuh"
 #include "slq_kernels.cuh"
 
 namespace {
@@ -224,6 +226,56 @@ int launch_ric12_layout(noc_ctx* ctx, int layout, const Ric12Args& a) {
   return layout == NOC_LAYOUT_A_THEN_B ? launch_ric12<0, MODE>(ctx, a) : launch_ric12<1, MODE>(ctx, a);
 }
 
+template <int MODE> struct Ric24Cfg { static constexpr int warps = 8; };
+template <> struct Ric24Cfg<RIC_AFFINE> { static constexpr int warps = 7; };
+
+template <int LAYOUT, int MODE>
+int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
+  constexpr int W = Ric24Cfg<MODE>::warps;
+  auto kern = k_ric24<LAYOUT, MODE, W>;
+  const size_t smem = ric24_smem_bytes<MODE>(W);
+  static bool attr_set = false;
+  if (!attr_set) {
+    NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    attr_set = true;
+  }
+  const long long per_cta = 2LL * W;
+  const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+    kern<<<grid, W * 32, smem, ctx->stream>>>(a);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  return NOC_OK;
+}
+
+// packs the weights for the n=24 kernels into scratch: W[1024] | Qf[576]
+int build_w24(noc_ctx* ctx, const double* dQRQf, const double** W, const double** Qf) {
+  void* w = nullptr;
+  int rc = scratch(ctx, SCR_W, sizeof(double) * (32 * 32 + 576), &w);
+  if (rc) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_SETUP);
+    k_build_w<<<1, 256, 0, ctx->stream>>>(dQRQf, (double*)w, 24, 8, 24 * 24 + 8 * 8);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  *W = (const double*)w;
+  *Qf = (const double*)w + 1024;
+  return NOC_OK;
+}
+
+int lqr24_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* dAB, const double* dQRQf,
+                 const double* dx0, double* dK, double* dK0, double* dP0, double* dcost, int32_t* dstatus) {
+  Ric24Args a{};
+  int rc = build_w24(ctx, dQRQf, &a.W, &a.Qf);
+  if (rc) return rc;
+  a.AB = dAB; a.x0 = dx0;
+  a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
+  a.batch = batch; a.N = p->N;
+  return p->layout == NOC_LAYOUT_A_THEN_B ? launch_ric24<0, RIC_LQR>(ctx, a) : launch_ric24<1, RIC_LQR>(ctx, a);
+}
+
 // packs the weights for the n=12 kernels into scratch: W[256] | Qf[144]
 int build_w12(noc_ctx* ctx, const double* dQRQf, bool dare, const double** W, const double** Qf) {
   void* w = nullptr;
@@ -249,6 +301,145 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
   a.batch = batch; a.N = p->N;
   return launch_ric12_layout<RIC_LQR>(ctx, p->layout, a);
+}
+
+template <int MODEL>
+int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* QRQf,
+                 double* K, double* K0, double* P0, double* cost, int32_t* status) {
+  int rc;
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t B = (size_t)batch, n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, N = p->N, rec = n * n + n * m;
+  const void *dx0, *dQ;
+  void *dK, *dK0, *dP0, *dcost, *dstatus;
+  if ((rc = stage_in(ctx, 0, x0, sizeof(double) * B * n, &dx0))) return rc;
+  if ((rc = stage_in(ctx, 1, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
+  if ((rc = stage_out(ctx, 0, K, sizeof(double) * B * N * m * n, &dK))) return rc;
+  if ((rc = stage_out(ctx, 1, K0, sizeof(double) * B * m * n, &dK0))) return rc;
+  if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
+  if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
+  if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
+  // chunk so that the A_k,B_k scratch stays within a share of the free HBM
+  size_t free_b = 0, total_b = 0;
+  NOC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  size_t have = 0;
+  if (ctx->scratch.size() > SCR_AB) have = ctx->scratch[SCR_AB].cap;
+  if (ctx->scratch.size() > SCR_XBAR) have += ctx->scratch[SCR_XBAR].cap;
+  const size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
+  const size_t per_inst = sizeof(double) * (N * rec + (N + 1) * n);
+  size_t chunk = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
+  if (chunk < B) chunk = std::max<size_t>(8, chunk & ~size_t(7));
+  void *dxbar, *dAB;
+  if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * chunk * (N + 1) * n, &dxbar))) return rc;
+  if ((rc = scratch(ctx, SCR_AB, sizeof(double) * chunk * N * rec, &dAB))) return rc;
+  noc_problem_t q = *p;
+  q.layout = NOC_LAYOUT_ROWS_AB;  // internal stream: one contiguous [A|B] row per F row
+  for (size_t off = 0; off < B; off += chunk) {
+    const long long cb = (long long)std::min(chunk, B - off);
+    const double* x0c = (const double*)dx0 + off * n;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
+      k_rollout_open_loop<MODEL><<<(unsigned)((cb + 127) / 128), 128, 0, ctx->stream>>>(x0c, nullptr, (double*)dxbar, cb, p->N, p->dt);
+    }
+    NOC_CUDA(ctx, cudaGetLastError());
+    const long long total = cb * p->N;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+      k_linearize<MODEL><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout, nullptr);
+    }
+    NOC_CUDA(ctx, cudaGetLastError());
+    rc = (MODEL == 0 ? lqr12_device : lqr24_device)(ctx, &q, cb, (const double*)dAB, (const double*)dQ, x0c,
+                      dK ? (double*)dK + off * N * m * n : nullptr, dK0 ? (double*)dK0 + off * m * n : nullptr,
+                      dP0 ? (double*)dP0 + off * n * n : nullptr, dcost ? (double*)dcost + off : nullptr,
+                      dstatus ? (int32_t*)dstatus + off : nullptr);
+    if (rc) { ctx->pending.clear(); return rc; }
+  }
+  return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
+}
+
+template <int MODEL>
+int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
+             const double* QRQf, double* x, double* u, double* K, double* cost, int32_t* iters, int32_t* alpha_idx,
+             int32_t* status) {
+  int rc;
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t B = (size_t)batch, n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, N = p->N, rec = n * n + n * m;
+  const void *dx0, *dxg, *dQ;
+  void *dx, *du, *dK, *dJ, *dit, *dai, *dst;
+  if ((rc = stage_in(ctx, 0, x0, sizeof(double) * B * n, &dx0))) return rc;
+  if ((rc = stage_in(ctx, 1, xgoal, sizeof(double) * B * n, &dxg))) return rc;
+  if ((rc = stage_in(ctx, 2, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
+  // outputs double as the solver's working state; the ones the caller does not want live in scratch
+  auto out_or_scratch = [&](int oslot, int sslot, void* host, size_t bytes, void** dev) -> int {
+    if (host) return stage_out(ctx, oslot, host, bytes, dev);
+    return scratch(ctx, sslot, bytes, dev);
+  };
+  if ((rc = out_or_scratch(0, SCR_X, x, sizeof(double) * B * (N + 1) * n, &dx))) return rc;
+  if ((rc = out_or_scratch(1, SCR_U, u, sizeof(double) * B * N * m, &du))) return rc;
+  if ((rc = out_or_scratch(2, SCR_K, K, sizeof(double) * B * N * m * n, &dK))) return rc;
+  if ((rc = out_or_scratch(3, SCR_J, cost, sizeof(double) * B, &dJ))) return rc;
+  if ((rc = out_or_scratch(4, SCR_ITERS, iters, sizeof(int32_t) * B, &dit))) return rc;
+  if ((rc = stage_out(ctx, 5, alpha_idx, sizeof(int32_t) * B * p->max_iter, &dai))) return rc;
+  if ((rc = out_or_scratch(6, SCR_STATUS, status, sizeof(int32_t) * B, &dst))) return rc;
+  void *dAB, *dkff, *ddV, *dmu, *dbst, *didx0, *didx1, *dcount;
+  if ((rc = scratch(ctx, SCR_AB, sizeof(double) * B * N * rec, &dAB))) return rc;
+  if ((rc = scratch(ctx, SCR_KFF, sizeof(double) * B * N * m, &dkff))) return rc;
+  if ((rc = scratch(ctx, SCR_DV, sizeof(double) * B * 2, &ddV))) return rc;
+  if ((rc = scratch(ctx, SCR_MU, sizeof(double) * B, &dmu))) return rc;
+  if ((rc = scratch(ctx, SCR_BSTATUS, sizeof(int32_t) * B, &dbst))) return rc;
+  if ((rc = scratch(ctx, SCR_IDX0, sizeof(int32_t) * B, &didx0))) return rc;
+  if ((rc = scratch(ctx, SCR_IDX1, sizeof(int32_t) * B, &didx1))) return rc;
+  if ((rc = scratch(ctx, SCR_COUNT, 64, &dcount))) return rc;
+  const size_t wbytes = sizeof(double) * (2 * n * n + m * m);
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
+    k_slq_init<MODEL><<<(unsigned)((batch + 127) / 128), 128, wbytes, ctx->stream>>>(
+        (const double*)dx0, (const double*)dxg, (const double*)dQ, (double*)dx, (double*)du, (double*)dJ, (double*)dmu,
+        (int32_t*)dst, (int32_t*)dit, (int32_t*)dai, (int32_t*)didx0, batch, p->N, p->dt, p->reg0, p->max_iter);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  typename std::conditional<MODEL == 0, Ric12Args, Ric24Args>::type ra{};
+  if (MODEL == 0) rc = build_w12(ctx, (const double*)dQ, false, &ra.W, &ra.Qf);
+  else rc = build_w24(ctx, (const double*)dQ, &ra.W, &ra.Qf);
+  if (rc) { ctx->pending.clear(); return rc; }
+  int count = (int)batch;
+  int32_t* cur = (int32_t*)didx0;
+  int32_t* nxt = (int32_t*)didx1;
+  for (int it = 0; it < p->max_iter && count > 0; ++it) {
+    {  // a1: time-parallel linearisation of the active instances
+      const long long total = (long long)count * p->N;
+      LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+      k_linearize<MODEL><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
+          (const double*)dx, (const double*)du, (double*)dAB, count, p->N, p->dt, NOC_LAYOUT_A_THEN_B, cur);
+    }
+    NOC_CUDA(ctx, cudaGetLastError());
+    // a2+a3: affine backward pass (regularisation retries in-kernel)
+    ra.AB = (const double*)dAB; ra.idx = cur; ra.xbar = (const double*)dx; ra.ubar = (const double*)du;
+    ra.xgoal = (const double*)dxg; ra.K = (double*)dK; ra.kff = (double*)dkff; ra.dV = (double*)ddV;
+    ra.mu = (double*)dmu; ra.status = (int32_t*)dbst; ra.batch = count; ra.N = p->N;
+    if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_AFFINE>(ctx, ra);
+    else rc = launch_ric24<0, RIC_AFFINE>(ctx, ra);
+    if (rc) { ctx->pending.clear(); return rc; }
+    // a4: candidate rollouts, line search, acceptance, convergence, next work list
+    NOC_CUDA(ctx, cudaMemsetAsync(dcount, 0, 4, ctx->stream));
+    SlqFwdArgs fa{};
+    fa.idx = cur; fa.next_idx = nxt; fa.next_count = (int32_t*)dcount; fa.xgoal = (const double*)dxg;
+    fa.qrqf = (const double*)dQ; fa.x = (double*)dx; fa.u = (double*)du; fa.K = (const double*)dK;
+    fa.kff = (const double*)dkff; fa.dV = (const double*)ddV; fa.J = (double*)dJ; fa.bstatus = (const int32_t*)dbst;
+    fa.status = (int32_t*)dst; fa.iters = (int32_t*)dit; fa.alpha_idx = (int32_t*)dai; fa.count = count; fa.N = p->N;
+    fa.iter = it; fa.max_iter = p->max_iter; fa.n_alpha = p->n_alpha; fa.dt = p->dt; fa.tol = p->tol;
+    fa.armijo = p->armijo;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+      k_slq_forward<MODEL><<<(unsigned)((count + 3) / 4), 128, wbytes, ctx->stream>>>(fa);
+    }
+    NOC_CUDA(ctx, cudaGetLastError());
+    int32_t hc = 0;
+    NOC_CUDA(ctx, cudaMemcpyAsync(&hc, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    count = hc;
+    std::swap(cur, nxt);
+  }
+  return flush_out(ctx, false);
 }
 
 }  // namespace
@@ -366,7 +557,9 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if (!AB || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "AB and QRQf are required");
   if (batch == 0) return NOC_OK;
   if (qr_per_instance) return fail(ctx, NOC_ERR_UNSUPPORTED, "per-instance Q/R/Qf not implemented yet");
-  if (!(p->n == 12 && p->m == 4)) return fail(ctx, NOC_ERR_UNSUPPORTED, "only n=12, m=4 has a sweep kernel");
+  const bool n24 = (p->n == 24 && p->m == 8);
+  if (!(p->n == 12 && p->m == 4) && !n24)
+    return fail(ctx, NOC_ERR_UNSUPPORTED, "sweep kernels exist for (n,m) = (12,4) and (24,8)");
   if (misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned (TMA bulk copies)");
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const int n = p->n, m = p->m, N = p->N;
@@ -381,8 +574,8 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
   if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
   if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
-  rc = lqr12_device(ctx, p, batch, (const double*)dAB, (const double*)dQ, (const double*)dx0, (double*)dK,
-                    (double*)dK0, (double*)dP0, (double*)dcost, (int32_t*)dstatus);
+  rc = (n24 ? lqr24_device : lqr12_device)(ctx, p, batch, (const double*)dAB, (const double*)dQ, (const double*)dx0,
+                                           (double*)dK, (double*)dK0, (double*)dP0, (double*)dcost, (int32_t*)dstatus);
   if (rc) { ctx->pending.clear(); return rc; }
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
@@ -444,56 +637,11 @@ int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
                           double* K, double* K0, double* P0, double* cost, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
-  if (p->model != NOC_MODEL_QUAD12) return fail(ctx, NOC_ERR_UNSUPPORTED, "from_x0 pipeline: only NOC_MODEL_QUAD12 so far");
+  if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "from_x0 pipeline needs a built-in model");
   if (!x0 || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0 and QRQf are required");
   if (batch == 0) return NOC_OK;
-  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t B = (size_t)batch, n = 12, m = 4, N = p->N, rec = 192;
-  const void *dx0, *dQ;
-  void *dK, *dK0, *dP0, *dcost, *dstatus;
-  if ((rc = stage_in(ctx, 0, x0, sizeof(double) * B * n, &dx0))) return rc;
-  if ((rc = stage_in(ctx, 1, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
-  if ((rc = stage_out(ctx, 0, K, sizeof(double) * B * N * m * n, &dK))) return rc;
-  if ((rc = stage_out(ctx, 1, K0, sizeof(double) * B * m * n, &dK0))) return rc;
-  if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
-  if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
-  if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
-  // chunk so that the A_k,B_k scratch stays within a share of the free HBM
-  size_t free_b = 0, total_b = 0;
-  NOC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
-  size_t have = 0;
-  if (ctx->scratch.size() > SCR_AB) have = ctx->scratch[SCR_AB].cap;
-  if (ctx->scratch.size() > SCR_XBAR) have += ctx->scratch[SCR_XBAR].cap;
-  const size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
-  const size_t per_inst = sizeof(double) * (N * rec + (N + 1) * n);
-  size_t chunk = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
-  if (chunk < B) chunk = std::max<size_t>(8, chunk & ~size_t(7));
-  void *dxbar, *dAB;
-  if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * chunk * (N + 1) * n, &dxbar))) return rc;
-  if ((rc = scratch(ctx, SCR_AB, sizeof(double) * chunk * N * rec, &dAB))) return rc;
-  noc_problem_t q = *p;
-  q.layout = NOC_LAYOUT_ROWS_AB;  // internal stream: one contiguous [A|B] row per F row
-  for (size_t off = 0; off < B; off += chunk) {
-    const long long cb = (long long)std::min(chunk, B - off);
-    const double* x0c = (const double*)dx0 + off * n;
-    {
-      LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
-      k_rollout_open_loop<0><<<(unsigned)((cb + 127) / 128), 128, 0, ctx->stream>>>(x0c, nullptr, (double*)dxbar, cb, p->N, p->dt);
-    }
-    NOC_CUDA(ctx, cudaGetLastError());
-    const long long total = cb * p->N;
-    {
-      LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
-      k_linearize<0><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout, nullptr);
-    }
-    NOC_CUDA(ctx, cudaGetLastError());
-    rc = lqr12_device(ctx, &q, cb, (const double*)dAB, (const double*)dQ, x0c,
-                      dK ? (double*)dK + off * N * m * n : nullptr, dK0 ? (double*)dK0 + off * m * n : nullptr,
-                      dP0 ? (double*)dP0 + off * n * n : nullptr, dcost ? (double*)dcost + off : nullptr,
-                      dstatus ? (int32_t*)dstatus + off : nullptr);
-    if (rc) { ctx->pending.clear(); return rc; }
-  }
-  return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
+  return p->model == NOC_MODEL_QUAD12 ? from_x0_impl<0>(ctx, p, batch, x0, QRQf, K, K0, P0, cost, status)
+                                      : from_x0_impl<1>(ctx, p, batch, x0, QRQf, K, K0, P0, cost, status);
 }
 
 int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* AB, const double* QR,
@@ -529,87 +677,15 @@ int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
                         int32_t* alpha_idx, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
-  if (p->model != NOC_MODEL_QUAD12) return fail(ctx, NOC_ERR_UNSUPPORTED, "noc_slq_solve_batch: only NOC_MODEL_QUAD12 so far");
+  if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "SLQ needs a built-in nonlinear model");
   if (!x0 || !xgoal || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0, xgoal and QRQf are required");
   if (p->max_iter < 1 || p->n_alpha < 1 || p->n_alpha > 32)
     return fail(ctx, NOC_ERR_BAD_ARG, "need max_iter >= 1 and 1 <= n_alpha <= 32");
   if (batch > 0x7fffffffLL) return fail(ctx, NOC_ERR_BAD_ARG, "batch too large for 32-bit work lists");
   if (batch == 0) return NOC_OK;
-  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t B = (size_t)batch, n = 12, m = 4, N = p->N, rec = 192;
-  const void *dx0, *dxg, *dQ;
-  void *dx, *du, *dK, *dJ, *dit, *dai, *dst;
-  if ((rc = stage_in(ctx, 0, x0, sizeof(double) * B * n, &dx0))) return rc;
-  if ((rc = stage_in(ctx, 1, xgoal, sizeof(double) * B * n, &dxg))) return rc;
-  if ((rc = stage_in(ctx, 2, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
-  // outputs double as the solver's working state; the ones the caller does not want live in scratch
-  auto out_or_scratch = [&](int oslot, int sslot, void* host, size_t bytes, void** dev) -> int {
-    if (host) return stage_out(ctx, oslot, host, bytes, dev);
-    return scratch(ctx, sslot, bytes, dev);
-  };
-  if ((rc = out_or_scratch(0, SCR_X, x, sizeof(double) * B * (N + 1) * n, &dx))) return rc;
-  if ((rc = out_or_scratch(1, SCR_U, u, sizeof(double) * B * N * m, &du))) return rc;
-  if ((rc = out_or_scratch(2, SCR_K, K, sizeof(double) * B * N * m * n, &dK))) return rc;
-  if ((rc = out_or_scratch(3, SCR_J, cost, sizeof(double) * B, &dJ))) return rc;
-  if ((rc = out_or_scratch(4, SCR_ITERS, iters, sizeof(int32_t) * B, &dit))) return rc;
-  if ((rc = stage_out(ctx, 5, alpha_idx, sizeof(int32_t) * B * p->max_iter, &dai))) return rc;
-  if ((rc = out_or_scratch(6, SCR_STATUS, status, sizeof(int32_t) * B, &dst))) return rc;
-  void *dAB, *dkff, *ddV, *dmu, *dbst, *didx0, *didx1, *dcount;
-  if ((rc = scratch(ctx, SCR_AB, sizeof(double) * B * N * rec, &dAB))) return rc;
-  if ((rc = scratch(ctx, SCR_KFF, sizeof(double) * B * N * m, &dkff))) return rc;
-  if ((rc = scratch(ctx, SCR_DV, sizeof(double) * B * 2, &ddV))) return rc;
-  if ((rc = scratch(ctx, SCR_MU, sizeof(double) * B, &dmu))) return rc;
-  if ((rc = scratch(ctx, SCR_BSTATUS, sizeof(int32_t) * B, &dbst))) return rc;
-  if ((rc = scratch(ctx, SCR_IDX0, sizeof(int32_t) * B, &didx0))) return rc;
-  if ((rc = scratch(ctx, SCR_IDX1, sizeof(int32_t) * B, &didx1))) return rc;
-  if ((rc = scratch(ctx, SCR_COUNT, 64, &dcount))) return rc;
-  const size_t wbytes = sizeof(double) * (2 * n * n + m * m);
-  {
-    LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
-    k_slq_init<0><<<(unsigned)((batch + 127) / 128), 128, wbytes, ctx->stream>>>(
-        (const double*)dx0, (const double*)dxg, (const double*)dQ, (double*)dx, (double*)du, (double*)dJ, (double*)dmu,
-        (int32_t*)dst, (int32_t*)dit, (int32_t*)dai, (int32_t*)didx0, batch, p->N, p->dt, p->reg0, p->max_iter);
-  }
-  NOC_CUDA(ctx, cudaGetLastError());
-  Ric12Args ra{};
-  if ((rc = build_w12(ctx, (const double*)dQ, false, &ra.W, &ra.Qf))) { ctx->pending.clear(); return rc; }
-  int count = (int)batch;
-  int32_t* cur = (int32_t*)didx0;
-  int32_t* nxt = (int32_t*)didx1;
-  for (int it = 0; it < p->max_iter && count > 0; ++it) {
-    {  // a1: time-parallel linearisation of the active instances
-      const long long total = (long long)count * p->N;
-      LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
-      k_linearize<0><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
-          (const double*)dx, (const double*)du, (double*)dAB, count, p->N, p->dt, NOC_LAYOUT_A_THEN_B, cur);
-    }
-    NOC_CUDA(ctx, cudaGetLastError());
-    // a2+a3: affine backward pass (regularisation retries in-kernel)
-    ra.AB = (const double*)dAB; ra.idx = cur; ra.xbar = (const double*)dx; ra.ubar = (const double*)du;
-    ra.xgoal = (const double*)dxg; ra.K = (double*)dK; ra.kff = (double*)dkff; ra.dV = (double*)ddV;
-    ra.mu = (double*)dmu; ra.status = (int32_t*)dbst; ra.batch = count; ra.N = p->N;
-    if ((rc = launch_ric12<0, RIC_AFFINE>(ctx, ra))) { ctx->pending.clear(); return rc; }
-    // a4: candidate rollouts, line search, acceptance, convergence, next work list
-    NOC_CUDA(ctx, cudaMemsetAsync(dcount, 0, 4, ctx->stream));
-    SlqFwdArgs fa{};
-    fa.idx = cur; fa.next_idx = nxt; fa.next_count = (int32_t*)dcount; fa.xgoal = (const double*)dxg;
-    fa.qrqf = (const double*)dQ; fa.x = (double*)dx; fa.u = (double*)du; fa.K = (const double*)dK;
-    fa.kff = (const double*)dkff; fa.dV = (const double*)ddV; fa.J = (double*)dJ; fa.bstatus = (const int32_t*)dbst;
-    fa.status = (int32_t*)dst; fa.iters = (int32_t*)dit; fa.alpha_idx = (int32_t*)dai; fa.count = count; fa.N = p->N;
-    fa.iter = it; fa.max_iter = p->max_iter; fa.n_alpha = p->n_alpha; fa.dt = p->dt; fa.tol = p->tol;
-    fa.armijo = p->armijo;
-    {
-      LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-      k_slq_forward<0><<<(unsigned)((count + 3) / 4), 128, wbytes, ctx->stream>>>(fa);
-    }
-    NOC_CUDA(ctx, cudaGetLastError());
-    int32_t hc = 0;
-    NOC_CUDA(ctx, cudaMemcpyAsync(&hc, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    count = hc;
-    std::swap(cur, nxt);
-  }
-  return flush_out(ctx, false);
+  return p->model == NOC_MODEL_QUAD12
+             ? slq_impl<0>(ctx, p, batch, x0, xgoal, QRQf, x, u, K, cost, iters, alpha_idx, status)
+             : slq_impl<1>(ctx, p, batch, x0, xgoal, QRQf, x, u, K, cost, iters, alpha_idx, status);
 }
 
 int noc_selftest_rcp(noc_ctx* ctx, const double* x, double* y_fast, double* y_ieee, int64_t n) {

@@ -1,0 +1,97 @@
+"""n=24 / m=8 (spring-coupled dual UAV, BASELINE.json configs[4]): CUDA vs the CPU oracle through the C-ABI,
+bit-exact, for the LTV sweep, the from-x0 pipeline and SLQ (iteration counts and step indices identical)."""
+import numpy as np
+import pytest
+
+from noc_b200 import problems as pb
+
+pytestmark = pytest.mark.gpu
+M = pb.MODEL_DUAL24
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from noc_b200 import capi
+    s = capi.Solver(0)
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("batch,N", [(1, 1), (3, 7), (34, 40)])
+def test_lqr24_sweep_bitexact(oracle, solver, layout, batch, N):
+    from noc_b200 import capi
+    Q, R, Qf = pb.default_weights(M)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(batch, seed=300 + batch, model=M)
+    AB = oracle.make_ab_batch(M, N, 0.02, x0, layout=layout)
+    ref = oracle.lqr_batch(24, 8, N, AB, qr, layout=layout, x0dev=x0)
+    K = np.empty((batch, N, 8, 24)); K0 = np.empty((batch, 8, 24)); P0 = np.empty((batch, 24, 24))
+    cost = np.empty(batch); status = np.full(batch, -1, dtype=np.int32)
+    prob = capi.problem(capi.MODEL_LTV_USER, N, layout=layout, n=24, m=8)
+    solver.lqr_solve_batch(prob, batch, AB, qr, x0dev=x0, K=K, K0=K0, P0=P0, cost=cost, status=status)
+    assert np.all(status == 0) and np.array_equal(status, ref["status"])
+    assert np.array_equal(K, ref["K"]) and np.array_equal(K0, ref["K0"])
+    assert np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
+    assert np.array_equal(P0, P0.transpose(0, 2, 1))
+
+
+def test_lqr24_dense_weights_random_ltv_and_not_pd(oracle, solver):
+    from noc_b200 import capi
+    rng = np.random.default_rng(15)
+    batch, N = 7, 12
+
+    def spd(k, s):
+        Mx = rng.normal(size=(k, k)); return s * (Mx @ Mx.T + k * np.eye(k))
+    Q, R, Qf = spd(24, 0.1), spd(8, 0.05), spd(24, 1.0)
+    A = np.eye(24) + 0.03 * rng.normal(size=(batch, N, 24, 24))
+    B = 0.1 * rng.normal(size=(batch, N, 24, 8))
+    AB = np.concatenate([A.reshape(batch, N, 576), B.reshape(batch, N, 192)], axis=2)
+    x0 = rng.normal(size=(batch, 24))
+    for Rm in (R, R - 3.0 * np.eye(8)):       # second: indefinite R -> NOT_PD for (some) instances
+        qr = pb.pack_qrqf(Q, Rm, Qf)
+        ref = oracle.lqr_batch(24, 8, N, AB, qr, x0dev=x0)
+        K = np.empty((batch, N, 8, 24)); P0 = np.empty((batch, 24, 24)); cost = np.empty(batch)
+        status = np.full(batch, -1, dtype=np.int32)
+        solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, N, n=24, m=8), batch, AB, qr, x0dev=x0, K=K, P0=P0,
+                               cost=cost, status=status)
+        assert np.array_equal(status, ref["status"])
+        assert np.array_equal(np.isnan(K), np.isnan(ref["K"]))
+        ok = ~np.isnan(ref["K"])
+        assert np.array_equal(K[ok], ref["K"][ok])
+        okp = ~np.isnan(ref["P0"])
+        assert np.array_equal(np.isnan(P0), ~okp) and np.array_equal(P0[okp], ref["P0"][okp])
+
+
+def test_from_x0_dual24_bitexact(oracle, solver):
+    from noc_b200 import capi
+    batch, N = 19, 50
+    Q, R, Qf = pb.default_weights(M)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(batch, seed=41, model=M)
+    ref = oracle.lqr_from_x0_batch(M, N, 0.02, x0, qr)
+    K0 = np.empty((batch, 8, 24)); P0 = np.empty((batch, 24, 24)); cost = np.empty(batch)
+    status = np.full(batch, -1, dtype=np.int32)
+    solver.lqr_solve_from_x0(capi.problem(M, N), batch, x0, qr, K0=K0, P0=P0, cost=cost, status=status)
+    assert np.all(status == 0)
+    assert np.array_equal(K0, ref["K0"]) and np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(max_iter=4)])
+def test_slq_dual24_bitexact(oracle, solver, kw):
+    from noc_b200 import capi
+    batch, N = 9, 30
+    Q, R, Qf = pb.default_weights(M)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.hover_state(batch, model=M)
+    xg = pb.sample_goals(batch, seed=77, model=M)
+    prob = capi.problem(M, N, **kw)
+    x = np.empty((batch, N + 1, 24)); u = np.empty((batch, N, 8)); K = np.empty((batch, N, 8, 24))
+    cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    aidx = np.full((batch, prob.max_iter), -7, dtype=np.int32)
+    solver.slq_solve_batch(prob, batch, x0, xg, qr, x=x, u=u, K=K, cost=cost, iters=iters, alpha_idx=aidx, status=status)
+    opts = oracle.slq_opts(M, N, max_iter=prob.max_iter)
+    ref = oracle.slq_batch(opts, x0, xg, qr, want_traj=True, want_K=True)
+    assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
+    assert np.array_equal(aidx, ref["alpha_idx"]) and np.array_equal(cost, ref["cost"])
+    assert np.array_equal(x, ref["x"]) and np.array_equal(u, ref["u"]) and np.array_equal(K, ref["K"])
