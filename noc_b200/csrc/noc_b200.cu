@@ -149,7 +149,7 @@ int scratch(noc_ctx* ctx, int slot, size_t bytes, void** out) {
 }
 
 enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
-       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U };
+       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1 };
 
 // W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
 // Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
@@ -200,11 +200,11 @@ bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u)
 template <int MODE> struct RicCfg { static constexpr int warps = 4, min_ctas = 2; };
 template <> struct RicCfg<RIC_AFFINE> { static constexpr int warps = 7, min_ctas = 1; };
 
-template <int LAYOUT, int MODE>
+template <int LAYOUT, int MODE, bool FUSED = false>
 int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
   constexpr int W = RicCfg<MODE>::warps;
-  auto kern = k_ric12<LAYOUT, MODE, W, RicCfg<MODE>::min_ctas>;
-  const size_t smem = ric12_smem_bytes<MODE>(W);
+  auto kern = k_ric12<LAYOUT, MODE, FUSED, W, RicCfg<MODE>::min_ctas>;
+  const size_t smem = ric12_smem_bytes<MODE, FUSED>(W);
   static bool attr_set = false;  // one flag per template instantiation
   if (!attr_set) {
     NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -318,21 +318,26 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
   if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
   if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
-  // chunk so that the A_k,B_k scratch stays within a share of the free HBM
+  // MODEL_QUAD12: the sweep linearises in-kernel (k_ric12<…, FUSED>), only the nominal trajectory is staged.
+  // MODEL_DUAL24: k_linearize writes the A_k,B_k stream into scratch.  Either way the batch is chunked so that
+  // the scratch stays within a share of the free HBM.
+  constexpr bool fused = (MODEL == 0);
   size_t free_b = 0, total_b = 0;
   NOC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   size_t have = 0;
   if (ctx->scratch.size() > SCR_AB) have = ctx->scratch[SCR_AB].cap;
   if (ctx->scratch.size() > SCR_XBAR) have += ctx->scratch[SCR_XBAR].cap;
   const size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
-  const size_t per_inst = sizeof(double) * (N * rec + (N + 1) * n);
+  const size_t per_inst = sizeof(double) * ((fused ? 0 : N * rec) + (N + 1) * n);
   size_t chunk = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
   if (chunk < B) chunk = std::max<size_t>(8, chunk & ~size_t(7));
-  void *dxbar, *dAB;
+  void *dxbar = nullptr, *dAB = nullptr;
   if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * chunk * (N + 1) * n, &dxbar))) return rc;
-  if ((rc = scratch(ctx, SCR_AB, sizeof(double) * chunk * N * rec, &dAB))) return rc;
+  if (!fused && (rc = scratch(ctx, SCR_AB, sizeof(double) * chunk * N * rec, &dAB))) return rc;
   noc_problem_t q = *p;
-  q.layout = NOC_LAYOUT_ROWS_AB;  // internal stream: one contiguous [A|B] row per F row
+  q.layout = NOC_LAYOUT_A_THEN_B;
+  Ric12Args fa{};
+  if (fused && (rc = build_w12(ctx, (const double*)dQ, false, &fa.W, &fa.Qf))) { ctx->pending.clear(); return rc; }
   for (size_t off = 0; off < B; off += chunk) {
     const long long cb = (long long)std::min(chunk, B - off);
     const double* x0c = (const double*)dx0 + off * n;
@@ -341,16 +346,24 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
       k_rollout_open_loop<MODEL><<<(unsigned)((cb + 127) / 128), 128, 0, ctx->stream>>>(x0c, nullptr, (double*)dxbar, cb, p->N, p->dt);
     }
     NOC_CUDA(ctx, cudaGetLastError());
-    const long long total = cb * p->N;
-    {
-      LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
-      k_linearize<MODEL><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout, nullptr);
+    double* Kc = dK ? (double*)dK + off * N * m * n : nullptr;
+    double* K0c = dK0 ? (double*)dK0 + off * m * n : nullptr;
+    double* P0c = dP0 ? (double*)dP0 + off * n * n : nullptr;
+    double* cc = dcost ? (double*)dcost + off : nullptr;
+    int32_t* sc = dstatus ? (int32_t*)dstatus + off : nullptr;
+    if constexpr (fused) {
+      fa.xbar = (const double*)dxbar; fa.ubar = nullptr; fa.dt = p->dt; fa.x0 = x0c;
+      fa.K = Kc; fa.K0 = K0c; fa.P0 = P0c; fa.cost = cc; fa.status = sc; fa.batch = cb; fa.N = p->N;
+      rc = launch_ric12<0, RIC_LQR, true>(ctx, fa);
+    } else {
+      const long long total = cb * p->N;
+      {
+        LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+        k_linearize<MODEL><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout, nullptr);
+      }
+      NOC_CUDA(ctx, cudaGetLastError());
+      rc = lqr24_device(ctx, &q, cb, (const double*)dAB, (const double*)dQ, x0c, Kc, K0c, P0c, cc, sc);
     }
-    NOC_CUDA(ctx, cudaGetLastError());
-    rc = (MODEL == 0 ? lqr12_device : lqr24_device)(ctx, &q, cb, (const double*)dAB, (const double*)dQ, x0c,
-                      dK ? (double*)dK + off * N * m * n : nullptr, dK0 ? (double*)dK0 + off * m * n : nullptr,
-                      dP0 ? (double*)dP0 + off * n * n : nullptr, dcost ? (double*)dcost + off : nullptr,
-                      dstatus ? (int32_t*)dstatus + off : nullptr);
     if (rc) { ctx->pending.clear(); return rc; }
   }
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
@@ -381,7 +394,8 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   if ((rc = stage_out(ctx, 5, alpha_idx, sizeof(int32_t) * B * p->max_iter, &dai))) return rc;
   if ((rc = out_or_scratch(6, SCR_STATUS, status, sizeof(int32_t) * B, &dst))) return rc;
   void *dAB, *dkff, *ddV, *dmu, *dbst, *didx0, *didx1, *dcount;
-  if ((rc = scratch(ctx, SCR_AB, sizeof(double) * B * N * rec, &dAB))) return rc;
+  dAB = nullptr;
+  if (MODEL != 0 && (rc = scratch(ctx, SCR_AB, sizeof(double) * B * N * rec, &dAB))) return rc;  // MODEL 0 linearises in the sweep
   if ((rc = scratch(ctx, SCR_KFF, sizeof(double) * B * N * m, &dkff))) return rc;
   if ((rc = scratch(ctx, SCR_DV, sizeof(double) * B * 2, &ddV))) return rc;
   if ((rc = scratch(ctx, SCR_MU, sizeof(double) * B, &dmu))) return rc;
@@ -389,6 +403,20 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   if ((rc = scratch(ctx, SCR_IDX0, sizeof(int32_t) * B, &didx0))) return rc;
   if ((rc = scratch(ctx, SCR_IDX1, sizeof(int32_t) * B, &didx1))) return rc;
   if ((rc = scratch(ctx, SCR_COUNT, 64, &dcount))) return rc;
+  void *dxn, *dun, *dretry0, *dretry1;
+  if ((rc = scratch(ctx, SCR_RETRY0, sizeof(int32_t) * B, &dretry0))) return rc;
+  if ((rc = scratch(ctx, SCR_RETRY1, sizeof(int32_t) * B, &dretry1))) return rc;
+  if ((rc = scratch(ctx, SCR_XN, sizeof(double) * B * (N + 1) * n, &dxn))) return rc;
+  if ((rc = scratch(ctx, SCR_UN, sizeof(double) * B * N * m, &dun))) return rc;
+  using FC = FwdCfg<MODEL>;
+  const size_t fwd_smem = FC::weight_bytes + 16 + FC::ring_bytes;
+  {
+    static bool fwd_attr = false;
+    if (!fwd_attr) {
+      NOC_CUDA(ctx, cudaFuncSetAttribute(k_slq_forward<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+      fwd_attr = true;
+    }
+  }
   const size_t wbytes = sizeof(double) * (2 * n * n + m * m);
   {
     LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
@@ -405,7 +433,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   int32_t* cur = (int32_t*)didx0;
   int32_t* nxt = (int32_t*)didx1;
   for (int it = 0; it < p->max_iter && count > 0; ++it) {
-    {  // a1: time-parallel linearisation of the active instances
+    if constexpr (MODEL != 0) {  // a1: time-parallel linearisation of the active instances (n=12 fuses it into the sweep)
       const long long total = (long long)count * p->N;
       LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
       k_linearize<MODEL><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
@@ -416,27 +444,40 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
     ra.AB = (const double*)dAB; ra.idx = cur; ra.xbar = (const double*)dx; ra.ubar = (const double*)du;
     ra.xgoal = (const double*)dxg; ra.K = (double*)dK; ra.kff = (double*)dkff; ra.dV = (double*)ddV;
     ra.mu = (double*)dmu; ra.status = (int32_t*)dbst; ra.batch = count; ra.N = p->N;
-    if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_AFFINE>(ctx, ra);
+    if constexpr (MODEL == 0) { ra.dt = p->dt; rc = launch_ric12<0, RIC_AFFINE, true>(ctx, ra); }
     else rc = launch_ric24<0, RIC_AFFINE>(ctx, ra);
     if (rc) { ctx->pending.clear(); return rc; }
-    // a4: candidate rollouts, line search, acceptance, convergence, next work list
-    NOC_CUDA(ctx, cudaMemsetAsync(dcount, 0, 4, ctx->stream));
+    // a4: closed-loop rollouts with backtracking, acceptance, convergence, next work list.  One launch per step
+    // length: trial 0 on the whole list, trial j+1 only on the instances whose trial j was rejected.
+    NOC_CUDA(ctx, cudaMemsetAsync(dcount, 0, 8, ctx->stream));
     SlqFwdArgs fa{};
-    fa.idx = cur; fa.next_idx = nxt; fa.next_count = (int32_t*)dcount; fa.xgoal = (const double*)dxg;
-    fa.qrqf = (const double*)dQ; fa.x = (double*)dx; fa.u = (double*)du; fa.K = (const double*)dK;
+    fa.next_idx = nxt; fa.next_count = (int32_t*)dcount; fa.retry_count = (int32_t*)dcount + 1;
+    fa.xgoal = (const double*)dxg;
+    fa.qrqf = (const double*)dQ; fa.x = (double*)dx; fa.u = (double*)du; fa.xn = (double*)dxn; fa.un = (double*)dun;
+    fa.K = (const double*)dK;
     fa.kff = (const double*)dkff; fa.dV = (const double*)ddV; fa.J = (double*)dJ; fa.bstatus = (const int32_t*)dbst;
-    fa.status = (int32_t*)dst; fa.iters = (int32_t*)dit; fa.alpha_idx = (int32_t*)dai; fa.count = count; fa.N = p->N;
+    fa.status = (int32_t*)dst; fa.iters = (int32_t*)dit; fa.alpha_idx = (int32_t*)dai; fa.N = p->N;
     fa.iter = it; fa.max_iter = p->max_iter; fa.n_alpha = p->n_alpha; fa.dt = p->dt; fa.tol = p->tol;
     fa.armijo = p->armijo;
-    {
-      LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-      k_slq_forward<MODEL><<<(unsigned)((count + 3) / 4), 128, wbytes, ctx->stream>>>(fa);
+    int32_t hc[2] = {0, 0};
+    const int32_t* list = cur;
+    int list_count = count;
+    int32_t* rin = (int32_t*)dretry0;
+    int32_t* rout = (int32_t*)dretry1;
+    for (int trial = 0; trial < p->n_alpha && list_count > 0; ++trial) {
+      fa.idx = list; fa.count = list_count; fa.trial = trial; fa.retry_idx = rin;
+      {
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_slq_forward<MODEL><<<(unsigned)((list_count + FC::threads - 1) / FC::threads), FC::threads, fwd_smem, ctx->stream>>>(fa);
+      }
+      NOC_CUDA(ctx, cudaGetLastError());
+      NOC_CUDA(ctx, cudaMemcpyAsync(hc, dcount, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      list = rin; list_count = hc[1];
+      std::swap(rin, rout);
+      if (list_count > 0) NOC_CUDA(ctx, cudaMemsetAsync((int32_t*)dcount + 1, 0, 4, ctx->stream));
     }
-    NOC_CUDA(ctx, cudaGetLastError());
-    int32_t hc = 0;
-    NOC_CUDA(ctx, cudaMemcpyAsync(&hc, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    count = hc;
+    count = hc[0];
     std::swap(cur, nxt);
   }
   return flush_out(ctx, false);

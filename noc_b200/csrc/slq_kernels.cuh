@@ -113,11 +113,16 @@ __global__ void __launch_bounds__(128) k_slq_init(const double* __restrict__ x0,
 struct SlqFwdArgs {
   const int32_t* idx;       // [count] active instances
   int32_t* next_idx;        // compacted list of the instances that continue
-  int32_t* next_count;      // atomic counter (zeroed by the host before the launch)
+  int32_t* next_count;      // atomic counter (zeroed by the host at the start of the SLQ iteration)
+  int32_t* retry_idx;       // instances whose trial was rejected: the host launches the next step length on them
+  int32_t* retry_count;     // atomic counter (zeroed by the host before every launch)
+  int trial;                // j of this launch: alpha = 2^-j for every instance of the work list
   const double* xgoal;      // [batch][n]
   const double* qrqf;
   double* x;                // [batch][N+1][n]  in: nominal, out: accepted trajectory (in place)
   double* u;                // [batch][N][m]
+  double* xn;               // [batch][N+1][n]  scratch: the nominal, saved by trial 0 while x / u are overwritten
+  double* un;               // [batch][N][m]
   const double* K;          // [batch][N][m*n]
   const double* kff;        // [batch][N][m]
   const double* dV;         // [batch][2]
@@ -134,87 +139,156 @@ struct SlqFwdArgs {
   double dt, tol, armijo;
 };
 
-// One warp per active instance; lane j rolls out the candidate alpha_j = 2^-j (all candidates at once instead
-// of the oracle's sequential backtracking: the first accepted j is the same).  Pass 2 re-runs the accepted
-// candidate (bit-identical recomputation) and lane 0 writes the trajectory in place.
+// One THREAD per active instance (the rollout is a sequential chain; the batch supplies the parallelism).
+// ncu on the first thread-per-instance version (profiles/ncu_r01_k_slq_forward_v2.txt): 52 % of the issue slots
+// stalled on the long scoreboard — every step waited for its own K_k, kff_k, xbar_k, ubar_k to come from HBM.
+// Now the per-step inputs (34 16-byte chunks for n=12) are streamed through a STAGES-deep cp.async ring in shared
+// memory, laid out [chunk][thread] so that both the copies and the reads are conflict-free.
+// Backtracking is sequential like the oracle's (alpha_j = 2^-j until the Armijo test passes) but runs as one
+// LAUNCH per step length: trial 0 goes over the whole work list, writes its trajectory IN PLACE over the nominal
+// (x_k, u_k are consumed before they are overwritten; the ring prefetches only later steps) and saves the nominal
+// it replaces to xn / un; the 1 % of instances whose trial is rejected are appended to a retry list, and trial j+1
+// (nominal read from xn / un) runs on that short list only.  alpha = 1 is accepted in 99 % of the iterations, so
+// no warp ever repeats a rollout because one of its 32 instances backtracks.
 template <int MODEL>
-__global__ void __launch_bounds__(128) k_slq_forward(const SlqFwdArgs a) {
-  constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
+struct FwdCfg {
+  static constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
+  static constexpr int threads = (MODEL == 0) ? 32 : 16;
+  static constexpr int stages = (MODEL == 0) ? 3 : 2;
+  static constexpr int cK = m * n / 2, cX = n / 2, cU = m / 2;    // 16-byte chunks per step: K | xbar | ubar | kff
+  static constexpr int chunks = cK + cX + 2 * cU;
+  static constexpr size_t ring_bytes = (size_t)stages * chunks * threads * 16;
+  static constexpr size_t weight_bytes = sizeof(double) * (2 * n * n + m * m);
+};
+
+template <int MODEL>
+__global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_forward(const SlqFwdArgs a) {
+  using C = FwdCfg<MODEL>;
+  constexpr int n = C::n, m = C::m, T = C::threads, S = C::stages;
   extern __shared__ __align__(16) double sw[];
   CostW<MODEL> w;
   load_weights<MODEL>(sw, a.qrqf, w);
-  const int lane = threadIdx.x & 31;
-  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  double2* ring = reinterpret_cast<double2*>(sw + (2 * n * n + m * m) + ((2 * n * n + m * m) & 1));
+  const int tid = threadIdx.x;
+  const int item = blockIdx.x * T + tid;
   if (item >= a.count) return;
   const long long b = a.idx[item];
   const int N = a.N;
-  double* xb = a.x + (size_t)b * (N + 1) * n;
-  double* ub = a.u + (size_t)b * N * m;
-  const double* Kb = a.K + (size_t)b * N * m * n;
-  const double* kb = a.kff + (size_t)b * N * m;
-  double xg[n];
-#pragma unroll
-  for (int i = 0; i < n; ++i) xg[i] = a.xgoal[b * n + i];
-
-  if (a.bstatus[b] != 0) {  // regularisation exhausted in the backward pass
-    if (lane == 0) { a.status[b] = 4; a.iters[b] = a.iter + 1; }
+  if (a.trial == 0 && a.bstatus[b] != 0) {  // regularisation exhausted in the backward pass
+    a.status[b] = 4;
+    a.iters[b] = a.iter + 1;
     return;
   }
+  double* xb = a.x + (size_t)b * (N + 1) * n;    // receives the trial's trajectory
+  double* ub = a.u + (size_t)b * N * m;
+  double* xs = a.xn + (size_t)b * (N + 1) * n;   // holds the nominal from trial 0 on
+  double* us = a.un + (size_t)b * N * m;
+  const bool first = a.trial == 0;
+  const double* xnom = first ? xb : xs;          // where this trial reads the nominal
+  const double* unom = first ? ub : us;
+  const double* Kb = a.K + (size_t)b * N * m * n;
+  const double* kb = a.kff + (size_t)b * N * m;
+  double xg[n], x0[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) { xg[i] = a.xgoal[b * n + i]; x0[i] = xnom[i]; }
   const double Jold = a.J[b];
   const double dV1 = a.dV[b * 2], dV2 = a.dV[b * 2 + 1];
 
-  double alpha = 1.0;
-  for (int j = 0; j < lane; ++j) alpha = alpha * 0.5;
-  int accepted = -1;
-  double Jacc = 0.0;
-  for (int pass = 0; pass < 2; ++pass) {
+  auto prefetch = [&](int k) {
+    if (k < N) {
+      double2* st = ring + (size_t)(k % S) * C::chunks * T + tid;
+      const double* srcK = Kb + (size_t)k * m * n;
+      const double* srcX = xnom + (size_t)k * n;
+      const double* srcU = unom + (size_t)k * m;
+      const double* srcF = kb + (size_t)k * m;
+#pragma unroll
+      for (int c = 0; c < C::cK; ++c) cp_async16(smem_u32(st + c * T), srcK + 2 * c);
+#pragma unroll
+      for (int c = 0; c < C::cX; ++c) cp_async16(smem_u32(st + (C::cK + c) * T), srcX + 2 * c);
+#pragma unroll
+      for (int c = 0; c < C::cU; ++c) cp_async16(smem_u32(st + (C::cK + C::cX + c) * T), srcU + 2 * c);
+#pragma unroll
+      for (int c = 0; c < C::cU; ++c) cp_async16(smem_u32(st + (C::cK + C::cX + C::cU + c) * T), srcF + 2 * c);
+    }
+    cp_async_commit();   // one group per step, also when empty: keeps the wait_group arithmetic uniform
+  };
+
+  // one closed-loop rollout with step length alpha (in place, nominal saved to the scratch); returns its cost
+  auto rollout = [&](double alpha) -> double {
     double xk[n], xn[n], uk[m];
 #pragma unroll
-    for (int i = 0; i < n; ++i) xk[i] = xb[i];
+    for (int i = 0; i < n; ++i) xk[i] = x0[i];
     double Jn = 0.0;
+#pragma unroll
+    for (int p = 0; p < S - 1; ++p) prefetch(p);
     for (int k = 0; k < N; ++k) {
+      prefetch(k + S - 1);
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(S - 1) : "memory");   // step k's group has landed
+      const double2* st = ring + (size_t)(k % S) * C::chunks * T + tid;
       double dx[n];
 #pragma unroll
-      for (int i = 0; i < n; ++i) dx[i] = xk[i] - xb[(size_t)k * n + i];
+      for (int i = 0; i < n; i += 2) {
+        const double2 v = st[(C::cK + i / 2) * T];
+        dx[i] = xk[i] - v.x; dx[i + 1] = xk[i + 1] - v.y;
+      }
 #pragma unroll
       for (int c = 0; c < m; ++c) {
         double tk = 0.0;
 #pragma unroll
-        for (int i = 0; i < n; ++i) tk = fmad(Kb[(size_t)k * m * n + c * n + i], dx[i], tk);
-        uk[c] = (ub[(size_t)k * m + c] + alpha * kb[(size_t)k * m + c]) + tk;
+        for (int i = 0; i < n; i += 2) {
+          const double2 kv = st[((c * n + i) / 2) * T];
+          tk = fmad(kv.x, dx[i], tk);
+          tk = fmad(kv.y, dx[i + 1], tk);
+        }
+        const double2 uv = st[(C::cK + C::cX + c / 2) * T];
+        const double2 fv = st[(C::cK + C::cX + C::cU + c / 2) * T];
+        uk[c] = (((c & 1) ? uv.y : uv.x) + alpha * ((c & 1) ? fv.y : fv.x)) + tk;
       }
       Jn = Jn + w.stage(xk, uk, xg);
       model::model_step<MODEL>(xk, uk, a.dt, xn);
-      if (pass == 1) {
-        __syncwarp();  // every lane has read the nominal x_k, u_k before lane 0 overwrites them
-        if (lane == 0) {
 #pragma unroll
-          for (int i = 0; i < n; ++i) xb[(size_t)k * n + i] = xk[i];
+      for (int i = 0; i < n; i += 2) {
+        if (first) *reinterpret_cast<double2*>(xs + (size_t)k * n + i) = st[(C::cK + i / 2) * T];           // save nominal
+        *reinterpret_cast<double2*>(xb + (size_t)k * n + i) = make_double2(xk[i], xk[i + 1]);               // new in place
+      }
 #pragma unroll
-          for (int c = 0; c < m; ++c) ub[(size_t)k * m + c] = uk[c];
-        }
+      for (int c = 0; c < m; c += 2) {
+        if (first) *reinterpret_cast<double2*>(us + (size_t)k * m + c) = st[(C::cK + C::cX + c / 2) * T];
+        *reinterpret_cast<double2*>(ub + (size_t)k * m + c) = make_double2(uk[c], uk[c + 1]);
       }
 #pragma unroll
       for (int i = 0; i < n; ++i) xk[i] = xn[i];
     }
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     Jn = Jn + w.terminal(xk, xg);
-    if (pass == 1) {
-      if (lane == 0) {
 #pragma unroll
-        for (int i = 0; i < n; ++i) xb[(size_t)N * n + i] = xk[i];
-      }
-      break;
+    for (int i = 0; i < n; i += 2) {
+      if (first) *reinterpret_cast<double2*>(xs + (size_t)N * n + i) = *reinterpret_cast<const double2*>(xb + (size_t)N * n + i);
+      *reinterpret_cast<double2*>(xb + (size_t)N * n + i) = make_double2(xk[i], xk[i + 1]);
     }
-    const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
-    const bool ok = (lane < a.n_alpha) && (Jold - Jn >= a.armijo * expected);
-    const unsigned mask = __ballot_sync(0xffffffffu, ok);
-    if (mask == 0u) break;
-    accepted = __ffs(mask) - 1;
-    Jacc = __shfl_sync(0xffffffffu, Jn, accepted);
-    alpha = __shfl_sync(0xffffffffu, alpha, accepted);
-  }
-  if (lane != 0) return;
-  if (accepted < 0) {
+    return Jn;
+  };
+
+  double alpha = 1.0;
+  for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
+  const int accepted = a.trial;
+  const double Jacc = rollout(alpha);
+  const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
+  if (!(Jold - Jacc >= a.armijo * expected)) {
+    if (a.trial + 1 < a.n_alpha) {   // next step length, next launch
+      const int pos = atomicAdd(a.retry_count, 1);
+      a.retry_idx[pos] = (int32_t)b;
+      return;
+    }
+    // no step length passed: put the nominal back (oracle: x, u unchanged) and stop this instance
+    const double2* sx = reinterpret_cast<const double2*>(xs);
+    const double2* su = reinterpret_cast<const double2*>(us);
+    double2* dxp = reinterpret_cast<double2*>(xb);
+    double2* dup = reinterpret_cast<double2*>(ub);
+#pragma unroll 8
+    for (int i = 0; i < (N + 1) * n / 2; ++i) dxp[i] = sx[i];
+#pragma unroll 8
+    for (int i = 0; i < N * m / 2; ++i) dup[i] = su[i];
     a.status[b] = 3;  // NOC_STATUS_LS_FAIL
     a.iters[b] = a.iter + 1;
     return;
