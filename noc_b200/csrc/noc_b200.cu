@@ -35,6 +35,8 @@ struct noc_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;   // device->host copies of finished chunks, overlapped with the next chunk
+  cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::string err;
   int64_t launches = 0;
   int sm_count = 0;
@@ -330,6 +332,10 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   const size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
   const size_t per_inst = sizeof(double) * ((fused ? 0 : N * rec) + (N + 1) * n);
   size_t chunk = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
+  // batch scheduler: with host-resident outputs a large batch is cut into (at least) four chunks so that the
+  // device->host copy of chunk i runs on the copy stream under the kernels of chunk i+1
+  const bool overlap = !ctx->pending.empty() && B >= 8192 && !(p->flags & NOC_FLAG_ASYNC);
+  if (overlap) chunk = std::min(chunk, (B / 4 + 31) & ~size_t(31));
   if (chunk < B) chunk = std::max<size_t>(8, chunk & ~size_t(7));
   void *dxbar = nullptr, *dAB = nullptr;
   if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * chunk * (N + 1) * n, &dxbar))) return rc;
@@ -365,6 +371,22 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
       rc = lqr24_device(ctx, &q, cb, (const double*)dAB, (const double*)dQ, x0c, Kc, K0c, P0c, cc, sc);
     }
     if (rc) { ctx->pending.clear(); return rc; }
+    if (overlap) {
+      cudaEvent_t ev = ctx->chunk_ev[(off / chunk) & 3];
+      NOC_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+      NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+      for (auto& c : ctx->pending) {
+        const size_t per = c.bytes / B;   // every output is [batch][...]
+        NOC_CUDA(ctx, cudaMemcpyAsync((char*)c.host + off * per, (const char*)c.dev + off * per, (size_t)cb * per,
+                                      cudaMemcpyDeviceToHost, ctx->copy_stream));
+      }
+    }
+  }
+  if (overlap) {
+    ctx->pending.clear();
+    NOC_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return NOC_OK;
   }
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
@@ -520,6 +542,9 @@ int noc_create(noc_ctx** out, int device_id) {
   c->device = device_id;
   c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
+  for (auto& e : c->chunk_ev)
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
   c->stream = c->own_stream;
   *out = c;
   return NOC_OK;
@@ -533,6 +558,9 @@ void noc_destroy(noc_ctx* ctx) {
     for (auto& b : *v)
       if (b.p) cudaFree(b.p);
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  for (auto& e : ctx->chunk_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }

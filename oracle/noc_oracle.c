@@ -69,6 +69,10 @@ void noc_oracle_sincos(double x, double* s, double* c) {
 #define Q_ARM 0.2
 #define Q_YAWC 0.02
 #define Q_G 9.81
+/* reciprocal inertias: the spec multiplies by these compile-time constants */
+#define Q_INV_JX (1.0 / Q_JX)
+#define Q_INV_JY (1.0 / Q_JY)
+#define Q_INV_JZ (1.0 / Q_JZ)
 /* dual-UAV coupling */
 #define D_KS 2.0
 #define D_CS 0.5
@@ -111,13 +115,14 @@ static void quad_f(const double* x, const double* u, double* xd) {
   xd[3] = a * r13;
   xd[4] = a * r23;
   xd[5] = a * r33 - Q_G;
-  const double tth = t.sth / t.cth;
+  const double sec = 1.0 / t.cth;
+  const double tth = t.sth * sec;
   xd[6] = (wx + (t.sph * tth) * wy) + (t.cph * tth) * wz;
   xd[7] = t.cph * wy - t.sph * wz;
-  xd[8] = (t.sph * wy + t.cph * wz) / t.cth;
-  xd[9] = (tau_x - (Q_JZ - Q_JY) * (wy * wz)) / Q_JX;
-  xd[10] = (tau_y - (Q_JX - Q_JZ) * (wz * wx)) / Q_JY;
-  xd[11] = (tau_z - (Q_JY - Q_JX) * (wx * wy)) / Q_JZ;
+  xd[8] = (t.sph * wy + t.cph * wz) * sec;
+  xd[9] = (tau_x - (Q_JZ - Q_JY) * (wy * wz)) * Q_INV_JX;
+  xd[10] = (tau_y - (Q_JX - Q_JZ) * (wz * wx)) * Q_INV_JY;
+  xd[11] = (tau_z - (Q_JY - Q_JX) * (wx * wy)) * Q_INV_JZ;
 }
 
 /* continuous Jacobians of one vehicle, dense row-major: Jx[12][12], Ju[12][4] (zero-filled first) */
@@ -150,8 +155,8 @@ static void quad_jac(const double* x, const double* u, double* Jx, double* Ju) {
     Ju[5 * 4 + j] = r33 / Q_MASS;
   }
   /* Euler rates */
-  const double tth = t.sth / t.cth;
   const double sec = 1.0 / t.cth;
+  const double tth = t.sth * sec;
   const double sw = t.sph * wy + t.cph * wz;  /* s_phi*wy + c_phi*wz */
   const double cw = t.cph * wy - t.sph * wz;  /* c_phi*wy - s_phi*wz */
   Jx[6 * 12 + 6] = cw * tth;
@@ -167,12 +172,12 @@ static void quad_jac(const double* x, const double* u, double* Jx, double* Ju) {
   Jx[8 * 12 + 10] = t.sph * sec;
   Jx[8 * 12 + 11] = t.cph * sec;
   /* body rates */
-  Jx[9 * 12 + 10] = -((Q_JZ - Q_JY) * wz) / Q_JX;
-  Jx[9 * 12 + 11] = -((Q_JZ - Q_JY) * wy) / Q_JX;
-  Jx[10 * 12 + 9] = -((Q_JX - Q_JZ) * wz) / Q_JY;
-  Jx[10 * 12 + 11] = -((Q_JX - Q_JZ) * wx) / Q_JY;
-  Jx[11 * 12 + 9] = -((Q_JY - Q_JX) * wy) / Q_JZ;
-  Jx[11 * 12 + 10] = -((Q_JY - Q_JX) * wx) / Q_JZ;
+  Jx[9 * 12 + 10] = -((Q_JZ - Q_JY) * wz) * Q_INV_JX;
+  Jx[9 * 12 + 11] = -((Q_JZ - Q_JY) * wy) * Q_INV_JX;
+  Jx[10 * 12 + 9] = -((Q_JX - Q_JZ) * wz) * Q_INV_JY;
+  Jx[10 * 12 + 11] = -((Q_JX - Q_JZ) * wx) * Q_INV_JY;
+  Jx[11 * 12 + 9] = -((Q_JY - Q_JX) * wy) * Q_INV_JZ;
+  Jx[11 * 12 + 10] = -((Q_JY - Q_JX) * wx) * Q_INV_JZ;
   Ju[9 * 4 + 1] = Q_ARM / Q_JX;   Ju[9 * 4 + 3] = -(Q_ARM / Q_JX);
   Ju[10 * 4 + 0] = -(Q_ARM / Q_JY); Ju[10 * 4 + 2] = Q_ARM / Q_JY;
   Ju[11 * 4 + 0] = Q_YAWC / Q_JZ;  Ju[11 * 4 + 1] = -(Q_YAWC / Q_JZ);
