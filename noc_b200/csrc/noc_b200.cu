@@ -151,7 +151,7 @@ int scratch(noc_ctx* ctx, int slot, size_t bytes, void** out) {
 }
 
 enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
-       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1 };
+       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC };
 
 // W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
 // Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
@@ -430,12 +430,14 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   if ((rc = scratch(ctx, SCR_RETRY1, sizeof(int32_t) * B, &dretry1))) return rc;
   if ((rc = scratch(ctx, SCR_XN, sizeof(double) * B * (N + 1) * n, &dxn))) return rc;
   if ((rc = scratch(ctx, SCR_UN, sizeof(double) * B * N * m, &dun))) return rc;
+  void* dlc;
+  if ((rc = scratch(ctx, SCR_LC, sizeof(double) * B * (N + 1), &dlc))) return rc;
   using FC = FwdCfg<MODEL>;
-  const size_t fwd_smem = FC::weight_bytes + 16 + FC::ring_bytes;
+  const size_t fwd_smem = FC::ring_bytes;
   {
     static bool fwd_attr = false;
     if (!fwd_attr) {
-      NOC_CUDA(ctx, cudaFuncSetAttribute(k_slq_forward<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+      NOC_CUDA(ctx, cudaFuncSetAttribute(k_slq_rollout<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
       fwd_attr = true;
     }
   }
@@ -477,7 +479,8 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
     fa.xgoal = (const double*)dxg;
     fa.qrqf = (const double*)dQ; fa.x = (double*)dx; fa.u = (double*)du; fa.xn = (double*)dxn; fa.un = (double*)dun;
     fa.K = (const double*)dK;
-    fa.kff = (const double*)dkff; fa.dV = (const double*)ddV; fa.J = (double*)dJ; fa.bstatus = (const int32_t*)dbst;
+    fa.kff = (const double*)dkff; fa.dV = (const double*)ddV; fa.lc = (double*)dlc; fa.J = (double*)dJ;
+    fa.bstatus = (const int32_t*)dbst;
     fa.status = (int32_t*)dst; fa.iters = (int32_t*)dit; fa.alpha_idx = (int32_t*)dai; fa.N = p->N;
     fa.iter = it; fa.max_iter = p->max_iter; fa.n_alpha = p->n_alpha; fa.dt = p->dt; fa.tol = p->tol;
     fa.armijo = p->armijo;
@@ -490,7 +493,18 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
       fa.idx = list; fa.count = list_count; fa.trial = trial; fa.retry_idx = rin;
       {
         LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-        k_slq_forward<MODEL><<<(unsigned)((list_count + FC::threads - 1) / FC::threads), FC::threads, fwd_smem, ctx->stream>>>(fa);
+        k_slq_rollout<MODEL><<<(unsigned)((list_count + FC::threads - 1) / FC::threads), FC::threads, fwd_smem, ctx->stream>>>(fa);
+      }
+      NOC_CUDA(ctx, cudaGetLastError());
+      {
+        const long long total = (long long)list_count * (p->N + 1);
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fa);
+      }
+      NOC_CUDA(ctx, cudaGetLastError());
+      {
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_slq_accept<MODEL><<<(unsigned)((list_count + 127) / 128), 128, 0, ctx->stream>>>(fa);
       }
       NOC_CUDA(ctx, cudaGetLastError());
       NOC_CUDA(ctx, cudaMemcpyAsync(hc, dcount, 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -36,9 +36,11 @@ __global__ void __launch_bounds__(128) k_rollout_open_loop(const double* __restr
   }
 }
 
-// One thread per (work item, k); `batch` counts work items (= instances unless idx is given).  The record is zero-filled with 16-byte stores, then the ~70 structural
-// non-zeros are written.  L2 merges the partial sectors before they reach HBM (record = 1536 B, written
-// within one thread).  Layout 0: A then B; layout 1: rows of [A row | B row].
+// One thread per (work item, k); `batch` counts work items (= instances unless idx is given).  The record is
+// ~85 % zeros, so a warp first zero-fills the 32 records of its lanes cooperatively — every store instruction
+// writes 512 contiguous bytes — and only then does each lane scatter the structural non-zeros of its own record
+// (a first version let every thread fill its own record: 32 lines per store instruction, 0.9 TB/s on the 6-KB
+// records of the dual-UAV model).  Layout 0: A then B; layout 1: rows of [A row | B row].
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_linearize(const double* __restrict__ xbar,
                                                    const double* __restrict__ ubar,  // may be null
@@ -46,21 +48,35 @@ __global__ void __launch_bounds__(128) k_linearize(const double* __restrict__ xb
                                                    int layout, const int32_t* __restrict__ idx) {
   constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, rec = n * n + n * m;
   const long long tw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tw >= batch * N) return;
-  const long long item = tw / N;
-  const int k = (int)(tw - item * N);
+  const bool active = tw < batch * N;
+  const long long twc = active ? tw : batch * N - 1;
+  const long long item = twc / N;
+  const int k = (int)(twc - item * N);
   const long long b = idx ? (long long)idx[item] : item;   // SLQ: only the instances still iterating
   const long long t = b * N + k;
+  double* r = AB + (size_t)t * rec;
+  {
+    const int lane = threadIdx.x & 31;
+    const double2 z = make_double2(0.0, 0.0);
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+      const unsigned long long pj = __shfl_sync(0xffffffffu, (unsigned long long)r, j);
+      const bool on = __shfl_sync(0xffffffffu, active ? 1 : 0, j) != 0;
+      if (on) {
+        double2* dst = reinterpret_cast<double2*>(pj);
+#pragma unroll
+        for (int i = lane; i < rec / 2; i += 32) dst[i] = z;
+      }
+    }
+    __syncwarp();
+  }
+  if (!active) return;
   double x[n], u[m];
   const double* xs = xbar + ((size_t)b * (N + 1) + k) * n;
 #pragma unroll
   for (int i = 0; i < n; ++i) x[i] = xs[i];
 #pragma unroll
   for (int j = 0; j < m; ++j) u[j] = ubar ? ubar[((size_t)b * N + k) * m + j] : model::kHover;
-  double* r = AB + (size_t)t * rec;
-  double2* r2 = reinterpret_cast<double2*>(r);
-#pragma unroll 8
-  for (int i = 0; i < rec / 2; ++i) r2[i] = make_double2(0.0, 0.0);
   if (layout == 0) {
     model::model_jac_discrete<MODEL>(
         x, u, dt, [&](int i, int j, double v) { r[i * n + j] = v; },

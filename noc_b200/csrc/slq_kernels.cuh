@@ -126,6 +126,7 @@ struct SlqFwdArgs {
   const double* K;          // [batch][N][m*n]
   const double* kff;        // [batch][N][m]
   const double* dV;         // [batch][2]
+  double* lc;               // [batch][N+1] stage costs of the trial (k < N) and its terminal cost (k = N)
   double* J;                // [batch]
   const int32_t* bstatus;   // [batch] backward-pass outcome (0 or NOC_STATUS_REG_FAIL)
   int32_t* status;          // [batch]
@@ -139,7 +140,12 @@ struct SlqFwdArgs {
   double dt, tol, armijo;
 };
 
-// One THREAD per active instance (the rollout is a sequential chain; the batch supplies the parallelism).
+// The forward pass is three kernels per step length: (1) k_slq_rollout, the sequential closed-loop rollout, one
+// THREAD per active instance, only the state/input recursion (latency-critical: ~300 instructions per step);
+// (2) k_slq_stage_cost, the stage and terminal costs of the new trajectory, TIME-PARALLEL over (instance, k);
+// (3) k_slq_accept, the ordered sum of the stage costs, Armijo test and bookkeeping.  Splitting the cost out of
+// the rollout removes 60 % of the instructions from the latency-bound chain (profiles/launches_cfg3_slq_r01.csv:
+// 1.7 ms per 200-step rollout before).
 // ncu on the first thread-per-instance version (profiles/ncu_r01_k_slq_forward_v2.txt): 52 % of the issue slots
 // stalled on the long scoreboard — every step waited for its own K_k, kff_k, xbar_k, ubar_k to come from HBM.
 // Now the per-step inputs (34 16-byte chunks for n=12) are streamed through a STAGES-deep cp.async ring in shared
@@ -158,27 +164,21 @@ struct FwdCfg {
   static constexpr int cK = m * n / 2, cX = n / 2, cU = m / 2;    // 16-byte chunks per step: K | xbar | ubar | kff
   static constexpr int chunks = cK + cX + 2 * cU;
   static constexpr size_t ring_bytes = (size_t)stages * chunks * threads * 16;
-  static constexpr size_t weight_bytes = sizeof(double) * (2 * n * n + m * m);
 };
 
+// (1) the sequential part: closed-loop rollout of trial a.trial, no cost evaluation.  One thread per instance.
 template <int MODEL>
-__global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_forward(const SlqFwdArgs a) {
+__global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_rollout(const SlqFwdArgs a) {
   using C = FwdCfg<MODEL>;
   constexpr int n = C::n, m = C::m, T = C::threads, S = C::stages;
   extern __shared__ __align__(16) double sw[];
-  CostW<MODEL> w;
-  load_weights<MODEL>(sw, a.qrqf, w);
-  double2* ring = reinterpret_cast<double2*>(sw + (2 * n * n + m * m) + ((2 * n * n + m * m) & 1));
+  double2* ring = reinterpret_cast<double2*>(sw);
   const int tid = threadIdx.x;
   const int item = blockIdx.x * T + tid;
   if (item >= a.count) return;
   const long long b = a.idx[item];
   const int N = a.N;
-  if (a.trial == 0 && a.bstatus[b] != 0) {  // regularisation exhausted in the backward pass
-    a.status[b] = 4;
-    a.iters[b] = a.iter + 1;
-    return;
-  }
+  if (a.trial == 0 && a.bstatus[b] != 0) return;   // regularisation exhausted: k_slq_accept records it
   double* xb = a.x + (size_t)b * (N + 1) * n;    // receives the trial's trajectory
   double* ub = a.u + (size_t)b * N * m;
   double* xs = a.xn + (size_t)b * (N + 1) * n;   // holds the nominal from trial 0 on
@@ -188,11 +188,8 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_forward(const Sl
   const double* unom = first ? ub : us;
   const double* Kb = a.K + (size_t)b * N * m * n;
   const double* kb = a.kff + (size_t)b * N * m;
-  double xg[n], x0[n];
-#pragma unroll
-  for (int i = 0; i < n; ++i) { xg[i] = a.xgoal[b * n + i]; x0[i] = xnom[i]; }
-  const double Jold = a.J[b];
-  const double dV1 = a.dV[b * 2], dV2 = a.dV[b * 2 + 1];
+  double alpha = 1.0;
+  for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
 
   auto prefetch = [&](int k) {
     if (k < N) {
@@ -213,66 +210,110 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_forward(const Sl
     cp_async_commit();   // one group per step, also when empty: keeps the wait_group arithmetic uniform
   };
 
-  // one closed-loop rollout with step length alpha (in place, nominal saved to the scratch); returns its cost
-  auto rollout = [&](double alpha) -> double {
-    double xk[n], xn[n], uk[m];
+  double xk[n], xn[n], uk[m];
 #pragma unroll
-    for (int i = 0; i < n; ++i) xk[i] = x0[i];
-    double Jn = 0.0;
+  for (int i = 0; i < n; ++i) xk[i] = xnom[i];
 #pragma unroll
-    for (int p = 0; p < S - 1; ++p) prefetch(p);
-    for (int k = 0; k < N; ++k) {
-      prefetch(k + S - 1);
-      asm volatile("cp.async.wait_group %0;\n" ::"n"(S - 1) : "memory");   // step k's group has landed
-      const double2* st = ring + (size_t)(k % S) * C::chunks * T + tid;
-      double dx[n];
-#pragma unroll
-      for (int i = 0; i < n; i += 2) {
-        const double2 v = st[(C::cK + i / 2) * T];
-        dx[i] = xk[i] - v.x; dx[i + 1] = xk[i + 1] - v.y;
-      }
-#pragma unroll
-      for (int c = 0; c < m; ++c) {
-        double tk = 0.0;
-#pragma unroll
-        for (int i = 0; i < n; i += 2) {
-          const double2 kv = st[((c * n + i) / 2) * T];
-          tk = fmad(kv.x, dx[i], tk);
-          tk = fmad(kv.y, dx[i + 1], tk);
-        }
-        const double2 uv = st[(C::cK + C::cX + c / 2) * T];
-        const double2 fv = st[(C::cK + C::cX + C::cU + c / 2) * T];
-        uk[c] = (((c & 1) ? uv.y : uv.x) + alpha * ((c & 1) ? fv.y : fv.x)) + tk;
-      }
-      Jn = Jn + w.stage(xk, uk, xg);
-      model::model_step<MODEL>(xk, uk, a.dt, xn);
-#pragma unroll
-      for (int i = 0; i < n; i += 2) {
-        if (first) *reinterpret_cast<double2*>(xs + (size_t)k * n + i) = st[(C::cK + i / 2) * T];           // save nominal
-        *reinterpret_cast<double2*>(xb + (size_t)k * n + i) = make_double2(xk[i], xk[i + 1]);               // new in place
-      }
-#pragma unroll
-      for (int c = 0; c < m; c += 2) {
-        if (first) *reinterpret_cast<double2*>(us + (size_t)k * m + c) = st[(C::cK + C::cX + c / 2) * T];
-        *reinterpret_cast<double2*>(ub + (size_t)k * m + c) = make_double2(uk[c], uk[c + 1]);
-      }
-#pragma unroll
-      for (int i = 0; i < n; ++i) xk[i] = xn[i];
-    }
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-    Jn = Jn + w.terminal(xk, xg);
+  for (int p = 0; p < S - 1; ++p) prefetch(p);
+  for (int k = 0; k < N; ++k) {
+    prefetch(k + S - 1);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(S - 1) : "memory");   // step k's group has landed
+    const double2* st = ring + (size_t)(k % S) * C::chunks * T + tid;
+    double dx[n];
 #pragma unroll
     for (int i = 0; i < n; i += 2) {
-      if (first) *reinterpret_cast<double2*>(xs + (size_t)N * n + i) = *reinterpret_cast<const double2*>(xb + (size_t)N * n + i);
-      *reinterpret_cast<double2*>(xb + (size_t)N * n + i) = make_double2(xk[i], xk[i + 1]);
+      const double2 v = st[(C::cK + i / 2) * T];
+      dx[i] = xk[i] - v.x; dx[i + 1] = xk[i + 1] - v.y;
     }
-    return Jn;
-  };
+#pragma unroll
+    for (int c = 0; c < m; ++c) {
+      double tk = 0.0;
+#pragma unroll
+      for (int i = 0; i < n; i += 2) {
+        const double2 kv = st[((c * n + i) / 2) * T];
+        tk = fmad(kv.x, dx[i], tk);
+        tk = fmad(kv.y, dx[i + 1], tk);
+      }
+      const double2 uv = st[(C::cK + C::cX + c / 2) * T];
+      const double2 fv = st[(C::cK + C::cX + C::cU + c / 2) * T];
+      uk[c] = (((c & 1) ? uv.y : uv.x) + alpha * ((c & 1) ? fv.y : fv.x)) + tk;
+    }
+    model::model_step<MODEL>(xk, uk, a.dt, xn);
+#pragma unroll
+    for (int i = 0; i < n; i += 2) {
+      if (first) *reinterpret_cast<double2*>(xs + (size_t)k * n + i) = st[(C::cK + i / 2) * T];           // save nominal
+      *reinterpret_cast<double2*>(xb + (size_t)k * n + i) = make_double2(xk[i], xk[i + 1]);               // new in place
+    }
+#pragma unroll
+    for (int c = 0; c < m; c += 2) {
+      if (first) *reinterpret_cast<double2*>(us + (size_t)k * m + c) = st[(C::cK + C::cX + c / 2) * T];
+      *reinterpret_cast<double2*>(ub + (size_t)k * m + c) = make_double2(uk[c], uk[c + 1]);
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) xk[i] = xn[i];
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < n; i += 2) {
+    if (first) *reinterpret_cast<double2*>(xs + (size_t)N * n + i) = *reinterpret_cast<const double2*>(xb + (size_t)N * n + i);
+    *reinterpret_cast<double2*>(xb + (size_t)N * n + i) = make_double2(xk[i], xk[i + 1]);
+  }
+}
 
+// (2) the time-parallel part: stage costs l_k (k < N) and the terminal cost (k = N) of the trial trajectories,
+// one thread per (work item, k) -> lc[b][k]
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_slq_stage_cost(const SlqFwdArgs a) {
+  constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
+  extern __shared__ __align__(16) double sw[];
+  CostW<MODEL> w;
+  load_weights<MODEL>(sw, a.qrqf, w);
+  const int N = a.N;
+  const long long tw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tw >= (long long)a.count * (N + 1)) return;
+  const int item = (int)(tw / (N + 1));
+  const int k = (int)(tw - (long long)item * (N + 1));
+  const long long b = a.idx[item];
+  if (a.trial == 0 && a.bstatus[b] != 0) return;
+  double x[n], xg[n], u[m];
+  const double* xp = a.x + ((size_t)b * (N + 1) + k) * n;
+#pragma unroll
+  for (int i = 0; i < n; ++i) { x[i] = xp[i]; xg[i] = a.xgoal[b * n + i]; }
+  double c;
+  if (k < N) {
+    const double* up = a.u + ((size_t)b * N + k) * m;
+#pragma unroll
+    for (int j = 0; j < m; ++j) u[j] = up[j];
+    c = w.stage(x, u, xg);
+  } else {
+    c = w.terminal(x, xg);
+  }
+  a.lc[(size_t)b * (N + 1) + k] = c;
+}
+
+// (3) per instance: J = sum of the stage costs in ascending k (the oracle's order), Armijo test, bookkeeping,
+// convergence test, next work list / retry list
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
+  constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= a.count) return;
+  const long long b = a.idx[item];
+  const int N = a.N;
+  if (a.trial == 0 && a.bstatus[b] != 0) {  // regularisation exhausted in the backward pass
+    a.status[b] = 4;
+    a.iters[b] = a.iter + 1;
+    return;
+  }
+  const double* lc = a.lc + (size_t)b * (N + 1);
+  double Jacc = 0.0;
+#pragma unroll 8
+  for (int k = 0; k <= N; ++k) Jacc = Jacc + lc[k];
+  const double Jold = a.J[b];
+  const double dV1 = a.dV[b * 2], dV2 = a.dV[b * 2 + 1];
   double alpha = 1.0;
   for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
   const int accepted = a.trial;
-  const double Jacc = rollout(alpha);
   const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
   if (!(Jold - Jacc >= a.armijo * expected)) {
     if (a.trial + 1 < a.n_alpha) {   // next step length, next launch
@@ -281,10 +322,10 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_forward(const Sl
       return;
     }
     // no step length passed: put the nominal back (oracle: x, u unchanged) and stop this instance
-    const double2* sx = reinterpret_cast<const double2*>(xs);
-    const double2* su = reinterpret_cast<const double2*>(us);
-    double2* dxp = reinterpret_cast<double2*>(xb);
-    double2* dup = reinterpret_cast<double2*>(ub);
+    const double2* sx = reinterpret_cast<const double2*>(a.xn + (size_t)b * (N + 1) * n);
+    const double2* su = reinterpret_cast<const double2*>(a.un + (size_t)b * N * m);
+    double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
+    double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
 #pragma unroll 8
     for (int i = 0; i < (N + 1) * n / 2; ++i) dxp[i] = sx[i];
 #pragma unroll 8
