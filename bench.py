@@ -184,6 +184,14 @@ def workload_config(gpus, batch=BATCH_PER_GPU):
 
 # ------------------------------------------------------------------------------------------ GPU arm
 def run_noc(args):
+    with StdoutToStderr():
+        line = _run_noc(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    return 0
+
+
+def _run_noc(args):
     import torch
     from noc_b200 import capi, problems as pb
 
@@ -320,6 +328,7 @@ def run_noc(args):
     e2e_value = world * B * args.steps / e2e_s
     e2e_bad = int((h_status != 0).sum().item())
 
+    line = None
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
         ric_avg_ms = ric_ms / max(ric_n, 1)
@@ -364,12 +373,27 @@ def run_noc(args):
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{args.cpu_sample} of the {B} instances, one pass, {secs:.2f} s wall on {cores} threads "
                           "(in-repo C oracle, OpenMP over instances; the reference has no solver source)"}
-        print(json.dumps(line), flush=True)
     solver.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return line if rank == 0 else None
+
+
+class StdoutToStderr:
+    """Route fd 1 to stderr while libraries initialise (NCCL prints its version banner on stdout); rank 0's JSON
+    line is the only thing this program writes to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
