@@ -202,10 +202,9 @@ bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u)
 template <int MODE> struct RicCfg { static constexpr int warps = 4, min_ctas = 2; };
 template <> struct RicCfg<RIC_AFFINE> { static constexpr int warps = 7, min_ctas = 1; };
 
-template <int LAYOUT, int MODE, bool FUSED = false>
-int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
-  constexpr int W = RicCfg<MODE>::warps;
-  auto kern = k_ric12<LAYOUT, MODE, FUSED, W, RicCfg<MODE>::min_ctas>;
+template <int LAYOUT, int MODE, bool FUSED, int W, int MIN_CTAS>
+int launch_ric12_cfg(noc_ctx* ctx, const Ric12Args& a) {
+  auto kern = k_ric12<LAYOUT, MODE, FUSED, W, MIN_CTAS>;
   const size_t smem = ric12_smem_bytes<MODE, FUSED>(W);
   static bool attr_set = false;  // one flag per template instantiation
   if (!attr_set) {
@@ -223,6 +222,14 @@ int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
   return NOC_OK;
 }
 
+template <int LAYOUT, int MODE, bool FUSED = false>
+int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
+  // short work lists (the tail of an SLQ solve, small batches): one warp per CTA, so that the few warps spread over
+  // all SMs instead of sharing a handful — the sweep is then latency-bound and a warp alone on an SM steps ~2x faster
+  if (a.batch <= 8LL * 2 * ctx->sm_count) return launch_ric12_cfg<LAYOUT, MODE, FUSED, 1, 1>(ctx, a);
+  return launch_ric12_cfg<LAYOUT, MODE, FUSED, RicCfg<MODE>::warps, RicCfg<MODE>::min_ctas>(ctx, a);
+}
+
 template <int MODE>
 int launch_ric12_layout(noc_ctx* ctx, int layout, const Ric12Args& a) {
   return layout == NOC_LAYOUT_A_THEN_B ? launch_ric12<0, MODE>(ctx, a) : launch_ric12<1, MODE>(ctx, a);
@@ -231,11 +238,11 @@ int launch_ric12_layout(noc_ctx* ctx, int layout, const Ric12Args& a) {
 template <int MODE> struct Ric24Cfg { static constexpr int warps = 8; };
 template <> struct Ric24Cfg<RIC_AFFINE> { static constexpr int warps = 7; };
 
-template <int LAYOUT, int MODE>
+template <int LAYOUT, int MODE, bool FUSED = false>
 int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
   constexpr int W = Ric24Cfg<MODE>::warps;
-  auto kern = k_ric24<LAYOUT, MODE, W>;
-  const size_t smem = ric24_smem_bytes<MODE>(W);
+  auto kern = k_ric24<LAYOUT, MODE, FUSED, W>;
+  const size_t smem = ric24_smem_bytes<MODE, FUSED>(W);
   static bool attr_set = false;
   if (!attr_set) {
     NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -323,7 +330,7 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   // MODEL_QUAD12: the sweep linearises in-kernel (k_ric12<…, FUSED>), only the nominal trajectory is staged.
   // MODEL_DUAL24: k_linearize writes the A_k,B_k stream into scratch.  Either way the batch is chunked so that
   // the scratch stays within a share of the free HBM.
-  constexpr bool fused = (MODEL == 0);
+  constexpr bool fused = true;   // both built-in models have the in-sweep linearisation (k_ric12 / k_ric24 <…, FUSED>)
   size_t free_b = 0, total_b = 0;
   NOC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   size_t have = 0;
@@ -342,8 +349,10 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   if (!fused && (rc = scratch(ctx, SCR_AB, sizeof(double) * chunk * N * rec, &dAB))) return rc;
   noc_problem_t q = *p;
   q.layout = NOC_LAYOUT_A_THEN_B;
-  Ric12Args fa{};
-  if (fused && (rc = build_w12(ctx, (const double*)dQ, false, &fa.W, &fa.Qf))) { ctx->pending.clear(); return rc; }
+  typename std::conditional<MODEL == 0, Ric12Args, Ric24Args>::type fa{};
+  if (MODEL == 0) rc = build_w12(ctx, (const double*)dQ, false, &fa.W, &fa.Qf);
+  else rc = build_w24(ctx, (const double*)dQ, &fa.W, &fa.Qf);
+  if (rc) { ctx->pending.clear(); return rc; }
   for (size_t off = 0; off < B; off += chunk) {
     const long long cb = (long long)std::min(chunk, B - off);
     const double* x0c = (const double*)dx0 + off * n;
@@ -360,7 +369,8 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
     if constexpr (fused) {
       fa.xbar = (const double*)dxbar; fa.ubar = nullptr; fa.dt = p->dt; fa.x0 = x0c;
       fa.K = Kc; fa.K0 = K0c; fa.P0 = P0c; fa.cost = cc; fa.status = sc; fa.batch = cb; fa.N = p->N;
-      rc = launch_ric12<0, RIC_LQR, true>(ctx, fa);
+      if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_LQR, true>(ctx, fa);
+      else rc = launch_ric24<0, RIC_LQR, true>(ctx, fa);
     } else {
       const long long total = cb * p->N;
       {
@@ -416,8 +426,8 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   if ((rc = stage_out(ctx, 5, alpha_idx, sizeof(int32_t) * B * p->max_iter, &dai))) return rc;
   if ((rc = out_or_scratch(6, SCR_STATUS, status, sizeof(int32_t) * B, &dst))) return rc;
   void *dAB, *dkff, *ddV, *dmu, *dbst, *didx0, *didx1, *dcount;
-  dAB = nullptr;
-  if (MODEL != 0 && (rc = scratch(ctx, SCR_AB, sizeof(double) * B * N * rec, &dAB))) return rc;  // MODEL 0 linearises in the sweep
+  dAB = nullptr;   // both models linearise inside the sweep (FUSED): no A_k,B_k stream
+  (void)rec;
   if ((rc = scratch(ctx, SCR_KFF, sizeof(double) * B * N * m, &dkff))) return rc;
   if ((rc = scratch(ctx, SCR_DV, sizeof(double) * B * 2, &ddV))) return rc;
   if ((rc = scratch(ctx, SCR_MU, sizeof(double) * B, &dmu))) return rc;
@@ -457,19 +467,14 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   int32_t* cur = (int32_t*)didx0;
   int32_t* nxt = (int32_t*)didx1;
   for (int it = 0; it < p->max_iter && count > 0; ++it) {
-    if constexpr (MODEL != 0) {  // a1: time-parallel linearisation of the active instances (n=12 fuses it into the sweep)
-      const long long total = (long long)count * p->N;
-      LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
-      k_linearize<MODEL><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>(
-          (const double*)dx, (const double*)du, (double*)dAB, count, p->N, p->dt, NOC_LAYOUT_A_THEN_B, cur);
-    }
-    NOC_CUDA(ctx, cudaGetLastError());
+    // a1 happens inside the sweep (k_ric12 / k_ric24 <…, RIC_AFFINE, FUSED>)
     // a2+a3: affine backward pass (regularisation retries in-kernel)
     ra.AB = (const double*)dAB; ra.idx = cur; ra.xbar = (const double*)dx; ra.ubar = (const double*)du;
     ra.xgoal = (const double*)dxg; ra.K = (double*)dK; ra.kff = (double*)dkff; ra.dV = (double*)ddV;
     ra.mu = (double*)dmu; ra.status = (int32_t*)dbst; ra.batch = count; ra.N = p->N;
-    if constexpr (MODEL == 0) { ra.dt = p->dt; rc = launch_ric12<0, RIC_AFFINE, true>(ctx, ra); }
-    else rc = launch_ric24<0, RIC_AFFINE>(ctx, ra);
+    ra.dt = p->dt;
+    if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_AFFINE, true>(ctx, ra);
+    else rc = launch_ric24<0, RIC_AFFINE, true>(ctx, ra);
     if (rc) { ctx->pending.clear(); return rc; }
     // a4: closed-loop rollouts with backtracking, acceptance, convergence, next work list.  One launch per step
     // length: trial 0 on the whole list, trial j+1 only on the instances whose trial j was rejected.

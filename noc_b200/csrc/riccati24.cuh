@@ -31,7 +31,7 @@ constexpr int R24_ES = 1632;    // affine: [xbar_k - xgoal ; ubar_k - u_h]
 constexpr int R24_VS = 1664;    // affine: Vx[24]
 constexpr int R24_HU = 1688;    // affine: h_u[8]
 constexpr int R24_XG = 1696;    // affine: xgoal[24]
-constexpr int R24_STRIDE_LQR = 1602, R24_STRIDE_AFF = 1722;   // 16 B modulo 128 B: the two instances of a warp differ in bank quad
+constexpr int R24_STRIDE_LQR = 1602, R24_STRIDE_LQR_FUSED = 1634, R24_STRIDE_AFF = 1722;   // 16 B modulo 128 B: the two instances of a warp differ in bank quad
 constexpr int R24_WLD = 34;                                   // padded row stride of W
 constexpr int R24_WS_DOUBLES = 32 * R24_WLD;
 constexpr int R24_QF_DOUBLES = 576;
@@ -51,6 +51,7 @@ struct Ric24Args {
   const double* xbar;    // [batch][N+1][24]
   const double* ubar;    // [batch][N][8]
   const double* xgoal;   // [batch][24]
+  double dt;             // FUSED: Euler step of the built-in model
   double* kff;           // [batch][N][8]
   double* dV;            // [batch][2]
   double* mu;            // [batch]
@@ -58,11 +59,14 @@ struct Ric24Args {
   int N;
 };
 
-template <int MODE>
-__host__ __device__ constexpr int r24_stride() { return MODE == RIC_AFFINE ? R24_STRIDE_AFF : R24_STRIDE_LQR; }
-template <int MODE>
+template <int MODE, bool FUSED>
+__host__ __device__ constexpr int r24_stride() {
+  return MODE == RIC_AFFINE ? R24_STRIDE_AFF : (FUSED ? R24_STRIDE_LQR_FUSED : R24_STRIDE_LQR);
+}
+template <int MODE, bool FUSED>
 inline size_t ric24_smem_bytes(int warps) {
-  return sizeof(double) * (size_t)(R24_WS_DOUBLES + R24_QF_DOUBLES + R24_BAR_DOUBLES + warps * 2 * r24_stride<MODE>());
+  return sizeof(double) *
+         (size_t)(R24_WS_DOUBLES + R24_QF_DOUBLES + R24_BAR_DOUBLES + warps * 2 * r24_stride<MODE, FUSED>());
 }
 
 // M x M square-root-free Cholesky in registers (oracle: chol_lower / chol_solve_neg), fully unrolled
@@ -133,10 +137,15 @@ __device__ __forceinline__ void r24_store_direct(double* Ps, const double* h, in
     if (on && i < j) Ps[i * 24 + j] = h[i];
 }
 
-template <int LAYOUT, int MODE, int WARPS>
+// FUSED (as in riccati12.cuh): the record is computed in the kernel from xbar_k, ubar_k instead of being read from
+// HBM.  Lanes 0..7 of an instance evaluate vehicle 0's Jacobian, lanes 8..15 vehicle 1's (same code, different
+// data); each stores one eighth of the state-dependent entries.  Zeros, the state-independent entries and the
+// (constant) spring-damper coupling entries are written once per sweep.
+template <int LAYOUT, int MODE, bool FUSED, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
   extern __shared__ __align__(128) double smem[];
-  constexpr int STRIDE = r24_stride<MODE>();
+  static_assert(!FUSED || LAYOUT == 0, "fused linearisation: A_THEN_B records");
+  constexpr int STRIDE = r24_stride<MODE, FUSED>();
   double* Ws = smem;
   double* Qfs = smem + R24_WS_DOUBLES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -170,20 +179,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
   const int offB = (LAYOUT == 1) ? cB : (xl ? cB : 576 + (cB - 24));
   const int strAB = (LAYOUT == 1) ? 32 : (xl ? 24 : 8);
 
-  const double* rec = a.AB + (size_t)b * N * R24_REC;
+  const double* rec = FUSED ? nullptr : a.AB + (size_t)b * N * R24_REC;
   const unsigned fs_u32 = smem_u32(Fs);
   unsigned phase = 0;
 
   auto fetch = [&](int k) {
-    if (lane == 0) mbar_expect_tx(bar, 2u * 6144u);
-    __syncwarp();
-    if (t == 0) bulk_g2s(fs_u32, rec + (size_t)k * R24_REC, 6144u, bar);
-    if (MODE == RIC_AFFINE) {
-      // xbar_k (192 B) | ubar_k (64 B): sixteen 16-byte chunks, one per lane
+    if (!FUSED) {
+      if (lane == 0) mbar_expect_tx(bar, 2u * 6144u);
+      __syncwarp();
+      if (t == 0) bulk_g2s(fs_u32, rec + (size_t)k * R24_REC, 6144u, bar);
+    }
+    if (FUSED || MODE == RIC_AFFINE) {
+      // xbar_k (192 B) | ubar_k (64 B, optional): sixteen 16-byte chunks, one per lane
       const double* xs = a.xbar + ((size_t)b * (N + 1) + k) * 24;
-      const double* us = a.ubar + ((size_t)b * N + k) * 8;
       if (t < 12) cp_async16(smem_u32(base + R24_XS + 2 * t), xs + 2 * t);
-      else cp_async16(smem_u32(base + R24_XS + 24 + 2 * (t - 12)), us + 2 * (t - 12));
+      else if (a.ubar) cp_async16(smem_u32(base + R24_XS + 24 + 2 * (t - 12)), a.ubar + ((size_t)b * N + k) * 8 + 2 * (t - 12));
       cp_async_commit();
     }
   };
@@ -199,6 +209,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
     int kfail = -1;
     double* Kp = (a.K && valid) ? a.K + ((size_t)b * N + (N - 1)) * 192 : nullptr;
     for (int e = t; e < 576; e += 16) Ps[e] = Qfs[e];
+    if (FUSED) {
+      for (int e = t; e < R24_REC; e += 16) Fs[e] = 0.0;
+      __syncwarp();
+      if (t == 0) {   // state-independent entries: per-vehicle constants first, then the coupling (it overwrites (3+i,3+i))
+        for (int v = 0; v < 2; ++v)
+          model::quad_jac_constants(a.dt, [&](int i, int j, double val) { Fs[(12 * v + i) * 24 + 12 * v + j] = val; },
+                                    [&](int i, int j, double val) { Fs[576 + (12 * v + i) * 8 + 4 * v + j] = val; });
+        model::dual_coupling_jac(a.dt, [&](int i, int j, double val) { Fs[i * 24 + j] = val; });
+      }
+    }
     if (MODE == RIC_AFFINE) {
       // xgoal -> shared; Vx <- Qf (xbar_N - xgoal): lane t computes rows t and t+16 (<24)
       for (int i = t; i < 24; i += 16) base[R24_XG + i] = a.xgoal[(size_t)b * 24 + i];
@@ -214,10 +234,33 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
 
     for (int it = 0; it < N; ++it) {
       const int k = N - 1 - it;
-      mbar_wait(bar, phase);
-      phase ^= 1u;
-      if (MODE == RIC_AFFINE) cp_async_wait_all();
+      if (!FUSED) {
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+      }
+      if (FUSED || MODE == RIC_AFFINE) cp_async_wait_all();
       __syncwarp();
+      if (FUSED) {
+        // a1 in the sweep: vehicle v = t>>3 of this instance, lane t&7 stores every eighth state-dependent entry
+        const int v = t >> 3, t8 = t & 7;
+        const double* Xs = base + R24_XS;
+        double xk[12], uk[4];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) xk[i] = Xs[12 * v + i];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) uk[c] = a.ubar ? Xs[24 + 4 * v + c] : model::kHover;
+        double* FA = Fs + (12 * v) * 24 + 12 * v;
+        double* FB = Fs + 576 + (12 * v) * 8 + 4 * v;
+        int e = 0;
+        model::quad_jac_discrete(
+            xk, uk, a.dt,
+            [&](int i, int j, double val) {
+              if (!model::quad_jac_is_const_A(i, j) && !model::dual_coupled_diag(i, j) && ((e++) & 7) == t8) FA[i * 24 + j] = val;
+            },
+            [&](int i, int j, double val) {
+              if (!model::quad_jac_is_const_B(i, j) && ((e++) & 7) == t8) FB[i * 8 + j] = val;
+            });
+      }
 
       double hacc[2] = {0.0, 0.0};
       if (MODE == RIC_AFFINE) {
@@ -240,6 +283,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
         hacc[0] = sa; hacc[1] = sb;
       }
 
+      if (FUSED) {
+        __syncwarp();  // the record is complete and every lane has consumed xbar_k, ubar_k
+        if (it + 1 < N) fetch(k - 1);
+      }
       // ---------------- phase 1: G[:,c] = P F[:,c], own two columns
       double g[24][2];
 #pragma unroll
@@ -308,7 +355,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
         }
       }
       __syncwarp();  // every lane is done with Fs (and Xs, Es, Vs)
-      if (it + 1 < N) fetch(k - 1);
+      if (!FUSED && it + 1 < N) fetch(k - 1);
 
       // ---------------- exchange: Hux columns (x-lanes) and Huu columns (u-lanes) -> shared
       {
