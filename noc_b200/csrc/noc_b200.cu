@@ -327,68 +327,62 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
   if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
   if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
-  // MODEL_QUAD12: the sweep linearises in-kernel (k_ric12<…, FUSED>), only the nominal trajectory is staged.
-  // MODEL_DUAL24: k_linearize writes the A_k,B_k stream into scratch.  Either way the batch is chunked so that
-  // the scratch stays within a share of the free HBM.
-  constexpr bool fused = true;   // both built-in models have the in-sweep linearisation (k_ric12 / k_ric24 <…, FUSED>)
+  // Both built-in models linearise inside the sweep (k_ric12 / k_ric24 <…, FUSED>): only the nominal trajectory is
+  // staged in scratch, no A_k,B_k stream exists.  Batch scheduler: an OUTER chunk bounds the scratch to a share of
+  // the free HBM and gets one rollout launch (latency-bound: one launch for everything costs as much as one for a
+  // quarter); with host-resident outputs it is cut into INNER chunks so that the device->host copy of chunk i runs
+  // on the copy stream under the sweep of chunk i+1.
   size_t free_b = 0, total_b = 0;
   NOC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   size_t have = 0;
-  if (ctx->scratch.size() > SCR_AB) have = ctx->scratch[SCR_AB].cap;
-  if (ctx->scratch.size() > SCR_XBAR) have += ctx->scratch[SCR_XBAR].cap;
+  if (ctx->scratch.size() > SCR_XBAR) have = ctx->scratch[SCR_XBAR].cap;
   const size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
-  const size_t per_inst = sizeof(double) * ((fused ? 0 : N * rec) + (N + 1) * n);
-  size_t chunk = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
-  // batch scheduler: with host-resident outputs a large batch is cut into (at least) four chunks so that the
-  // device->host copy of chunk i runs on the copy stream under the kernels of chunk i+1
+  const size_t per_inst = sizeof(double) * (N + 1) * n;
+  size_t outer = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
+  if (outer < B) outer = std::max<size_t>(32, outer & ~size_t(31));
   const bool overlap = !ctx->pending.empty() && B >= 8192 && !(p->flags & NOC_FLAG_ASYNC);
-  if (overlap) chunk = std::min(chunk, (B / 4 + 31) & ~size_t(31));
-  if (chunk < B) chunk = std::max<size_t>(8, chunk & ~size_t(7));
-  void *dxbar = nullptr, *dAB = nullptr;
-  if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * chunk * (N + 1) * n, &dxbar))) return rc;
-  if (!fused && (rc = scratch(ctx, SCR_AB, sizeof(double) * chunk * N * rec, &dAB))) return rc;
-  noc_problem_t q = *p;
-  q.layout = NOC_LAYOUT_A_THEN_B;
+  const size_t inner_pref = overlap ? ((B / 4 + 31) & ~size_t(31)) : outer;
+  void* dxbar = nullptr;
+  if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * outer * (N + 1) * n, &dxbar))) return rc;
+  (void)rec;
   typename std::conditional<MODEL == 0, Ric12Args, Ric24Args>::type fa{};
   if (MODEL == 0) rc = build_w12(ctx, (const double*)dQ, false, &fa.W, &fa.Qf);
   else rc = build_w24(ctx, (const double*)dQ, &fa.W, &fa.Qf);
   if (rc) { ctx->pending.clear(); return rc; }
-  for (size_t off = 0; off < B; off += chunk) {
-    const long long cb = (long long)std::min(chunk, B - off);
-    const double* x0c = (const double*)dx0 + off * n;
+  int chunk_no = 0;
+  for (size_t o = 0; o < B; o += outer) {
+    const size_t ob = std::min(outer, B - o);
     {
       LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
-      k_rollout_open_loop<MODEL><<<(unsigned)((cb + 127) / 128), 128, 0, ctx->stream>>>(x0c, nullptr, (double*)dxbar, cb, p->N, p->dt);
+      k_rollout_open_loop<MODEL><<<(unsigned)((ob + 127) / 128), 128, 0, ctx->stream>>>(
+          (const double*)dx0 + o * n, nullptr, (double*)dxbar, (long long)ob, p->N, p->dt, (long long)n, (long long)(ob * n));
     }
     NOC_CUDA(ctx, cudaGetLastError());
-    double* Kc = dK ? (double*)dK + off * N * m * n : nullptr;
-    double* K0c = dK0 ? (double*)dK0 + off * m * n : nullptr;
-    double* P0c = dP0 ? (double*)dP0 + off * n * n : nullptr;
-    double* cc = dcost ? (double*)dcost + off : nullptr;
-    int32_t* sc = dstatus ? (int32_t*)dstatus + off : nullptr;
-    if constexpr (fused) {
-      fa.xbar = (const double*)dxbar; fa.ubar = nullptr; fa.dt = p->dt; fa.x0 = x0c;
-      fa.K = Kc; fa.K0 = K0c; fa.P0 = P0c; fa.cost = cc; fa.status = sc; fa.batch = cb; fa.N = p->N;
+    const size_t inner = std::min(ob, inner_pref);
+    for (size_t i = 0; i < ob; i += inner, ++chunk_no) {
+      const size_t off = o + i;
+      const long long cb = (long long)std::min(inner, ob - i);
+      fa.xbar = (const double*)dxbar + i * n; fa.xbar_sb = (long long)n; fa.xbar_sk = (long long)(ob * n);   // step-major scratch
+      fa.ubar = nullptr; fa.dt = p->dt;
+      fa.x0 = (const double*)dx0 + off * n;
+      fa.K = dK ? (double*)dK + off * N * m * n : nullptr;
+      fa.K0 = dK0 ? (double*)dK0 + off * m * n : nullptr;
+      fa.P0 = dP0 ? (double*)dP0 + off * n * n : nullptr;
+      fa.cost = dcost ? (double*)dcost + off : nullptr;
+      fa.status = dstatus ? (int32_t*)dstatus + off : nullptr;
+      fa.batch = cb; fa.N = p->N;
       if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_LQR, true>(ctx, fa);
       else rc = launch_ric24<0, RIC_LQR, true>(ctx, fa);
-    } else {
-      const long long total = cb * p->N;
-      {
-        LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
-        k_linearize<MODEL><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, nullptr, (double*)dAB, cb, p->N, p->dt, q.layout, nullptr);
-      }
-      NOC_CUDA(ctx, cudaGetLastError());
-      rc = lqr24_device(ctx, &q, cb, (const double*)dAB, (const double*)dQ, x0c, Kc, K0c, P0c, cc, sc);
-    }
-    if (rc) { ctx->pending.clear(); return rc; }
-    if (overlap) {
-      cudaEvent_t ev = ctx->chunk_ev[(off / chunk) & 3];
-      NOC_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
-      NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
-      for (auto& c : ctx->pending) {
-        const size_t per = c.bytes / B;   // every output is [batch][...]
-        NOC_CUDA(ctx, cudaMemcpyAsync((char*)c.host + off * per, (const char*)c.dev + off * per, (size_t)cb * per,
-                                      cudaMemcpyDeviceToHost, ctx->copy_stream));
+      if (rc) { ctx->pending.clear(); return rc; }
+      if (overlap) {
+        cudaEvent_t ev = ctx->chunk_ev[chunk_no & 3];
+        NOC_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+        NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
+        for (auto& c : ctx->pending) {
+          const size_t per = c.bytes / B;   // every output is [batch][...]
+          NOC_CUDA(ctx, cudaMemcpyAsync((char*)c.host + off * per, (const char*)c.dev + off * per, (size_t)cb * per,
+                                        cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
       }
     }
   }
@@ -686,9 +680,11 @@ int noc_rollout_open_loop(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
   {
     LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
     if (p->model == NOC_MODEL_QUAD12)
-      k_rollout_open_loop<0><<<grid, 128, 0, ctx->stream>>>((const double*)dx0, (const double*)du, (double*)dx, batch, p->N, p->dt);
+      k_rollout_open_loop<0><<<grid, 128, 0, ctx->stream>>>((const double*)dx0, (const double*)du, (double*)dx, batch, p->N, p->dt,
+                                                  (long long)(p->N + 1) * p->n, (long long)p->n);
     else
-      k_rollout_open_loop<1><<<grid, 128, 0, ctx->stream>>>((const double*)dx0, (const double*)du, (double*)dx, batch, p->N, p->dt);
+      k_rollout_open_loop<1><<<grid, 128, 0, ctx->stream>>>((const double*)dx0, (const double*)du, (double*)dx, batch, p->N, p->dt,
+                                                  (long long)(p->N + 1) * p->n, (long long)p->n);
   }
   NOC_CUDA(ctx, cudaGetLastError());
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);

@@ -13,7 +13,7 @@ template <int MODEL>
 __global__ void __launch_bounds__(128) k_rollout_open_loop(const double* __restrict__ x0,
                                                            const double* __restrict__ ubar,  // may be null
                                                            double* __restrict__ xbar, long long batch, int N,
-                                                           double dt) {
+                                                           double dt, long long xsb, long long xsk) {
   constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= batch) return;
@@ -22,7 +22,10 @@ __global__ void __launch_bounds__(128) k_rollout_open_loop(const double* __restr
   for (int i = 0; i < n; ++i) x[i] = x0[b * n + i];
 #pragma unroll
   for (int j = 0; j < m; ++j) u[j] = model::kHover;
-  double* out = xbar + (size_t)b * (N + 1) * n;
+  // x_k of instance b goes to xbar + b*xsb + k*xsk (doubles).  Dense instance-major: xsb=(N+1)*n, xsk=n.  The
+  // library's internal scratch is step-major (xsb=n, xsk=batch*n): consecutive threads write consecutive 96-byte
+  // segments, so the stores coalesce and the sweep later reads one contiguous slab per step.
+  double* out = xbar + (size_t)b * xsb;
 #pragma unroll
   for (int i = 0; i < n; ++i) out[i] = x[i];
   for (int k = 0; k < N; ++k) {
@@ -32,7 +35,7 @@ __global__ void __launch_bounds__(128) k_rollout_open_loop(const double* __restr
     }
     model::model_step<MODEL>(x, u, dt, xn);
 #pragma unroll
-    for (int i = 0; i < n; ++i) { x[i] = xn[i]; out[(size_t)(k + 1) * n + i] = xn[i]; }
+    for (int i = 0; i < n; ++i) { x[i] = xn[i]; out[(size_t)(k + 1) * xsk + i] = xn[i]; }
   }
 }
 

@@ -48,7 +48,8 @@ struct Ric24Args {
   double* cost;          // [batch] or nullptr
   int32_t* status;       // [batch] or nullptr
   const int32_t* idx;    // RIC_AFFINE work list or nullptr
-  const double* xbar;    // [batch][N+1][24]
+  const double* xbar;    // nominal states: x_k of instance b at xbar + b*xbar_sb + k*xbar_sk ([batch][N+1][24] when 0/0)
+  long long xbar_sb, xbar_sk;   // strides in doubles; 0 = the dense instance-major layout
   const double* ubar;    // [batch][N][8]
   const double* xgoal;   // [batch][24]
   double dt;             // FUSED: Euler step of the built-in model
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
   const unsigned fs_u32 = smem_u32(Fs);
   unsigned phase = 0;
 
+  const size_t xsb = a.xbar_sb ? (size_t)a.xbar_sb : (size_t)(N + 1) * 24, xsk = a.xbar_sk ? (size_t)a.xbar_sk : 24;
   auto fetch = [&](int k) {
     if (!FUSED) {
       if (lane == 0) mbar_expect_tx(bar, 2u * 6144u);
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
     }
     if (FUSED || MODE == RIC_AFFINE) {
       // xbar_k (192 B) | ubar_k (64 B, optional): sixteen 16-byte chunks, one per lane
-      const double* xs = a.xbar + ((size_t)b * (N + 1) + k) * 24;
+      const double* xs = a.xbar + (size_t)b * xsb + (size_t)k * xsk;
       if (t < 12) cp_async16(smem_u32(base + R24_XS + 2 * t), xs + 2 * t);
       else if (a.ubar) cp_async16(smem_u32(base + R24_XS + 24 + 2 * (t - 12)), a.ubar + ((size_t)b * N + k) * 8 + 2 * (t - 12));
       cp_async_commit();
@@ -223,7 +225,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
       // xgoal -> shared; Vx <- Qf (xbar_N - xgoal): lane t computes rows t and t+16 (<24)
       for (int i = t; i < 24; i += 16) base[R24_XG + i] = a.xgoal[(size_t)b * 24 + i];
       __syncwarp();
-      const double* xN = a.xbar + ((size_t)b * (N + 1) + N) * 24;
+      const double* xN = a.xbar + (size_t)b * xsb + (size_t)N * xsk;
       for (int r = t; r < 24; r += 16) {
         double s = 0.0;
         for (int j = 0; j < 24; ++j) s = fmad(Qfs[r * 24 + j], xN[j] - base[R24_XG + j], s);
