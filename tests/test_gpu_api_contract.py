@@ -1,0 +1,123 @@
+"""C-ABI contract on a GPU: error codes instead of crashes, empty and degenerate shapes, optional outputs,
+host/device pointer mixing, determinism.  (errors are return codes, per-instance outcomes go to
+status[].)"""
+import numpy as np
+import pytest
+
+from noc_b200 import problems as pb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def solver():
+    from noc_b200 import capi
+    s = capi.Solver(0)
+    yield s
+    s.close()
+
+
+def _qr():
+    return pb.pack_qrqf(*pb.default_weights())
+
+
+def test_empty_batch_is_ok(solver):
+    from noc_b200 import capi
+    e = np.empty(0)
+    solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5), 0, np.empty((0, 5, 192)), _qr(), K=np.empty((0, 5, 4, 12)))
+    solver.lqr_solve_from_x0(capi.problem(0, 5), 0, np.empty((0, 12)), _qr(), cost=e)
+    solver.slq_solve_batch(capi.problem(0, 5), 0, np.empty((0, 12)), np.empty((0, 12)), _qr(), cost=e)
+    solver.dare_solve_batch(capi.problem(capi.MODEL_LTV_USER, 1), 0, np.empty((0, 192)), _qr()[:160], np.empty((0, 144)),
+                            np.empty((0, 48)), np.empty(0, dtype=np.int32), np.empty(0, dtype=np.int32))
+
+
+def test_bad_arguments_return_codes(solver):
+    from noc_b200 import capi
+    x0 = pb.sample_x0(4, seed=1)
+    with pytest.raises(capi.NocError) as e:
+        solver.lqr_solve_from_x0(capi.problem(0, 5), 4, None, _qr())
+    assert e.value.code == capi.ERR_BAD_ARG
+    with pytest.raises(capi.NocError) as e:
+        solver.lqr_solve_from_x0(capi.problem(0, 0), 4, x0, _qr())            # horizon 0
+    assert e.value.code == capi.ERR_BAD_ARG
+    with pytest.raises(capi.NocError) as e:
+        solver.lqr_solve_from_x0(capi.problem(0, 5, n=10), 4, x0, _qr())       # model / dims mismatch
+    assert e.value.code == capi.ERR_BAD_ARG
+    with pytest.raises(capi.NocError) as e:
+        solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5, n=6, m=2), 4, np.zeros((4, 5, 48)), _qr())
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    with pytest.raises(capi.NocError) as e:
+        solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5), 4, np.zeros((4, 5, 192)), _qr(), qr_per_instance=True)
+    assert e.value.code == capi.ERR_UNSUPPORTED
+    with pytest.raises(capi.NocError) as e:
+        solver.slq_solve_batch(capi.problem(0, 5, n_alpha=40), 4, x0, x0, _qr())
+    assert e.value.code == capi.ERR_BAD_ARG
+    with pytest.raises(capi.NocError) as e:
+        solver.slq_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5), 4, x0, x0, _qr())
+    assert e.value.code == capi.ERR_BAD_ARG
+    with pytest.raises(capi.NocError) as e:
+        solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5, layout=7), 4, np.zeros((4, 5, 192)), _qr())
+    assert e.value.code == capi.ERR_BAD_ARG
+    # the context is still usable after errors
+    cost = np.empty(4)
+    solver.lqr_solve_from_x0(capi.problem(0, 5), 4, x0, _qr(), cost=cost)
+    assert np.all(np.isfinite(cost))
+
+
+def test_misaligned_device_records_are_rejected(solver):
+    import torch
+    from noc_b200 import capi
+    buf = torch.zeros(4 * 5 * 192 + 1, dtype=torch.float64, device="cuda")
+    with pytest.raises(capi.NocError) as e:
+        solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5), 4, buf[1:], torch.from_numpy(_qr()).cuda(),
+                               K0=torch.empty(4, 48, dtype=torch.float64, device="cuda"))
+    assert e.value.code == capi.ERR_BAD_ARG
+
+
+def test_horizon_one_and_single_instance(oracle, solver):
+    from noc_b200 import capi
+    qr = _qr()
+    x0 = pb.sample_x0(1, seed=2)
+    ref = oracle.lqr_from_x0_batch(0, 1, 0.02, x0, qr)
+    K0 = np.empty((1, 4, 12)); P0 = np.empty((1, 12, 12)); cost = np.empty(1)
+    solver.lqr_solve_from_x0(capi.problem(0, 1), 1, x0, qr, K0=K0, P0=P0, cost=cost)
+    assert np.array_equal(K0, ref["K0"]) and np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
+    xg = pb.sample_goals(3, seed=3)
+    xs = pb.hover_state(3)
+    for N in (1, 2):
+        c = np.empty(3); it = np.zeros(3, dtype=np.int32); st = np.zeros(3, dtype=np.int32)
+        solver.slq_solve_batch(capi.problem(0, N), 3, xs, xg, qr, cost=c, iters=it, status=st)
+        r = oracle.slq_batch(oracle.slq_opts(0, N), xs, xg, qr, want_traj=False)
+        assert np.array_equal(c, r["cost"]) and np.array_equal(it, r["iters"]) and np.array_equal(st, r["status"])
+
+
+def test_mixed_host_and_device_pointers_and_async(oracle, solver):
+    import torch
+    from noc_b200 import capi
+    batch, N = 40, 16
+    qr = _qr()
+    x0 = pb.sample_x0(batch, seed=4)
+    ref = oracle.lqr_from_x0_batch(0, N, 0.02, x0, qr)
+    d_x0 = torch.from_numpy(x0).cuda()
+    K0 = np.empty((batch, 4, 12))                      # host output
+    d_cost = torch.empty(batch, dtype=torch.float64, device="cuda")   # device output
+    solver.lqr_solve_from_x0(capi.problem(0, N), batch, d_x0, qr, K0=K0, cost=d_cost)
+    assert np.array_equal(K0, ref["K0"]) and np.array_equal(d_cost.cpu().numpy(), ref["cost"])
+    # async flag with device pointers only: returns before completion, noc_synchronize() finishes it
+    d_K0 = torch.empty(batch, 4, 12, dtype=torch.float64, device="cuda")
+    d_qr = torch.from_numpy(qr).cuda()
+    solver.lqr_solve_from_x0(capi.problem(0, N, flags=capi.FLAG_ASYNC), batch, d_x0, d_qr, K0=d_K0, cost=d_cost)
+    solver.synchronize()
+    assert np.array_equal(d_K0.cpu().numpy(), ref["K0"])
+
+
+def test_per_kernel_profile_counters(solver):
+    from noc_b200 import capi
+    x0 = pb.sample_x0(64, seed=5)
+    solver.profile_reset(); solver.profile_enable(True)
+    n0 = solver.launch_count
+    solver.lqr_solve_from_x0(capi.problem(0, 10), 64, x0, _qr(), cost=np.empty(64))
+    solver.profile_enable(False)
+    ms, cnt = solver.profile_read(capi.KERNEL_RICCATI)
+    assert cnt == 1 and ms > 0 and solver.launch_count - n0 == 3      # rollout, weight packing, fused sweep
+    assert solver.profile_read(capi.KERNEL_LINEARIZE)[1] == 0          # linearisation is fused into the sweep
