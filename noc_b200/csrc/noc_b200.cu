@@ -151,7 +151,7 @@ int scratch(noc_ctx* ctx, int slot, size_t bytes, void** out) {
 }
 
 enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
-       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC };
+       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC, SCR_FLAGS };
 
 // W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
 // Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
@@ -434,8 +434,10 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   if ((rc = scratch(ctx, SCR_RETRY1, sizeof(int32_t) * B, &dretry1))) return rc;
   if ((rc = scratch(ctx, SCR_XN, sizeof(double) * B * (N + 1) * n, &dxn))) return rc;
   if ((rc = scratch(ctx, SCR_UN, sizeof(double) * B * N * m, &dun))) return rc;
-  void* dlc;
+  void *dlc, *dflags;
   if ((rc = scratch(ctx, SCR_LC, sizeof(double) * B * (N + 1), &dlc))) return rc;
+  if ((rc = scratch(ctx, SCR_FLAGS, sizeof(int32_t) * B, &dflags))) return rc;
+  NOC_CUDA(ctx, cudaMemsetAsync(dflags, 0, sizeof(int32_t) * B, ctx->stream));
   using FC = FwdCfg<MODEL>;
   const size_t fwd_smem = FC::ring_bytes;
   {
@@ -472,9 +474,8 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
     if (rc) { ctx->pending.clear(); return rc; }
     // a4: closed-loop rollouts with backtracking, acceptance, convergence, next work list.  One launch per step
     // length: trial 0 on the whole list, trial j+1 only on the instances whose trial j was rejected.
-    NOC_CUDA(ctx, cudaMemsetAsync(dcount, 0, 8, ctx->stream));
     SlqFwdArgs fa{};
-    fa.next_idx = nxt; fa.next_count = (int32_t*)dcount; fa.retry_count = (int32_t*)dcount + 1;
+    fa.flags = (int32_t*)dflags;
     fa.xgoal = (const double*)dxg;
     fa.qrqf = (const double*)dQ; fa.x = (double*)dx; fa.u = (double*)du; fa.xn = (double*)dxn; fa.un = (double*)dun;
     fa.K = (const double*)dK;
@@ -489,7 +490,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
     int32_t* rin = (int32_t*)dretry0;
     int32_t* rout = (int32_t*)dretry1;
     for (int trial = 0; trial < p->n_alpha && list_count > 0; ++trial) {
-      fa.idx = list; fa.count = list_count; fa.trial = trial; fa.retry_idx = rin;
+      fa.idx = list; fa.count = list_count; fa.trial = trial;
       {
         LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
         k_slq_rollout<MODEL><<<(unsigned)((list_count + FC::threads - 1) / FC::threads), FC::threads, fwd_smem, ctx->stream>>>(fa);
@@ -506,12 +507,23 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
         k_slq_accept<MODEL><<<(unsigned)((list_count + 127) / 128), 128, 0, ctx->stream>>>(fa);
       }
       NOC_CUDA(ctx, cudaGetLastError());
-      NOC_CUDA(ctx, cudaMemcpyAsync(hc, dcount, 8, cudaMemcpyDeviceToHost, ctx->stream));
+      {  // rejected trials -> sorted retry list
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_compact_flags<<<1, 1024, 0, ctx->stream>>>((int32_t*)dflags, 2, batch, rin, (int32_t*)dcount + 1);
+      }
+      NOC_CUDA(ctx, cudaGetLastError());
+      NOC_CUDA(ctx, cudaMemcpyAsync(hc + 1, (int32_t*)dcount + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
       NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       list = rin; list_count = hc[1];
       std::swap(rin, rout);
-      if (list_count > 0) NOC_CUDA(ctx, cudaMemsetAsync((int32_t*)dcount + 1, 0, 4, ctx->stream));
     }
+    {  // instances that go on to the next iteration -> sorted work list
+      LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+      k_compact_flags<<<1, 1024, 0, ctx->stream>>>((int32_t*)dflags, 1, batch, nxt, (int32_t*)dcount);
+    }
+    NOC_CUDA(ctx, cudaGetLastError());
+    NOC_CUDA(ctx, cudaMemcpyAsync(hc, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     count = hc[0];
     std::swap(cur, nxt);
   }

@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(128) k_slq_init(const double* __restrict__ x0,
 
 struct SlqFwdArgs {
   const int32_t* idx;       // [count] active instances
-  int32_t* next_idx;        // compacted list of the instances that continue
-  int32_t* next_count;      // atomic counter (zeroed by the host at the start of the SLQ iteration)
-  int32_t* retry_idx;       // instances whose trial was rejected: the host launches the next step length on them
-  int32_t* retry_count;     // atomic counter (zeroed by the host before every launch)
+  int32_t* flags;           // [batch] bit 0: continues with the next SLQ iteration; bit 1: trial rejected, try the next
+                            // step length.  k_compact_flags turns the bits into SORTED work lists: a list in
+                            // instance order keeps the per-instance streams of a warp at a regular stride (an
+                            // atomicAdd-ordered list made the full-size rollouts 1.6x slower).
   int trial;                // j of this launch: alpha = 2^-j for every instance of the work list
   const double* xgoal;      // [batch][n]
   const double* qrqf;
@@ -317,8 +317,7 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
   const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
   if (!(Jold - Jacc >= a.armijo * expected)) {
     if (a.trial + 1 < a.n_alpha) {   // next step length, next launch
-      const int pos = atomicAdd(a.retry_count, 1);
-      a.retry_idx[pos] = (int32_t)b;
+      a.flags[b] |= 2;
       return;
     }
     // no step length passed: put the nominal back (oracle: x, u unchanged) and stop this instance
@@ -344,9 +343,62 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
     return;
   }
   if (a.iter + 1 < a.max_iter) {
-    const int pos = atomicAdd(a.next_count, 1);
-    a.next_idx[pos] = (int32_t)b;
+    a.flags[b] |= 1;
   }
+}
+
+// Ordered stream compaction of one flag bit: out = ascending list of the i < n with flags[i] & mask, the bit is
+// cleared, *out_count = length.  Single CTA (work lists are at most a few hundred thousand entries).
+__global__ void __launch_bounds__(1024) k_compact_flags(int32_t* __restrict__ flags, int mask, long long n,
+                                                        int32_t* __restrict__ out, int32_t* __restrict__ out_count) {
+  constexpr int ITEMS = 8;
+  __shared__ int warp_sums[32];
+  __shared__ int round_total;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int base = 0;
+  for (long long start = 0; start < n; start += 1024 * ITEMS) {
+    const long long i0 = start + (long long)threadIdx.x * ITEMS;
+    bool f[ITEMS];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) {
+      const long long i = i0 + j;
+      f[j] = false;
+      if (i < n) {
+        const int v = flags[i];
+        f[j] = (v & mask) != 0;
+        if (f[j]) flags[i] = v & ~mask;
+      }
+      cnt += f[j] ? 1 : 0;
+    }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sums[lane];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, wi, o);
+        if (lane >= o) wi += v;
+      }
+      warp_sums[lane] = wi - w;   // exclusive prefix of the warp totals
+      if (lane == 31) round_total = wi;
+    }
+    __syncthreads();
+    int pos = base + warp_sums[wid] + incl - cnt;
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j)
+      if (f[j]) out[pos++] = (int32_t)(i0 + j);
+    base += round_total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out_count = base;
 }
 
 }  // namespace noc
