@@ -15,19 +15,42 @@ __global__ void __launch_bounds__(128) k_rollout_open_loop(const double* __restr
                                                            double* __restrict__ xbar, long long batch, int N,
                                                            double dt, long long xsb, long long xsk) {
   constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
-  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= batch) return;
+  constexpr int LD = n + 1;                         // padded row of the transpose tile (odd stride: no bank conflicts)
+  __shared__ __align__(16) double tile[4][32 * LD];
+  const long long b_raw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = b_raw < batch;
+  const long long b = active ? b_raw : batch - 1;
+  const int lane = threadIdx.x & 31;
+  double* tl = tile[threadIdx.x >> 5];
   double x[n], xn[n], u[m];
 #pragma unroll
   for (int i = 0; i < n; ++i) x[i] = x0[b * n + i];
 #pragma unroll
   for (int j = 0; j < m; ++j) u[j] = model::kHover;
-  // x_k of instance b goes to xbar + b*xsb + k*xsk (doubles).  Dense instance-major: xsb=(N+1)*n, xsk=n.  The
-  // library's internal scratch is step-major (xsb=n, xsk=batch*n): consecutive threads write consecutive 96-byte
-  // segments, so the stores coalesce and the sweep later reads one contiguous slab per step.
-  double* out = xbar + (size_t)b * xsb;
+  // x_k of instance b goes to xbar + b*xsb + k*xsk (doubles).  Dense instance-major: xsb=(N+1)*n, xsk=n: every
+  // thread stores its own segments.  The library's internal scratch is step-major (xsb=n, xsk=batch*n): the 32
+  // states of a warp are contiguous, so they are transposed through shared memory and written as 512-byte rows
+  // (thread-private stores touched 32 sectors per instruction and made the LSU the rollout's bottleneck).
+  const bool step_major = (xsb == n);
+  const long long wb0 = b_raw - lane;              // first instance of this warp
+  const int wcount = (int)((batch - wb0 < 32) ? (batch - wb0 > 0 ? batch - wb0 : 0) : 32);
+  auto emit = [&](int k, const double* v) {
+    if (!step_major) {
+      if (active) {
+        double* o = xbar + (size_t)b * xsb + (size_t)k * xsk;
 #pragma unroll
-  for (int i = 0; i < n; ++i) out[i] = x[i];
+        for (int i = 0; i < n; ++i) o[i] = v[i];
+      }
+      return;
+    }
+#pragma unroll
+    for (int i = 0; i < n; ++i) tl[lane * LD + i] = v[i];
+    __syncwarp();
+    double* o = xbar + (size_t)wb0 * n + (size_t)k * xsk;   // wcount * n contiguous doubles
+    for (int e = lane; e < wcount * n; e += 32) o[e] = tl[(e / n) * LD + (e % n)];
+    __syncwarp();
+  };
+  emit(0, x);
   for (int k = 0; k < N; ++k) {
     if (ubar) {
 #pragma unroll
@@ -35,7 +58,8 @@ __global__ void __launch_bounds__(128) k_rollout_open_loop(const double* __restr
     }
     model::model_step<MODEL>(x, u, dt, xn);
 #pragma unroll
-    for (int i = 0; i < n; ++i) { x[i] = xn[i]; out[(size_t)(k + 1) * xsk + i] = xn[i]; }
+    for (int i = 0; i < n; ++i) x[i] = xn[i];
+    emit(k + 1, x);
   }
 }
 
