@@ -403,7 +403,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="noc", choices=["noc", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU (default: config 2)")
-    ap.add_argument("--cpu-sample", type=int, default=16384)
+    ap.add_argument("--cpu-sample", type=int, default=32768)
     ap.add_argument("--ref-sample", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
