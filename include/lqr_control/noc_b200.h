@@ -114,7 +114,8 @@ void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N);
 
 /* ---- SURVEY §8(a) a2+a3: backward Riccati recursion, Cholesky, gains -------------------------
  * Finite-horizon LTV LQR sweep for `batch` independent instances.
- *   AB        [batch][N][n*n+n*m]   A_k,B_k records (prob->layout)
+ *   AB        [batch][N][n*n+n*m]   A_k,B_k records (prob->layout); (n,m) = (12,4) or (24,8); a device pointer
+ *                                   must be 16-byte aligned (the records are fetched by TMA bulk copies)
  *   QRQf      [n*n + m*m + n*n]     Q, R, Qf shared by the batch, or [batch][...] if qr_per_instance
  *   x0dev     [batch][n] or NULL    initial deviation; needed only for `cost`
  *   K         [batch][N][m*n] or NULL   feedback gains u = K x
@@ -135,8 +136,10 @@ int noc_rollout_open_loop(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch
                           const double* ubar, double* xbar);
 
 /* ---- configs 2 / 4 end to end: x0 -> hover-thrust nominal -> linearise -> sweep -----------------
- * Same outputs as noc_lqr_solve_batch; x0dev = x0 (goal = origin).  The A_k,B_k stream lives in
- * library scratch (chunked to the free HBM) and never crosses PCIe.                                  */
+ * Same outputs as noc_lqr_solve_batch; x0dev = x0 (goal = origin).  The linearisation is fused into the
+ * sweep: no A_k,B_k stream is materialised, only the nominal trajectory is staged in library scratch (chunked
+ * to the free HBM).  With host output pointers and batch >= 8192 the batch is processed in chunks whose
+ * device->host copies overlap the next chunk's kernels.  Device output pointers must be 16-byte aligned.  */
 int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* x0,
                           const double* QRQf, double* K, double* K0, double* P0, double* cost,
                           int32_t* status);
