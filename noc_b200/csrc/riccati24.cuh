@@ -312,8 +312,49 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
         }
       }
 
-      // ---------------- phase 2: H[i][c] = W[i][c] + sum_l F[l][i] G[l][c]
-      double hA[12], hB[24], huA[8], huB[8];
+      // ---------------- phase 2a: the eight u-rows of H = W + F^T G for the own columns (Hux for x-lanes, Huu for
+      // u-lanes).  A separate pass with its own 16 accumulators: together with the 36 Hxx accumulators and the 48
+      // G values the single-pass version needed 200+ registers and spilled (ncu: long-scoreboard stalls on local
+      // loads, profiles/ncu_r01_k_ric24_v1.txt).  The results go to shared memory at once and are re-read as the
+      // right-hand sides of the gain solves.
+      {
+        double huA[8], huB[8];
+        const double* wa = Ws + cA * R24_WLD + 24;
+        const double* wb = Ws + cB * R24_WLD + 24;
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const double2 va = lds128(wa + i);
+          const double2 vb = lds128(wb + i);
+          huA[i] = va.x; huA[i + 1] = va.y; huB[i] = vb.x; huB[i + 1] = vb.y;
+        }
+#pragma unroll
+        for (int l = 0; l < 24; ++l) {
+          const double ga = g[l][0], gb = g[l][1];
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) {
+            const double2 v = lds128(Fs + r24_foff<LAYOUT>(l, 24 + c));
+            huA[c] = fmad(v.x, ga, huA[c]); huA[c + 1] = fmad(v.y, ga, huA[c + 1]);
+            huB[c] = fmad(v.x, gb, huB[c]); huB[c + 1] = fmad(v.y, gb, huB[c + 1]);
+          }
+        }
+        if (MODE == RIC_AFFINE && !xl) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            if (c == uA) huA[c] = huA[c] + mu;
+            if (c == uB) huB[c] = huB[c] + mu;
+          }
+        }
+        // exchange: Hux columns (x-lanes) and Huu columns (u-lanes) -> shared
+        double* dA = xl ? Hs + jA : Us + uA;
+        double* dB = xl ? Hs + jB : Us + uB;
+        const int ds = xl ? 24 : 8;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { dA[c * ds] = huA[c]; dB[c * ds] = huB[c]; }
+        if (MODE == RIC_AFFINE && !xl) { base[R24_HU + uA] = hacc[0]; base[R24_HU + uB] = hacc[1]; }
+      }
+
+      // ---------------- phase 2b: Hxx rows of the own x-columns
+      double hA[12], hB[24];
       {
         const double* wa = Ws + cA * R24_WLD;
         const double* wb = Ws + cB * R24_WLD;
@@ -321,12 +362,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
         for (int i = 0; i < 12; i += 2) { const double2 v = lds128(wa + i); hA[i] = v.x; hA[i + 1] = v.y; }
 #pragma unroll
         for (int i = 0; i < 24; i += 2) { const double2 v = lds128(wb + i); hB[i] = v.x; hB[i + 1] = v.y; }
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const double2 va = lds128(wa + 24 + i);
-          const double2 vb = lds128(wb + 24 + i);
-          huA[i] = va.x; huA[i + 1] = va.y; huB[i] = vb.x; huB[i + 1] = vb.y;
-        }
       }
 #pragma unroll
       for (int l = 0; l < 24; ++l) {
@@ -342,40 +377,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
           const double2 v = lds128(Fs + r24_foff<LAYOUT>(l, i));
           hB[i] = fmad(v.x, gb, hB[i]); hB[i + 1] = fmad(v.y, gb, hB[i + 1]);
         }
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          const double2 v = lds128(Fs + r24_foff<LAYOUT>(l, 24 + c));
-          huA[c] = fmad(v.x, ga, huA[c]); huA[c + 1] = fmad(v.y, ga, huA[c + 1]);
-          huB[c] = fmad(v.x, gb, huB[c]); huB[c + 1] = fmad(v.y, gb, huB[c + 1]);
-        }
       }
-      if (MODE == RIC_AFFINE && !xl) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          if (c == uA) huA[c] = huA[c] + mu;
-          if (c == uB) huB[c] = huB[c] + mu;
-        }
-      }
-      __syncwarp();  // every lane is done with Fs (and Xs, Es, Vs)
+      __syncwarp();  // every lane is done with Fs (and Xs, Es, Vs); the exchanged Hux / Huu are visible
       if (!FUSED && it + 1 < N) fetch(k - 1);
 
-      // ---------------- exchange: Hux columns (x-lanes) and Huu columns (u-lanes) -> shared
-      {
-        double* dA = xl ? Hs + jA : Us + uA;
-        double* dB = xl ? Hs + jB : Us + uB;
-        const int ds = xl ? 24 : 8;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) { dA[c * ds] = huA[c]; dB[c * ds] = huB[c]; }
-        if (MODE == RIC_AFFINE && !xl) { base[R24_HU + uA] = hacc[0]; base[R24_HU + uB] = hacc[1]; }
-      }
-      __syncwarp();
-
-      // ---------------- phase 3: redundant 8x8 L D L^T, gains of the own x-columns
+      // ---------------- phase 3: redundant 8x8 L D L^T, gains of the own x-columns.  The right-hand sides are read
+      // back from shared memory one at a time, just before their solve, to keep the live register set small
+      // (x-lanes: their Hux columns; u-lanes solve dummies).
       LdlReg<8> ch;
       failed |= ch.factor(Us);
-      double kA[8], kB[8];
-      ch.solve_neg(huA, kA);
-      ch.solve_neg(huB, kB);
+      const double* sA = xl ? Hs + jA : Us + uA;
+      const double* sB = xl ? Hs + jB : Us + uB;
+      const int ds = xl ? 24 : 8;
       if (MODE == RIC_AFFINE) {
         double hur[8], kf[8];
 #pragma unroll
@@ -384,7 +397,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
         if (xl) {
           double sa = hacc[0], sb = hacc[1];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) { sa = fmad(huA[c], kf[c], sa); sb = fmad(huB[c], kf[c], sb); }
+          for (int c = 0; c < 8; ++c) { sa = fmad(sA[c * ds], kf[c], sa); sb = fmad(sB[c * ds], kf[c], sb); }
           base[R24_VS + jA] = sa;
           base[R24_VS + jB] = sb;
         }
@@ -406,6 +419,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
 #pragma unroll
           for (int c = 0; c < 8; c += 2) stg128_cs(fp + c, kf[c], kf[c + 1]);
         }
+      }
+      double kA[8], kB[8];
+      {
+        double rhs[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rhs[c] = sA[c * ds];
+        ch.solve_neg(rhs, kA);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) rhs[c] = sB[c * ds];
+        ch.solve_neg(rhs, kB);
       }
       if (failed && kfail < 0) kfail = k;
       if (Kp) {
