@@ -69,6 +69,18 @@ int main() {
     auto sbest = sh.solveFromInitialStates(B, x0.data(), sK0.data(), sP0.data(), scost.data(), sst.data());
     CHECK(same(sK0, rK0) && same(sP0, rP0) && same(scost, rcost) && sst == rst);
     CHECK(sbest.first == rb && sbest.second == rcost[rb]);
+    {  // a second GPU, when the box has one: two shards on two devices (one host thread each)
+      bool two = false;
+      try { Context probe(1); two = true; } catch (const NocError&) {}
+      if (two) {
+        ShardedBatchedLqr sh2({0, 1}, N);
+        std::vector<double> tK0(B * 48), tP0(B * 144), tcost(B);
+        std::vector<int32_t> tst(B, -1);
+        auto tbest = sh2.solveFromInitialStates(B, x0.data(), tK0.data(), tP0.data(), tcost.data(), tst.data());
+        CHECK(same(tK0, rK0) && same(tP0, rP0) && same(tcost, rcost) && tst == rst && tbest.first == rb);
+        std::printf("two-GPU shards OK\n");
+      }
+    }
     auto s0 = shardSlice(10, 0, 3), s1 = shardSlice(10, 1, 3), s2 = shardSlice(10, 2, 3);
     CHECK(s0.first == 0 && s0.second == 4 && s1.first == 4 && s1.second == 7 && s2.first == 7 && s2.second == 10);
   }
