@@ -206,12 +206,10 @@ template <int LAYOUT, int MODE, bool FUSED, int W, int MIN_CTAS>
 int launch_ric12_cfg(noc_ctx* ctx, const Ric12Args& a) {
   auto kern = k_ric12<LAYOUT, MODE, FUSED, W, MIN_CTAS>;
   const size_t smem = ric12_smem_bytes<MODE, FUSED>(W);
-  static bool attr_set = false;  // one flag per template instantiation
-  if (!attr_set) {
-    NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
-  }
+  // function attributes are per device and contexts may live on several devices / host threads: set them on every
+  // launch (two cheap driver calls) instead of caching a process-wide flag
+  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const long long per_cta = 8LL * W;
   const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
   {
@@ -243,12 +241,8 @@ int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
   constexpr int W = Ric24Cfg<MODE>::warps;
   auto kern = k_ric24<LAYOUT, MODE, FUSED, W>;
   const size_t smem = ric24_smem_bytes<MODE, FUSED>(W);
-  static bool attr_set = false;
-  if (!attr_set) {
-    NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    attr_set = true;
-  }
+  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const long long per_cta = 2LL * W;
   const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
   {
@@ -440,13 +434,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   NOC_CUDA(ctx, cudaMemsetAsync(dflags, 0, sizeof(int32_t) * B, ctx->stream));
   using FC = FwdCfg<MODEL>;
   const size_t fwd_smem = FC::ring_bytes;
-  {
-    static bool fwd_attr = false;
-    if (!fwd_attr) {
-      NOC_CUDA(ctx, cudaFuncSetAttribute(k_slq_rollout<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
-      fwd_attr = true;
-    }
-  }
+  NOC_CUDA(ctx, cudaFuncSetAttribute(k_slq_rollout<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
   const size_t wbytes = sizeof(double) * (2 * n * n + m * m);
   {
     LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
