@@ -236,9 +236,8 @@ int launch_ric12_layout(noc_ctx* ctx, int layout, const Ric12Args& a) {
 template <int MODE> struct Ric24Cfg { static constexpr int warps = 8; };
 template <> struct Ric24Cfg<RIC_AFFINE> { static constexpr int warps = 7; };
 
-template <int LAYOUT, int MODE, bool FUSED = false>
-int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
-  constexpr int W = Ric24Cfg<MODE>::warps;
+template <int LAYOUT, int MODE, bool FUSED, int W>
+int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a) {
   auto kern = k_ric24<LAYOUT, MODE, FUSED, W>;
   const size_t smem = ric24_smem_bytes<MODE, FUSED>(W);
   NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -251,6 +250,13 @@ int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
   }
   NOC_CUDA(ctx, cudaGetLastError());
   return NOC_OK;
+}
+
+template <int LAYOUT, int MODE, bool FUSED = false>
+int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
+  // short work lists: one warp (two instances) per CTA so that the latency-bound tail spreads over all SMs
+  if (a.batch <= 2LL * 2 * ctx->sm_count) return launch_ric24_cfg<LAYOUT, MODE, FUSED, 1>(ctx, a);
+  return launch_ric24_cfg<LAYOUT, MODE, FUSED, Ric24Cfg<MODE>::warps>(ctx, a);
 }
 
 // packs the weights for the n=24 kernels into scratch: W[1024] | Qf[576]
