@@ -2,8 +2,8 @@
 // at every control tick, solve a finite-horizon LQR around the hover-thrust nominal for a cloud of candidate
 // initial states (measurement uncertainty / warm starts), pick the best rollout and apply its first-step gain.
 // Build (after `make -C noc_b200/csrc`):
-//   g++ -std=c++17 -O2 -I include examples/mpc_candidates.cpp -L noc_b200 -lnoc_b200 \
-//       -Wl,-rpath,$PWD/noc_b200 -Wl,-rpath,/usr/local/cuda/lib64 -pthread -o examples/mpc_candidates
+//   g++ -std=c++17 -O2 -I include examples/mpc_candidates.cpp -L noc_b200 -lnoc_b200
+//     -Wl,-rpath,$PWD/noc_b200 -Wl,-rpath,/usr/local/cuda/lib64 -pthread -o examples/mpc_candidates
 #include <chrono>
 #include <cstdio>
 #include <random>
