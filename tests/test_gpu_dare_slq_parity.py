@@ -135,3 +135,20 @@ def test_slq_optional_outputs(oracle, solver):
     solver.slq_solve_batch(prob, batch, x0, xg, qr, cost=cost, iters=iters)
     ref = oracle.slq_batch(oracle.slq_opts(0, N), x0, xg, qr, want_traj=False)
     assert np.array_equal(cost, ref["cost"]) and np.array_equal(iters, ref["iters"])
+
+
+def test_slq_multiwarp_config_and_worklist_compaction(oracle, solver):
+    """A batch large enough for the 7-warp CTA configuration of the backward pass (> 2,368 instances); instances
+    converge at different iterations, so the sorted work-list compaction is exercised at scale."""
+    from noc_b200 import capi
+    batch, N = 3000, 24
+    qr = pb.pack_qrqf(*pb.default_weights())
+    xs = pb.hover_state(batch); xg = pb.sample_goals(batch, seed=17)
+    prob = capi.problem(0, N)
+    cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    aidx = np.zeros((batch, prob.max_iter), dtype=np.int32)
+    solver.slq_solve_batch(prob, batch, xs, xg, qr, cost=cost, iters=iters, alpha_idx=aidx, status=status)
+    ref = oracle.slq_batch(oracle.slq_opts(0, N), xs, xg, qr, want_traj=False)
+    assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
+    assert np.array_equal(aidx, ref["alpha_idx"]) and np.array_equal(cost, ref["cost"])
+    assert len(set(iters.tolist())) > 3

@@ -95,3 +95,37 @@ def test_slq_dual24_bitexact(oracle, solver, kw):
     assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
     assert np.array_equal(aidx, ref["alpha_idx"]) and np.array_equal(cost, ref["cost"])
     assert np.array_equal(x, ref["x"]) and np.array_equal(u, ref["u"]) and np.array_equal(K, ref["K"])
+
+
+def test_lqr24_multiwarp_config_bitexact(oracle, solver):
+    """Batches above 2 x 2 x SM-count use the 8-warp CTA configuration of k_ric24 (smaller ones one warp per CTA)."""
+    from noc_b200 import capi
+    batch, N = 1500, 12
+    Q, R, Qf = pb.default_weights(M)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(batch, seed=91, model=M)
+    ref = oracle.lqr_from_x0_batch(M, N, 0.02, x0, qr)
+    K0 = np.empty((batch, 8, 24)); P0 = np.empty((batch, 24, 24)); cost = np.empty(batch)
+    status = np.full(batch, -1, dtype=np.int32)
+    solver.lqr_solve_from_x0(capi.problem(M, N), batch, x0, qr, K0=K0, P0=P0, cost=cost, status=status)
+    assert np.all(status == 0)
+    assert np.array_equal(K0, ref["K0"]) and np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
+    AB = oracle.make_ab_batch(M, N, 0.02, x0)
+    ref2 = oracle.lqr_batch(24, 8, N, AB, qr, x0dev=x0, want_K=True)
+    K = np.empty((batch, N, 8, 24))
+    solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, N, n=24, m=8), batch, AB, qr, K=K)
+    assert np.array_equal(K, ref2["K"])
+
+
+def test_slq_dual24_multiwarp_config(oracle, solver):
+    from noc_b200 import capi
+    batch, N = 1300, 10
+    Q, R, Qf = pb.default_weights(M)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.hover_state(batch, model=M)
+    xg = pb.sample_goals(batch, seed=78, model=M)
+    prob = capi.problem(M, N, max_iter=6)
+    cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    solver.slq_solve_batch(prob, batch, x0, xg, qr, cost=cost, iters=iters, status=status)
+    ref = oracle.slq_batch(oracle.slq_opts(M, N, max_iter=6), x0, xg, qr, want_traj=False)
+    assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"]) and np.array_equal(cost, ref["cost"])
