@@ -304,6 +304,25 @@ def _run_noc(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
 
+    # ---- extra: every gain K_k back to the host as well (2.5 GB per step over PCIe: the copy dominates)
+    allk = None
+    if world == 1 and not args.no_allk:
+        try:
+            h_K = torch.empty(B, N, N_U, N_X, dtype=torch.float64).pin_memory()
+            for _ in range(1):
+                solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K=h_K, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
+            t1 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K=h_K, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
+            dt_allk = (time.perf_counter() - t1) / reps
+            allk = {"value": B / dt_allk, "unit": UNIT, "ms_per_step": 1e3 * dt_allk,
+                    "d2h_bytes_per_step": d2h + h_K.numel() * 8,
+                    "what": "as e2e, plus all N gains K_k copied to pinned host memory"}
+            del h_K
+        except Exception as ex:   # pinned allocation refused: report, do not fail the bench
+            allk = {"unavailable": str(ex)[:120]}
+
     # ---- extra: the same pipeline with x0 and the outputs resident in HBM (no PCIe), device-timed
     d_P0 = torch.empty(B, N_X, N_X, **f64)
     p_dev = capi.problem(capi.MODEL_QUAD12, N, flags=capi.FLAG_ASYNC)
@@ -351,6 +370,7 @@ def _run_noc(args):
                            "pinned host K0,P0,cost,status (device->host copies of finished chunks overlap the next chunk)",
                     "ms_per_step": 1e3 * e2e_s / args.steps, "median_ms_per_step": 1e3 * float(np.median(step_s)),
                     "max_ms_per_step": 1e3 * float(np.max(step_s))},
+            "e2e_all_gains_to_host": allk,
             "pipeline_device_resident": {"value": world * B / (pipe_ms * 1e-3) if world == 1 else None, "unit": UNIT,
                                          "ms_per_step": pipe_ms,
                                          "what": "x0 -> rollout -> fused linearise+sweep -> K0,P0,cost,status, all in HBM (rank 0)"},
@@ -406,6 +426,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32768)
     ap.add_argument("--ref-sample", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-allk", action="store_true", help="skip the all-gains-to-host extra")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "noc":
         log("note: fewer than 3 warm-up steps requested")
