@@ -114,7 +114,7 @@ void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N);
 
 /* ---- SURVEY §8(a) a2+a3: backward Riccati recursion, Cholesky, gains -------------------------
  * Finite-horizon LTV LQR sweep for `batch` independent instances.
- *   AB        [batch][N][n*n+n*m]   A_k,B_k records (prob->layout); (n,m) = (12,4) or (24,8); a device pointer
+ *   AB        [batch][N][n*n+n*m]   A_k,B_k records (prob->layout); any 1<=n<=24, 1<=m<=8 ((12,4) and (24,8) are the tuned shapes); a device pointer
  *                                   must be 16-byte aligned (the records are fetched by TMA bulk copies)
  *   QRQf      [n*n + m*m + n*n]     Q, R, Qf shared by the batch, or [batch][...] if qr_per_instance
  *   x0dev     [batch][n] or NULL    initial deviation; needed only for `cost`

@@ -14,6 +14,7 @@
 #include "pipeline_kernels.cuh"
 #include "riccati12.cuh"
 #include "riccati24.cuh"
+#include "riccati_generic.cuh"
 #include "slq_kernels.cuh"
 
 namespace {
@@ -646,8 +647,9 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if (batch == 0) return NOC_OK;
   if (qr_per_instance) return fail(ctx, NOC_ERR_UNSUPPORTED, "per-instance Q/R/Qf not implemented yet");
   const bool n24 = (p->n == 24 && p->m == 8);
-  if (!(p->n == 12 && p->m == 4) && !n24)
-    return fail(ctx, NOC_ERR_UNSUPPORTED, "sweep kernels exist for (n,m) = (12,4) and (24,8)");
+  const bool generic = !(p->n == 12 && p->m == 4) && !n24;
+  if (generic && (p->n < 1 || p->n > RG_NMAX || p->m < 1 || p->m > RG_MMAX))
+    return fail(ctx, NOC_ERR_UNSUPPORTED, "LTV sweep: 1 <= n <= 24 and 1 <= m <= 8 (tuned kernels: (12,4), (24,8))");
   if (misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned (TMA bulk copies)");
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const int n = p->n, m = p->m, N = p->N;
@@ -662,8 +664,20 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
   if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
   if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
-  rc = (n24 ? lqr24_device : lqr12_device)(ctx, p, batch, (const double*)dAB, (const double*)dQ, (const double*)dx0,
-                                           (double*)dK, (double*)dK0, (double*)dP0, (double*)dcost, (int32_t*)dstatus);
+  if (generic) {
+    RicGenArgs g{};
+    g.AB = (const double*)dAB; g.QRQf = (const double*)dQ; g.x0 = (const double*)dx0; g.K = (double*)dK;
+    g.K0 = (double*)dK0; g.P0 = (double*)dP0; g.cost = (double*)dcost; g.status = (int32_t*)dstatus;
+    g.batch = batch; g.n = n; g.m = m; g.N = N; g.layout = p->layout;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+      k_ric_generic<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(g);
+    }
+    rc = (cudaGetLastError() == cudaSuccess) ? NOC_OK : fail(ctx, NOC_ERR_CUDA, "k_ric_generic launch failed");
+  } else {
+    rc = (n24 ? lqr24_device : lqr12_device)(ctx, p, batch, (const double*)dAB, (const double*)dQ, (const double*)dx0,
+                                             (double*)dK, (double*)dK0, (double*)dP0, (double*)dcost, (int32_t*)dstatus);
+  }
   if (rc) { ctx->pending.clear(); return rc; }
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }

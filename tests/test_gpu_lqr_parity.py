@@ -193,3 +193,49 @@ def test_lqr_tail_and_big_mixed(oracle, solver):
                                status=status)
         assert np.all(status == 0)
         assert np.array_equal(K, ref["K"]) and np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
+
+
+@pytest.mark.parametrize("n,m", [(1, 1), (2, 1), (6, 2), (7, 3), (12, 8), (20, 4), (24, 3)])
+@pytest.mark.parametrize("layout", [0, 1])
+def test_generic_dimensions_bitexact(oracle, solver, n, m, layout):
+    """NOC_MODEL_LTV_USER with dimensions other than the tuned (12,4) / (24,8): the thread-per-instance kernel."""
+    from noc_b200 import capi
+    rng = np.random.default_rng(100 * n + m)
+    batch, N = 70, 9
+
+    def spd(k, s):
+        Mx = rng.normal(size=(k, k)); return s * (Mx @ Mx.T + k * np.eye(k))
+    Q, R, Qf = spd(n, 0.1), spd(m, 0.05), spd(n, 1.0)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    A = np.eye(n) + 0.05 * rng.normal(size=(batch, N, n, n))
+    B = 0.2 * rng.normal(size=(batch, N, n, m))
+    if layout == 0:
+        AB = np.concatenate([A.reshape(batch, N, n * n), B.reshape(batch, N, n * m)], axis=2)
+    else:
+        AB = np.concatenate([A, B], axis=3).reshape(batch, N, n * (n + m))
+    x0 = rng.normal(size=(batch, n))
+    ref = oracle.lqr_batch(n, m, N, AB, qr, layout=layout, x0dev=x0)
+    K = np.empty((batch, N, m, n)); K0 = np.empty((batch, m, n)); P0 = np.empty((batch, n, n)); cost = np.empty(batch)
+    status = np.full(batch, -1, dtype=np.int32)
+    solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, N, n=n, m=m, layout=layout), batch, AB, qr, x0dev=x0, K=K,
+                           K0=K0, P0=P0, cost=cost, status=status)
+    assert np.all(status == 0) and np.array_equal(status, ref["status"])
+    assert np.array_equal(K, ref["K"]) and np.array_equal(K0, ref["K0"])
+    assert np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
+
+
+def test_generic_dimensions_not_pd(oracle, solver):
+    from noc_b200 import capi
+    rng = np.random.default_rng(8)
+    n, m, batch, N = 5, 2, 12, 7
+    Q = np.eye(n); R = np.diag([0.1, -5.0]); Qf = np.eye(n)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    AB = np.concatenate([(np.eye(n) + 0.1 * rng.normal(size=(batch, N, n, n))).reshape(batch, N, n * n),
+                         (0.3 * rng.normal(size=(batch, N, n, m))).reshape(batch, N, n * m)], axis=2)
+    ref = oracle.lqr_batch(n, m, N, AB, qr)
+    assert np.any(ref["status"] == 1)
+    K = np.empty((batch, N, m, n)); P0 = np.empty((batch, n, n)); status = np.full(batch, -1, dtype=np.int32)
+    solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, N, n=n, m=m), batch, AB, qr, K=K, P0=P0, status=status)
+    assert np.array_equal(status, ref["status"]) and np.array_equal(np.isnan(K), np.isnan(ref["K"]))
+    ok = ~np.isnan(ref["K"])
+    assert np.array_equal(K[ok], ref["K"][ok]) and np.array_equal(np.isnan(P0), np.isnan(ref["P0"]))
