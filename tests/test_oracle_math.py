@@ -308,3 +308,78 @@ def test_slq_dual24_runs(oracle):
     b = oracle.slq_batch(oracle.slq_opts(pb.MODEL_DUAL24, N), x0[None], g[None], qr, threads=1)
     assert b["cost"][0] == r["cost"] and b["iters"][0] == r["iters"]
     assert np.array_equal(b["alpha_idx"][0], r["alpha_idx"])
+
+
+# ---------------------------------------------------------------- SLQ against an independent numpy iLQR
+def _numpy_ilqr(oracle, x0, xg, Q, R, Qf, N, dt=0.02, tol=1e-8, max_iter=50, n_alpha=11, armijo=1e-4):
+    """Textbook iLQR written with numpy matrix algebra (np.linalg.solve, no LDL^T, no fma chains): the same
+    specification in a different arithmetic, so agreement is to rounding, not to the bit."""
+    uh = pb.hover_input()
+    f = lambda x, u: x + dt * _f_numpy(x, u)
+
+    def cost(xs, us):
+        J = 0.0
+        for k in range(N):
+            ex, eu = xs[k] - xg, us[k] - uh
+            J += 0.5 * (ex @ Q @ ex + eu @ R @ eu)
+        ex = xs[N] - xg
+        return J + 0.5 * ex @ Qf @ ex
+
+    us = np.tile(uh, (N, 1))
+    xs = np.empty((N + 1, 12)); xs[0] = x0
+    for k in range(N):
+        xs[k + 1] = f(xs[k], us[k])
+    J = cost(xs, us)
+    alphas_taken = []
+    for it in range(max_iter):
+        Vxx, Vx = Qf.copy(), Qf @ (xs[N] - xg)
+        Ks, ks = np.empty((N, 4, 12)), np.empty((N, 4))
+        dV1 = dV2 = 0.0
+        for k in range(N - 1, -1, -1):
+            A, B = oracle.linearize(0, xs[k], us[k], dt)
+            Qx = Q @ (xs[k] - xg) + A.T @ Vx
+            Qu = R @ (us[k] - uh) + B.T @ Vx
+            Qxx = Q + A.T @ Vxx @ A
+            Qux = B.T @ Vxx @ A
+            Quu = R + B.T @ Vxx @ B
+            Ks[k] = -np.linalg.solve(Quu, Qux)
+            ks[k] = -np.linalg.solve(Quu, Qu)
+            Vxx = Qxx + Qux.T @ Ks[k]
+            Vxx = 0.5 * (Vxx + Vxx.T)
+            Vx = Qx + Qux.T @ ks[k]
+            dV1 += ks[k] @ Qu
+            dV2 += 0.5 * ks[k] @ Quu @ ks[k]
+        accepted = None
+        for j in range(n_alpha):
+            a = 0.5 ** j
+            xn = np.empty_like(xs); un = np.empty_like(us); xn[0] = x0
+            for k in range(N):
+                un[k] = us[k] + a * ks[k] + Ks[k] @ (xn[k] - xs[k])
+                xn[k + 1] = f(xn[k], un[k])
+            Jn = cost(xn, un)
+            if J - Jn >= armijo * (-(a * dV1 + a * a * dV2)):
+                accepted = j
+                break
+        if accepted is None:
+            return J, it + 1, alphas_taken, 3
+        alphas_taken.append(accepted)
+        rel = (J - Jn) / max(J, 1e-12)
+        xs, us, J = xn, un, Jn
+        if rel < tol:
+            return J, it + 1, alphas_taken, 0
+    return J, max_iter, alphas_taken, 2
+
+
+def test_slq_vs_independent_numpy_ilqr(oracle):
+    Q, R, Qf = pb.default_weights()
+    qr = pb.pack_qrqf(Q, R, Qf)
+    N = 30
+    goals = pb.sample_goals(4, seed=404)
+    for b in range(4):
+        x0 = pb.hover_state(1)[0] if b < 2 else pb.sample_x0(1, seed=50 + b)[0]
+        ref = oracle.slq(oracle.slq_opts(0, N), x0, goals[b], qr)
+        J, iters, alphas, status = _numpy_ilqr(oracle, x0, goals[b], Q, R, Qf, N)
+        assert status == ref["status"]                                   # converged, or MAX_ITER for the hard start
+        assert iters == ref["iters"]                                   # identical iteration counts
+        assert alphas == [int(a) for a in ref["alpha_idx"][:iters]]     # identical accepted step lengths
+        assert abs(J - ref["cost"]) <= 1e-9 * abs(ref["cost"])          # north_star's tolerance
