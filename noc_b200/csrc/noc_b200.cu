@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <type_traits>
@@ -337,7 +338,9 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   NOC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
   size_t have = 0;
   if (ctx->scratch.size() > SCR_XBAR) have = ctx->scratch[SCR_XBAR].cap;
-  const size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
+  size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
+  if (const char* cap = std::getenv("NOC_B200_SCRATCH_MB"))   // test hook: force several outer chunks
+    budget = std::max<size_t>((size_t)std::atoll(cap) << 20, (size_t)1 << 20);
   const size_t per_inst = sizeof(double) * (N + 1) * n;
   size_t outer = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
   if (outer < B) outer = std::max<size_t>(32, outer & ~size_t(31));

@@ -121,3 +121,30 @@ def test_per_kernel_profile_counters(solver):
     ms, cnt = solver.profile_read(capi.KERNEL_RICCATI)
     assert cnt == 1 and ms > 0 and solver.launch_count - n0 == 3      # rollout, weight packing, fused sweep
     assert solver.profile_read(capi.KERNEL_LINEARIZE)[1] == 0          # linearisation is fused into the sweep
+
+
+def test_outer_chunking_of_the_nominal_scratch(oracle):
+    """NOC_B200_SCRATCH_MB caps the scratch budget so that a modest batch is cut into several outer chunks (each
+    with its own rollout launch) and, with host outputs, inner copy chunks: results must not depend on the cut."""
+    import os
+    from noc_b200 import capi
+    batch, N = 9000, 40
+    qr = _qr()
+    x0 = pb.sample_x0(batch, seed=6)
+    os.environ["NOC_B200_SCRATCH_MB"] = "8"          # 8 MB / (41 x 96 B) = ~2,100 instances per outer chunk
+    try:
+        s = capi.Solver(0)
+        K0 = np.empty((batch, 4, 12)); cost = np.empty(batch); st = np.full(batch, -1, dtype=np.int32)
+        s.lqr_solve_from_x0(capi.problem(0, N), batch, x0, qr, K0=K0, cost=cost, status=st)
+        s.close()
+    finally:
+        del os.environ["NOC_B200_SCRATCH_MB"]
+    sel = np.arange(0, batch, 97)
+    ref = oracle.lqr_from_x0_batch(0, N, 0.02, x0[sel], qr, want_P0=False)
+    assert np.all(st == 0)
+    assert np.array_equal(K0[sel], ref["K0"]) and np.array_equal(cost[sel], ref["cost"])
+    s2 = capi.Solver(0)
+    K0b = np.empty((batch, 4, 12)); costb = np.empty(batch)
+    s2.lqr_solve_from_x0(capi.problem(0, N), batch, x0, qr, K0=K0b, cost=costb)
+    s2.close()
+    assert np.array_equal(K0, K0b) and np.array_equal(cost, costb)
