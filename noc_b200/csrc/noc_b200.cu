@@ -226,8 +226,12 @@ template <int LAYOUT, int MODE, bool FUSED = false>
 int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
   // short work lists (the tail of an SLQ solve, small batches): one warp per CTA, so that the few warps spread over
   // all SMs instead of sharing a handful — the sweep is then latency-bound and a warp alone on an SM steps ~2x faster
+#if defined(NOC_EXP_MASK)   // experiment build only: one 7/8-warp CTA per SM, warps selected by the mask
+  return launch_ric12_cfg<LAYOUT, MODE, FUSED, (MODE == RIC_AFFINE ? 7 : 8), 1>(ctx, a);
+#else
   if (a.batch <= 8LL * 2 * ctx->sm_count) return launch_ric12_cfg<LAYOUT, MODE, FUSED, 1, 1>(ctx, a);
   return launch_ric12_cfg<LAYOUT, MODE, FUSED, RicCfg<MODE>::warps, RicCfg<MODE>::min_ctas>(ctx, a);
+#endif
 }
 
 template <int MODE>

@@ -9,7 +9,7 @@ from noc_b200 import capi, problems as pb
 lib = sys.argv[1] if len(sys.argv) > 1 else None
 if lib:
     capi.LIB_PATH = os.path.abspath(lib)
-B, N = 65536, 100
+B, N = int(os.environ.get('EXP_B', 65536)), 100
 dev = torch.device("cuda", 0)
 s = capi.Solver(0)
 stream = torch.cuda.Stream(device=dev); s.set_stream(stream.cuda_stream)
