@@ -14,13 +14,20 @@ __global__ void __launch_bounds__(128) k_outer(double* out, int iters, double a,
 #pragma unroll
   for (int s = 0; s < 4; ++s) f[s] = 1.0 + s;
   for (int it = 0; it < iters; ++it) {
+    if (SNAKE == 2) {   // column-major: f[s] stays in its operand slot for twelve consecutive DFMAs
 #pragma unroll
-    for (int r = 0; r < 12; ++r)
+      for (int s = 0; s < 4; ++s)
 #pragma unroll
-      for (int ss = 0; ss < 4; ++ss) {
-        const int s = (SNAKE && (r & 1)) ? 3 - ss : ss;
-        acc[r][s] = __fma_rn(p[r], f[s], acc[r][s]);
-      }
+        for (int r = 0; r < 12; ++r) acc[r][s] = __fma_rn(p[r], f[s], acc[r][s]);
+    } else {
+#pragma unroll
+      for (int r = 0; r < 12; ++r)
+#pragma unroll
+        for (int ss = 0; ss < 4; ++ss) {
+          const int s = (SNAKE && (r & 1)) ? 3 - ss : ss;
+          acc[r][s] = __fma_rn(p[r], f[s], acc[r][s]);
+        }
+    }
     // new operands every iteration (cheap, non-FP64): flip sign bits
 #pragma unroll
     for (int r = 0; r < 12; ++r) p[r] = __longlong_as_double(__double_as_longlong(p[r]) ^ ((long long)it << 63));
@@ -46,14 +53,15 @@ int main() {
   double* d; CK(cudaMalloc(&d, 64));
   const int iters = 20000;
   printf("{\"gpu\": \"%s\"", p.name);
-  for (int snake = 0; snake < 2; ++snake)
+  for (int snake = 0; snake < 3; ++snake)
     for (int ctas = 1; ctas <= 8; ctas *= 2) {   // CTAs of 128 threads per SM = warps per scheduler
       const int blocks = p.multiProcessorCount * ctas;
-      float ms = snake ? time_ms([&] { k_outer<1><<<blocks, 128>>>(d, iters, 1.0, 1.0); })
-                       : time_ms([&] { k_outer<0><<<blocks, 128>>>(d, iters, 1.0, 1.0); });
+      float ms = snake == 2 ? time_ms([&] { k_outer<2><<<blocks, 128>>>(d, iters, 1.0, 1.0); })
+                 : snake  ? time_ms([&] { k_outer<1><<<blocks, 128>>>(d, iters, 1.0, 1.0); })
+                          : time_ms([&] { k_outer<0><<<blocks, 128>>>(d, iters, 1.0, 1.0); });
       const double fma = 48.0 * iters * 128.0 * blocks;
-      printf(", \"%s_w%d_tflops\": %.2f, \"%s_w%d_lanes_per_clk_per_sm\": %.1f", snake ? "snake" : "rowmajor", ctas,
-             2 * fma / ms * 1e-9, snake ? "snake" : "rowmajor", ctas, fma / (ms * 1e-3) / (clk_khz * 1e3) / p.multiProcessorCount);
+      printf(", \"%s_w%d_tflops\": %.2f, \"%s_w%d_lanes_per_clk_per_sm\": %.1f", snake == 2 ? "colmajor" : snake ? "snake" : "rowmajor", ctas,
+             2 * fma / ms * 1e-9, snake == 2 ? "colmajor" : snake ? "snake" : "rowmajor", ctas, fma / (ms * 1e-3) / (clk_khz * 1e3) / p.multiProcessorCount);
     }
   printf("}\n");
   return 0;
