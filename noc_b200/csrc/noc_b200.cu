@@ -153,7 +153,7 @@ int scratch(noc_ctx* ctx, int slot, size_t bytes, void** out) {
 }
 
 enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
-       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC, SCR_FLAGS };
+       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC, SCR_FLAGS, SCR_XC, SCR_UC, SCR_LCC };
 
 // W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
 // Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
@@ -518,6 +518,39 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
       NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       list = rin; list_count = hc[1];
       std::swap(rin, rout);
+      // Speculative round: all remaining step lengths of the rejected instances at once (one launch set instead
+      // of up to n_alpha-1 sequential ones), when the candidate trajectories fit a 2 GB scratch.
+      const int J = p->n_alpha - 1 - trial;
+      const size_t per_cand = sizeof(double) * ((N + 1) * n + N * m + (N + 1));
+      if (trial == 0 && list_count > 0 && J > 0 && (size_t)list_count * J * per_cand <= ((size_t)2 << 30)) {
+        void *dxc, *duc, *dlcc;
+        const size_t rc_ = (size_t)list_count * J;
+        int e1 = scratch(ctx, SCR_XC, sizeof(double) * rc_ * (N + 1) * n, &dxc);
+        int e2 = e1 ? e1 : scratch(ctx, SCR_UC, sizeof(double) * rc_ * N * m, &duc);
+        int e3 = e2 ? e2 : scratch(ctx, SCR_LCC, sizeof(double) * rc_ * (N + 1), &dlcc);
+        if (e3) { ctx->pending.clear(); return e3; }
+        fa.idx = list; fa.trial = 1; fa.cand_J = J; fa.xc = (double*)dxc; fa.uc = (double*)duc; fa.lcc = (double*)dlcc;
+        fa.count = (int)rc_;
+        {
+          LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+          k_slq_rollout<MODEL><<<(unsigned)((rc_ + FC::threads - 1) / FC::threads), FC::threads, fwd_smem, ctx->stream>>>(fa);
+        }
+        NOC_CUDA(ctx, cudaGetLastError());
+        {
+          const long long total = (long long)rc_ * (p->N + 1);
+          LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+          k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fa);
+        }
+        NOC_CUDA(ctx, cudaGetLastError());
+        fa.count = list_count;
+        {
+          LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+          k_slq_accept<MODEL><<<(unsigned)((list_count + 127) / 128), 128, 0, ctx->stream>>>(fa);
+        }
+        NOC_CUDA(ctx, cudaGetLastError());
+        fa.cand_J = 0;
+        list_count = 0;   // every rejected instance has been settled
+      }
     }
     {  // instances that go on to the next iteration -> sorted work list
       LaunchScope ls(ctx, NOC_KERNEL_FORWARD);

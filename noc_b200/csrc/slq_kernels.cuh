@@ -117,6 +117,12 @@ struct SlqFwdArgs {
                             // instance order keeps the per-instance streams of a warp at a regular stride (an
                             // atomicAdd-ordered list made the full-size rollouts 1.6x slower).
   int trial;                // j of this launch: alpha = 2^-j for every instance of the work list
+  // speculative round (cand_J > 0): work item = (list position i, candidate c), step length 2^-(c+1); the
+  // trajectories go to the candidate scratch instead of x / u and k_slq_accept picks the first accepted c
+  int cand_J;               // candidates per instance (n_alpha - 1), 0 = ordinary round
+  double* xc;               // [count/cand_J][cand_J][N+1][n]
+  double* uc;               // [count/cand_J][cand_J][N][m]
+  double* lcc;              // [count/cand_J][cand_J][N+1]
   const double* xgoal;      // [batch][n]
   const double* qrqf;
   double* x;                // [batch][N+1][n]  in: nominal, out: accepted trajectory (in place)
@@ -176,20 +182,22 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_rollout(const Sl
   const int tid = threadIdx.x;
   const int item = blockIdx.x * T + tid;
   if (item >= a.count) return;
-  const long long b = a.idx[item];
+  const bool cand = a.cand_J > 0;
+  const long long b = a.idx[cand ? item / a.cand_J : item];
+  const int trial = cand ? item % a.cand_J + 1 : a.trial;
   const int N = a.N;
-  if (a.trial == 0 && a.bstatus[b] != 0) return;   // regularisation exhausted: k_slq_accept records it
-  double* xb = a.x + (size_t)b * (N + 1) * n;    // receives the trial's trajectory
-  double* ub = a.u + (size_t)b * N * m;
+  if (trial == 0 && a.bstatus[b] != 0) return;   // regularisation exhausted: k_slq_accept records it
+  double* xb = cand ? a.xc + (size_t)item * (N + 1) * n : a.x + (size_t)b * (N + 1) * n;   // receives the trajectory
+  double* ub = cand ? a.uc + (size_t)item * N * m : a.u + (size_t)b * N * m;
   double* xs = a.xn + (size_t)b * (N + 1) * n;   // holds the nominal from trial 0 on
   double* us = a.un + (size_t)b * N * m;
-  const bool first = a.trial == 0;
+  const bool first = trial == 0;
   const double* xnom = first ? xb : xs;          // where this trial reads the nominal
   const double* unom = first ? ub : us;
   const double* Kb = a.K + (size_t)b * N * m * n;
   const double* kb = a.kff + (size_t)b * N * m;
   double alpha = 1.0;
-  for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
+  for (int j = 0; j < trial; ++j) alpha = alpha * 0.5;
 
   auto prefetch = [&](int k) {
     if (k < N) {
@@ -273,22 +281,24 @@ __global__ void __launch_bounds__(128) k_slq_stage_cost(const SlqFwdArgs a) {
   if (tw >= (long long)a.count * (N + 1)) return;
   const int item = (int)(tw / (N + 1));
   const int k = (int)(tw - (long long)item * (N + 1));
-  const long long b = a.idx[item];
-  if (a.trial == 0 && a.bstatus[b] != 0) return;
+  const bool cand = a.cand_J > 0;
+  const long long b = a.idx[cand ? item / a.cand_J : item];
+  if (!cand && a.trial == 0 && a.bstatus[b] != 0) return;
   double x[n], xg[n], u[m];
-  const double* xp = a.x + ((size_t)b * (N + 1) + k) * n;
+  const double* xp = cand ? a.xc + ((size_t)item * (N + 1) + k) * n : a.x + ((size_t)b * (N + 1) + k) * n;
 #pragma unroll
   for (int i = 0; i < n; ++i) { x[i] = xp[i]; xg[i] = a.xgoal[b * n + i]; }
   double c;
   if (k < N) {
-    const double* up = a.u + ((size_t)b * N + k) * m;
+    const double* up = cand ? a.uc + ((size_t)item * N + k) * m : a.u + ((size_t)b * N + k) * m;
 #pragma unroll
     for (int j = 0; j < m; ++j) u[j] = up[j];
     c = w.stage(x, u, xg);
   } else {
     c = w.terminal(x, xg);
   }
-  a.lc[(size_t)b * (N + 1) + k] = c;
+  if (cand) a.lcc[(size_t)item * (N + 1) + k] = c;
+  else a.lc[(size_t)b * (N + 1) + k] = c;
 }
 
 // (3) per instance: J = sum of the stage costs in ascending k (the oracle's order), Armijo test, bookkeeping,
@@ -305,33 +315,63 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
     a.iters[b] = a.iter + 1;
     return;
   }
-  const double* lc = a.lc + (size_t)b * (N + 1);
-  double Jacc = 0.0;
-#pragma unroll 8
-  for (int k = 0; k <= N; ++k) Jacc = Jacc + lc[k];
   const double Jold = a.J[b];
   const double dV1 = a.dV[b * 2], dV2 = a.dV[b * 2 + 1];
-  double alpha = 1.0;
-  for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
-  const int accepted = a.trial;
-  const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
-  if (!(Jold - Jacc >= a.armijo * expected)) {
-    if (a.trial + 1 < a.n_alpha) {   // next step length, next launch
-      a.flags[b] |= 2;
-      return;
+  int accepted = -1;
+  double Jacc = 0.0;
+  if (a.cand_J > 0) {
+    // speculative round: candidates c = 0 .. cand_J-1 hold alpha = 2^-(c+1); take the first that passes, in order
+    double alpha = 0.5;
+    for (int c = 0; c < a.cand_J; ++c) {
+      const double* lc = a.lcc + ((size_t)item * a.cand_J + c) * (N + 1);
+      double Jc = 0.0;
+#pragma unroll 8
+      for (int k = 0; k <= N; ++k) Jc = Jc + lc[k];
+      const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
+      if (Jold - Jc >= a.armijo * expected) { accepted = c + 1; Jacc = Jc; break; }
+      alpha = alpha * 0.5;
     }
-    // no step length passed: put the nominal back (oracle: x, u unchanged) and stop this instance
-    const double2* sx = reinterpret_cast<const double2*>(a.xn + (size_t)b * (N + 1) * n);
-    const double2* su = reinterpret_cast<const double2*>(a.un + (size_t)b * N * m);
+    // accepted candidate (or, if none passed, the saved nominal) -> x, u
+    const size_t slot = (size_t)item * a.cand_J + (accepted > 0 ? accepted - 1 : 0);
+    const double2* sx = reinterpret_cast<const double2*>(accepted > 0 ? a.xc + slot * (N + 1) * n : a.xn + (size_t)b * (N + 1) * n);
+    const double2* su = reinterpret_cast<const double2*>(accepted > 0 ? a.uc + slot * N * m : a.un + (size_t)b * N * m);
     double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
     double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
 #pragma unroll 8
     for (int i = 0; i < (N + 1) * n / 2; ++i) dxp[i] = sx[i];
 #pragma unroll 8
     for (int i = 0; i < N * m / 2; ++i) dup[i] = su[i];
-    a.status[b] = 3;  // NOC_STATUS_LS_FAIL
-    a.iters[b] = a.iter + 1;
-    return;
+    if (accepted < 0) {
+      a.status[b] = 3;  // NOC_STATUS_LS_FAIL (the nominal has been put back)
+      a.iters[b] = a.iter + 1;
+      return;
+    }
+  } else {
+    const double* lc = a.lc + (size_t)b * (N + 1);
+#pragma unroll 8
+    for (int k = 0; k <= N; ++k) Jacc = Jacc + lc[k];
+    double alpha = 1.0;
+    for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
+    accepted = a.trial;
+    const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
+    if (!(Jold - Jacc >= a.armijo * expected)) {
+      if (a.trial + 1 < a.n_alpha) {   // next step length(s), next launch
+        a.flags[b] |= 2;
+        return;
+      }
+      // no step length passed: put the nominal back (oracle: x, u unchanged) and stop this instance
+      const double2* sx = reinterpret_cast<const double2*>(a.xn + (size_t)b * (N + 1) * n);
+      const double2* su = reinterpret_cast<const double2*>(a.un + (size_t)b * N * m);
+      double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
+      double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
+#pragma unroll 8
+      for (int i = 0; i < (N + 1) * n / 2; ++i) dxp[i] = sx[i];
+#pragma unroll 8
+      for (int i = 0; i < N * m / 2; ++i) dup[i] = su[i];
+      a.status[b] = 3;  // NOC_STATUS_LS_FAIL
+      a.iters[b] = a.iter + 1;
+      return;
+    }
   }
   if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + a.iter] = accepted;
   const double denom = (Jold > 1e-12) ? Jold : 1e-12;
