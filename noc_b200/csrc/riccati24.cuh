@@ -293,22 +293,45 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
       double g[24][2];
 #pragma unroll
       for (int r = 0; r < 24; ++r) { g[r][0] = 0.0; g[r][1] = 0.0; }
+      if (!FUSED) {
 #pragma unroll 4
-      for (int l = 0; l < 24; ++l) {
-        const double fa = Fs[offA + l * strAB];
-        const double fb = Fs[offB + l * strAB];
+        for (int l = 0; l < 24; ++l) {
+          const double fa = Fs[offA + l * strAB];
+          const double fb = Fs[offB + l * strAB];
 #pragma unroll
-        for (int r = 0; r < 24; r += 2) {
-          const double2 v = lds128(Ps + l * 24 + r);
-          g[r][0] = fmad(v.x, fa, g[r][0]);
-          g[r][1] = fmad(v.x, fb, g[r][1]);
-          g[r + 1][0] = fmad(v.y, fa, g[r + 1][0]);
-          g[r + 1][1] = fmad(v.y, fb, g[r + 1][1]);
+          for (int r = 0; r < 24; r += 2) {
+            const double2 v = lds128(Ps + l * 24 + r);
+            g[r][0] = fmad(v.x, fa, g[r][0]);
+            g[r][1] = fmad(v.x, fb, g[r][1]);
+            g[r + 1][0] = fmad(v.y, fa, g[r + 1][0]);
+            g[r + 1][1] = fmad(v.y, fb, g[r + 1][1]);
+          }
+          if (MODE == RIC_AFFINE) {
+            const double vx = base[R24_VS + l];
+            hacc[0] = fmad(fa, vx, hacc[0]);
+            hacc[1] = fmad(fb, vx, hacc[1]);
+          }
         }
-        if (MODE == RIC_AFFINE) {
-          const double vx = base[R24_VS + l];
-          hacc[0] = fmad(fa, vx, hacc[0]);
-          hacc[1] = fmad(fb, vx, hacc[1]);
+      } else {
+        // built-in dual model: slot A holds a column of vehicle 0 (x or u) in every lane, slot B one of vehicle 1;
+        // rows of the other vehicle are structurally zero there except its three spring-damper rows, so 9 of the
+        // 24 (l, slot) products are skipped by all lanes alike
+#pragma unroll
+        for (int l = 0; l < 24; ++l) {
+          const bool nzA = l < 12 || (l >= 15 && l < 18), nzB = l >= 12 || (l >= 3 && l < 6);
+          const double fa = nzA ? Fs[offA + l * strAB] : 0.0;
+          const double fb = nzB ? Fs[offB + l * strAB] : 0.0;
+#pragma unroll
+          for (int r = 0; r < 24; r += 2) {
+            const double2 v = lds128(Ps + l * 24 + r);
+            if (nzA) { g[r][0] = fmad(v.x, fa, g[r][0]); g[r + 1][0] = fmad(v.y, fa, g[r + 1][0]); }
+            if (nzB) { g[r][1] = fmad(v.x, fb, g[r][1]); g[r + 1][1] = fmad(v.y, fb, g[r + 1][1]); }
+          }
+          if (MODE == RIC_AFFINE) {
+            const double vx = base[R24_VS + l];
+            if (nzA) hacc[0] = fmad(fa, vx, hacc[0]);
+            if (nzB) hacc[1] = fmad(fb, vx, hacc[1]);
+          }
         }
       }
 
@@ -332,9 +355,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
           const double ga = g[l][0], gb = g[l][1];
 #pragma unroll
           for (int c = 0; c < 8; c += 2) {
+            const bool n0 = !FUSED || model::dual_jac_nz_B(l, c), n1 = !FUSED || model::dual_jac_nz_B(l, c + 1);
+            if (!n0 && !n1) continue;
             const double2 v = lds128(Fs + r24_foff<LAYOUT>(l, 24 + c));
-            huA[c] = fmad(v.x, ga, huA[c]); huA[c + 1] = fmad(v.y, ga, huA[c + 1]);
-            huB[c] = fmad(v.x, gb, huB[c]); huB[c + 1] = fmad(v.y, gb, huB[c + 1]);
+            if (n0) { huA[c] = fmad(v.x, ga, huA[c]); huB[c] = fmad(v.x, gb, huB[c]); }
+            if (n1) { huA[c + 1] = fmad(v.y, ga, huA[c + 1]); huB[c + 1] = fmad(v.y, gb, huB[c + 1]); }
           }
         }
         if (MODE == RIC_AFFINE && !xl) {
@@ -368,14 +393,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
         const double ga = g[l][0], gb = g[l][1];
 #pragma unroll
         for (int i = 0; i < 12; i += 2) {
+          const bool n0 = !FUSED || model::dual_jac_nz_A(l, i), n1 = !FUSED || model::dual_jac_nz_A(l, i + 1);
+          if (!n0 && !n1) continue;
           const double2 v = lds128(Fs + r24_foff<LAYOUT>(l, i));
-          hA[i] = fmad(v.x, ga, hA[i]); hA[i + 1] = fmad(v.y, ga, hA[i + 1]);
-          hB[i] = fmad(v.x, gb, hB[i]); hB[i + 1] = fmad(v.y, gb, hB[i + 1]);
+          if (n0) { hA[i] = fmad(v.x, ga, hA[i]); hB[i] = fmad(v.x, gb, hB[i]); }
+          if (n1) { hA[i + 1] = fmad(v.y, ga, hA[i + 1]); hB[i + 1] = fmad(v.y, gb, hB[i + 1]); }
         }
 #pragma unroll
         for (int i = 12; i < 24; i += 2) {
+          const bool n0 = !FUSED || model::dual_jac_nz_A(l, i), n1 = !FUSED || model::dual_jac_nz_A(l, i + 1);
+          if (!n0 && !n1) continue;
           const double2 v = lds128(Fs + r24_foff<LAYOUT>(l, i));
-          hB[i] = fmad(v.x, gb, hB[i]); hB[i + 1] = fmad(v.y, gb, hB[i + 1]);
+          if (n0) hB[i] = fmad(v.x, gb, hB[i]);
+          if (n1) hB[i + 1] = fmad(v.y, gb, hB[i + 1]);
         }
       }
       __syncwarp();  // every lane is done with Fs (and Xs, Es, Vs); the exchanged Hux / Huu are visible
