@@ -303,6 +303,21 @@ __global__ void __launch_bounds__(128) k_slq_stage_cost(const SlqFwdArgs a) {
 
 // (3) per instance: J = sum of the stage costs in ascending k (the oracle's order), Armijo test, bookkeeping,
 // convergence test, next work list / retry list
+// bookkeeping of an accepted step (trial index `accepted`, cost Jacc): records, convergence test, next work list
+__device__ __forceinline__ void slq_record_step(const SlqFwdArgs& a, long long b, double Jold, double Jacc, int accepted) {
+  if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + a.iter] = accepted;
+  const double denom = (Jold > 1e-12) ? Jold : 1e-12;
+  const double rel = (Jold - Jacc) / denom;
+  a.J[b] = Jacc;
+  a.iters[b] = a.iter + 1;
+  if (rel < a.tol) {
+    a.status[b] = 0;
+    return;
+  }
+  if (a.iter + 1 < a.max_iter) a.flags[b] |= 1;
+}
+
+// ordinary round (one step length per launch): one thread per instance
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
   constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
@@ -317,74 +332,77 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
   }
   const double Jold = a.J[b];
   const double dV1 = a.dV[b * 2], dV2 = a.dV[b * 2 + 1];
-  int accepted = -1;
   double Jacc = 0.0;
-  if (a.cand_J > 0) {
-    // speculative round: candidates c = 0 .. cand_J-1 hold alpha = 2^-(c+1); take the first that passes, in order
-    double alpha = 0.5;
-    for (int c = 0; c < a.cand_J; ++c) {
-      const double* lc = a.lcc + ((size_t)item * a.cand_J + c) * (N + 1);
-      double Jc = 0.0;
+  const double* lc = a.lc + (size_t)b * (N + 1);
 #pragma unroll 8
-      for (int k = 0; k <= N; ++k) Jc = Jc + lc[k];
-      const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
-      if (Jold - Jc >= a.armijo * expected) { accepted = c + 1; Jacc = Jc; break; }
-      alpha = alpha * 0.5;
+  for (int k = 0; k <= N; ++k) Jacc = Jacc + lc[k];
+  double alpha = 1.0;
+  for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
+  const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
+  if (!(Jold - Jacc >= a.armijo * expected)) {
+    if (a.trial + 1 < a.n_alpha) {   // next step length(s), next launch
+      a.flags[b] |= 2;
+      return;
     }
-    // accepted candidate (or, if none passed, the saved nominal) -> x, u
-    const size_t slot = (size_t)item * a.cand_J + (accepted > 0 ? accepted - 1 : 0);
-    const double2* sx = reinterpret_cast<const double2*>(accepted > 0 ? a.xc + slot * (N + 1) * n : a.xn + (size_t)b * (N + 1) * n);
-    const double2* su = reinterpret_cast<const double2*>(accepted > 0 ? a.uc + slot * N * m : a.un + (size_t)b * N * m);
+    // no step length passed: put the nominal back (oracle: x, u unchanged) and stop this instance
+    const double2* sx = reinterpret_cast<const double2*>(a.xn + (size_t)b * (N + 1) * n);
+    const double2* su = reinterpret_cast<const double2*>(a.un + (size_t)b * N * m);
     double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
     double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
 #pragma unroll 8
     for (int i = 0; i < (N + 1) * n / 2; ++i) dxp[i] = sx[i];
 #pragma unroll 8
     for (int i = 0; i < N * m / 2; ++i) dup[i] = su[i];
-    if (accepted < 0) {
-      a.status[b] = 3;  // NOC_STATUS_LS_FAIL (the nominal has been put back)
-      a.iters[b] = a.iter + 1;
-      return;
-    }
-  } else {
-    const double* lc = a.lc + (size_t)b * (N + 1);
-#pragma unroll 8
-    for (int k = 0; k <= N; ++k) Jacc = Jacc + lc[k];
-    double alpha = 1.0;
-    for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
-    accepted = a.trial;
-    const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
-    if (!(Jold - Jacc >= a.armijo * expected)) {
-      if (a.trial + 1 < a.n_alpha) {   // next step length(s), next launch
-        a.flags[b] |= 2;
-        return;
-      }
-      // no step length passed: put the nominal back (oracle: x, u unchanged) and stop this instance
-      const double2* sx = reinterpret_cast<const double2*>(a.xn + (size_t)b * (N + 1) * n);
-      const double2* su = reinterpret_cast<const double2*>(a.un + (size_t)b * N * m);
-      double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
-      double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
-#pragma unroll 8
-      for (int i = 0; i < (N + 1) * n / 2; ++i) dxp[i] = sx[i];
-#pragma unroll 8
-      for (int i = 0; i < N * m / 2; ++i) dup[i] = su[i];
-      a.status[b] = 3;  // NOC_STATUS_LS_FAIL
-      a.iters[b] = a.iter + 1;
-      return;
-    }
-  }
-  if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + a.iter] = accepted;
-  const double denom = (Jold > 1e-12) ? Jold : 1e-12;
-  const double rel = (Jold - Jacc) / denom;
-  a.J[b] = Jacc;
-  a.iters[b] = a.iter + 1;
-  if (rel < a.tol) {
-    a.status[b] = 0;
+    a.status[b] = 3;  // NOC_STATUS_LS_FAIL
+    a.iters[b] = a.iter + 1;
     return;
   }
-  if (a.iter + 1 < a.max_iter) {
-    a.flags[b] |= 1;
+  slq_record_step(a, b, Jold, Jacc, a.trial);
+}
+
+// speculative round (cand_J > 0): one WARP per rejected instance.  Lane c sums the stage costs of candidate c
+// (alpha = 2^-(c+1)) in ascending k and runs its Armijo test; the first passing candidate in order wins (the
+// oracle's sequential backtracking stops at the same one); then the warp copies the winning trajectory (or, if none
+// passed, the saved nominal) over x, u with coalesced 16-byte accesses.  (One thread per instance did both jobs
+// serially at first: 0.5-0.6 ms per launch for a handful of instances, profiles/launches_cfg3_slq_r01c.csv.)
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
+  constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
+  const int lane = threadIdx.x & 31;
+  const int item = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (item >= a.count) return;   // warp-uniform
+  const long long b = a.idx[item];
+  const int N = a.N;
+  const double Jold = a.J[b];
+  const double dV1 = a.dV[b * 2], dV2 = a.dV[b * 2 + 1];
+  double Jc = 0.0;
+  bool pass = false;
+  if (lane < a.cand_J) {
+    const double* lc = a.lcc + ((size_t)item * a.cand_J + lane) * (N + 1);
+#pragma unroll 8
+    for (int k = 0; k <= N; ++k) Jc = Jc + lc[k];
+    double alpha = 0.5;
+    for (int j = 0; j < lane; ++j) alpha = alpha * 0.5;
+    const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
+    pass = Jold - Jc >= a.armijo * expected;
   }
+  const unsigned won = __ballot_sync(0xffffffffu, pass);
+  const int c = won ? __ffs((int)won) - 1 : -1;
+  const double Jacc = __shfl_sync(0xffffffffu, Jc, c < 0 ? 0 : c);
+  const size_t slot = (size_t)item * a.cand_J + (c < 0 ? 0 : c);
+  const double2* sx = reinterpret_cast<const double2*>(c >= 0 ? a.xc + slot * (N + 1) * n : a.xn + (size_t)b * (N + 1) * n);
+  const double2* su = reinterpret_cast<const double2*>(c >= 0 ? a.uc + slot * N * m : a.un + (size_t)b * N * m);
+  double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
+  double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
+  for (int i = lane; i < (N + 1) * n / 2; i += 32) dxp[i] = sx[i];
+  for (int i = lane; i < N * m / 2; i += 32) dup[i] = su[i];
+  if (lane != 0) return;
+  if (c < 0) {
+    a.status[b] = 3;  // NOC_STATUS_LS_FAIL (the nominal has been put back)
+    a.iters[b] = a.iter + 1;
+    return;
+  }
+  slq_record_step(a, b, Jold, Jacc, c + 1);
 }
 
 // Ordered stream compaction of one flag bit: out = ascending list of the i < n with flags[i] & mask, the bit is
