@@ -495,7 +495,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
       fa.idx = list; fa.count = list_count; fa.trial = trial;
       {
         LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-        k_slq_rollout<MODEL><<<(unsigned)((list_count + FC::threads - 1) / FC::threads), FC::threads, fwd_smem, ctx->stream>>>(fa);
+        k_slq_rollout<MODEL><<<(unsigned)((list_count + FC::inst - 1) / FC::inst), FC::threads, fwd_smem, ctx->stream>>>(fa);
       }
       NOC_CUDA(ctx, cudaGetLastError());
       {
@@ -533,7 +533,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
         fa.count = (int)rc_;
         {
           LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-          k_slq_rollout<MODEL><<<(unsigned)((rc_ + FC::threads - 1) / FC::threads), FC::threads, fwd_smem, ctx->stream>>>(fa);
+          k_slq_rollout<MODEL><<<(unsigned)((rc_ + FC::inst - 1) / FC::inst), FC::threads, fwd_smem, ctx->stream>>>(fa);
         }
         NOC_CUDA(ctx, cudaGetLastError());
         {

@@ -146,47 +146,56 @@ struct SlqFwdArgs {
   double dt, tol, armijo;
 };
 
-// The forward pass is three kernels per step length: (1) k_slq_rollout, the sequential closed-loop rollout, one
-// THREAD per active instance, only the state/input recursion (latency-critical: ~300 instructions per step);
-// (2) k_slq_stage_cost, the stage and terminal costs of the new trajectory, TIME-PARALLEL over (instance, k);
-// (3) k_slq_accept, the ordered sum of the stage costs, Armijo test and bookkeeping.  Splitting the cost out of
-// the rollout removes 60 % of the instructions from the latency-bound chain (profiles/launches_cfg3_slq_r01.csv:
-// 1.7 ms per 200-step rollout before).
-// ncu on the first thread-per-instance version (profiles/ncu_r01_k_slq_forward_v2.txt): 52 % of the issue slots
-// stalled on the long scoreboard — every step waited for its own K_k, kff_k, xbar_k, ubar_k to come from HBM.
-// Now the per-step inputs (34 16-byte chunks for n=12) are streamed through a STAGES-deep cp.async ring in shared
-// memory, laid out [chunk][thread] so that both the copies and the reads are conflict-free.
+// The forward pass is three kernels per step length: (1) k_slq_rollout, the sequential closed-loop rollout, only
+// the state/input recursion (latency-critical); (2) k_slq_stage_cost, the stage and terminal costs of the new
+// trajectory, TIME-PARALLEL over (instance, k); (3) k_slq_accept, the ordered sum of the stage costs, Armijo test
+// and bookkeeping.  Splitting the cost out of the rollout removes 60 % of the instructions from the latency-bound
+// chain (profiles/launches_cfg3_slq_r01.csv: 1.7 ms per 200-step rollout before).
+// Rollout mapping: FOUR lanes per instance, eight instances per warp, one warp per CTA.  The first
+// thread-per-instance versions were bound by the LSU, not by HBM or the dependent chain: every 16-byte access of a
+// warp went to 32 different instances, i.e. 32 sectors in 32 cache lines per instruction, ~1600 line requests per
+// warp and step (profiles/ncu_r01_k_slq_rollout_v4.txt: lg_throttle 5.1 + short/long scoreboard 8.7 stall cycles
+// per issue, 4.4 us per step).  With four lanes per instance a warp instruction covers eight 64-byte segments; lane
+// t copies every fourth 16-byte chunk of the step's inputs (K_k, kff_k, xbar_k, ubar_k) into a STAGES-deep
+// cp.async ring in shared memory, computes the feedback rows c = t (, t+4) of u = ubar + alpha k + K (x - xbar)
+// as the oracle's ascending fma chain, the four lanes exchange their u by shuffle, and every lane steps the model
+// redundantly (bitwise the same result), so no further exchange is needed.
 // Backtracking is sequential like the oracle's (alpha_j = 2^-j until the Armijo test passes) but runs as one
 // LAUNCH per step length: trial 0 goes over the whole work list, writes its trajectory IN PLACE over the nominal
 // (x_k, u_k are consumed before they are overwritten; the ring prefetches only later steps) and saves the nominal
-// it replaces to xn / un; the 1 % of instances whose trial is rejected are appended to a retry list, and trial j+1
-// (nominal read from xn / un) runs on that short list only.  alpha = 1 is accepted in 99 % of the iterations, so
-// no warp ever repeats a rollout because one of its 32 instances backtracks.
+// it replaces to xn / un; the 1 % of instances whose trial is rejected go to a retry list that the speculative
+// round settles (nominal read from xn / un).  alpha = 1 is accepted in 99 % of the iterations, so no warp ever
+// repeats a rollout because one of its instances backtracks.
 template <int MODEL>
 struct FwdCfg {
   static constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
-  static constexpr int threads = (MODEL == 0) ? 32 : 16;
+  static constexpr int lanes = 4;                    // per instance
+  static constexpr int inst = 8;                     // instances per warp = per CTA
+  static constexpr int threads = 32;
+  static constexpr int rows = m / lanes;             // feedback rows per lane
   static constexpr int stages = (MODEL == 0) ? 3 : 2;
   static constexpr int cK = m * n / 2, cX = n / 2, cU = m / 2;    // 16-byte chunks per step: K | xbar | ubar | kff
   static constexpr int chunks = cK + cX + 2 * cU;
-  static constexpr size_t ring_bytes = (size_t)stages * chunks * threads * 16;
+  static_assert((cX + cU) % 4 == 0, "the store list x_k | u_k must fill whole lane groups");
+  static constexpr size_t ring_bytes = (size_t)stages * inst * chunks * 16;
 };
 
-// (1) the sequential part: closed-loop rollout of trial a.trial, no cost evaluation.  One thread per instance.
+// (1) the sequential part: closed-loop rollout of trial a.trial, no cost evaluation.
 template <int MODEL>
 __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_rollout(const SlqFwdArgs a) {
   using C = FwdCfg<MODEL>;
-  constexpr int n = C::n, m = C::m, T = C::threads, S = C::stages;
+  constexpr int n = C::n, m = C::m, S = C::stages;
   extern __shared__ __align__(16) double sw[];
   double2* ring = reinterpret_cast<double2*>(sw);
-  const int tid = threadIdx.x;
-  const int item = blockIdx.x * T + tid;
-  if (item >= a.count) return;
+  const int lane = threadIdx.x, q = lane >> 2, t = lane & 3;
+  const long long item_raw = (long long)blockIdx.x * C::inst + q;
+  bool valid = item_raw < a.count;          // invalid slots shadow the last item: all 32 lanes stay in the shuffles
+  const int item = (int)(valid ? item_raw : a.count - 1);
   const bool cand = a.cand_J > 0;
   const long long b = a.idx[cand ? item / a.cand_J : item];
   const int trial = cand ? item % a.cand_J + 1 : a.trial;
   const int N = a.N;
-  if (trial == 0 && a.bstatus[b] != 0) return;   // regularisation exhausted: k_slq_accept records it
+  if (trial == 0 && a.bstatus[b] != 0) valid = false;   // regularisation exhausted: k_slq_accept records it
   double* xb = cand ? a.xc + (size_t)item * (N + 1) * n : a.x + (size_t)b * (N + 1) * n;   // receives the trajectory
   double* ub = cand ? a.uc + (size_t)item * N * m : a.u + (size_t)b * N * m;
   double* xs = a.xn + (size_t)b * (N + 1) * n;   // holds the nominal from trial 0 on
@@ -201,19 +210,22 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_rollout(const Sl
 
   auto prefetch = [&](int k) {
     if (k < N) {
-      double2* st = ring + (size_t)(k % S) * C::chunks * T + tid;
+      double2* st = ring + ((size_t)(k % S) * C::inst + q) * C::chunks;
       const double* srcK = Kb + (size_t)k * m * n;
       const double* srcX = xnom + (size_t)k * n;
       const double* srcU = unom + (size_t)k * m;
       const double* srcF = kb + (size_t)k * m;
 #pragma unroll
-      for (int c = 0; c < C::cK; ++c) cp_async16(smem_u32(st + c * T), srcK + 2 * c);
+      for (int c0 = 0; c0 < C::cK; c0 += 4) cp_async16(smem_u32(st + c0 + t), srcK + 2 * (c0 + t));
+      // xbar | ubar | kff: one virtual list of cX + 2 cU chunks (contiguous in the ring, three arrays in global
+      // memory); lane t takes entry 4g + t of group g, so the four lanes of an instance copy neighbouring chunks
+      // in ONE instruction (a per-lane `if` here compiles to four divergent paths of single-lane copies)
 #pragma unroll
-      for (int c = 0; c < C::cX; ++c) cp_async16(smem_u32(st + (C::cK + c) * T), srcX + 2 * c);
-#pragma unroll
-      for (int c = 0; c < C::cU; ++c) cp_async16(smem_u32(st + (C::cK + C::cX + c) * T), srcU + 2 * c);
-#pragma unroll
-      for (int c = 0; c < C::cU; ++c) cp_async16(smem_u32(st + (C::cK + C::cX + C::cU + c) * T), srcF + 2 * c);
+      for (int g = 0; g < (C::cX + 2 * C::cU + 3) / 4; ++g) {
+        const int e = 4 * g + t;
+        const double* src = e < C::cX ? srcX + 2 * e : e < C::cX + C::cU ? srcU + 2 * (e - C::cX) : srcF + 2 * (e - C::cX - C::cU);
+        if (e < C::cX + 2 * C::cU) cp_async16(smem_u32(st + C::cK + e), src);
+      }
     }
     cp_async_commit();   // one group per step, also when empty: keeps the wait_group arithmetic uniform
   };
@@ -224,47 +236,65 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_rollout(const Sl
 #pragma unroll
   for (int p = 0; p < S - 1; ++p) prefetch(p);
   for (int k = 0; k < N; ++k) {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(S - 2) : "memory");   // this lane's copies of step k have landed
+    __syncwarp();   // ... and everybody else's; every lane is done reading the stage the next prefetch overwrites
     prefetch(k + S - 1);
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(S - 1) : "memory");   // step k's group has landed
-    const double2* st = ring + (size_t)(k % S) * C::chunks * T + tid;
+    const double2* st = ring + ((size_t)(k % S) * C::inst + q) * C::chunks;
     double dx[n];
 #pragma unroll
     for (int i = 0; i < n; i += 2) {
-      const double2 v = st[(C::cK + i / 2) * T];
+      const double2 v = st[C::cK + i / 2];
       dx[i] = xk[i] - v.x; dx[i + 1] = xk[i + 1] - v.y;
     }
+    double ur[C::rows];
 #pragma unroll
-    for (int c = 0; c < m; ++c) {
+    for (int r = 0; r < C::rows; ++r) {
+      const int c = t + 4 * r;   // own feedback row
+      const double2* krow = st + (c * n) / 2;
       double tk = 0.0;
 #pragma unroll
       for (int i = 0; i < n; i += 2) {
-        const double2 kv = st[((c * n + i) / 2) * T];
+        const double2 kv = krow[i / 2];
         tk = fmad(kv.x, dx[i], tk);
         tk = fmad(kv.y, dx[i + 1], tk);
       }
-      const double2 uv = st[(C::cK + C::cX + c / 2) * T];
-      const double2 fv = st[(C::cK + C::cX + C::cU + c / 2) * T];
-      uk[c] = (((c & 1) ? uv.y : uv.x) + alpha * ((c & 1) ? fv.y : fv.x)) + tk;
+      const double* up = reinterpret_cast<const double*>(st + C::cK + C::cX);
+      ur[r] = (up[c] + alpha * up[m + c]) + tk;
     }
+#pragma unroll
+    for (int c = 0; c < m; ++c) uk[c] = __shfl_sync(0xffffffffu, ur[c / 4], (lane & ~3) | (c & 3));
     model::model_step<MODEL>(xk, uk, a.dt, xn);
+    if (valid) {
+      // x_k | u_k as one list of cX + cU chunks; lane t stores entry 4g + t of group g (value picked from the
+      // registers by t), and on trial 0 first saves the nominal chunk it replaces (still in the ring)
 #pragma unroll
-    for (int i = 0; i < n; i += 2) {
-      if (first) *reinterpret_cast<double2*>(xs + (size_t)k * n + i) = st[(C::cK + i / 2) * T];           // save nominal
-      *reinterpret_cast<double2*>(xb + (size_t)k * n + i) = make_double2(xk[i], xk[i + 1]);               // new in place
-    }
-#pragma unroll
-    for (int c = 0; c < m; c += 2) {
-      if (first) *reinterpret_cast<double2*>(us + (size_t)k * m + c) = st[(C::cK + C::cX + c / 2) * T];
-      *reinterpret_cast<double2*>(ub + (size_t)k * m + c) = make_double2(uk[c], uk[c + 1]);
+      for (int g = 0; g < (C::cX + C::cU) / 4; ++g) {
+        const int e = 4 * g + t;
+        const bool isx = e < C::cX;
+        const size_t off = isx ? (size_t)k * n + 2 * e : (size_t)k * m + 2 * (e - C::cX);
+        if (first) *reinterpret_cast<double2*>((isx ? xs : us) + off) = st[C::cK + e];
+        auto chunk = [&](int ee) { return ee < C::cX ? make_double2(xk[2 * ee], xk[2 * ee + 1]) : make_double2(uk[2 * (ee - C::cX)], uk[2 * (ee - C::cX) + 1]); };
+        const double2 v0 = chunk(4 * g), v1 = chunk(4 * g + 1), v2 = chunk(4 * g + 2), v3 = chunk(4 * g + 3);
+        const double2 lo = (t & 1) ? v1 : v0, hi = (t & 1) ? v3 : v2;
+        *reinterpret_cast<double2*>((isx ? xb : ub) + off) = (t & 2) ? hi : lo;
+      }
     }
 #pragma unroll
     for (int i = 0; i < n; ++i) xk[i] = xn[i];
   }
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  if (valid) {
 #pragma unroll
-  for (int i = 0; i < n; i += 2) {
-    if (first) *reinterpret_cast<double2*>(xs + (size_t)N * n + i) = *reinterpret_cast<const double2*>(xb + (size_t)N * n + i);
-    *reinterpret_cast<double2*>(xb + (size_t)N * n + i) = make_double2(xk[i], xk[i + 1]);
+    for (int g = 0; g < (C::cX + 3) / 4; ++g) {
+      const int e = 4 * g + t;
+      auto chunk = [&](int ee) { return ee < C::cX ? make_double2(xk[2 * ee], xk[2 * ee + 1]) : make_double2(0.0, 0.0); };
+      const double2 v0 = chunk(4 * g), v1 = chunk(4 * g + 1), v2 = chunk(4 * g + 2), v3 = chunk(4 * g + 3);
+      const double2 lo = (t & 1) ? v1 : v0, hi = (t & 1) ? v3 : v2;
+      if (e < C::cX) {
+        if (first) *reinterpret_cast<double2*>(xs + (size_t)N * n + 2 * e) = *reinterpret_cast<const double2*>(xb + (size_t)N * n + 2 * e);
+        *reinterpret_cast<double2*>(xb + (size_t)N * n + 2 * e) = (t & 2) ? hi : lo;
+      }
+    }
   }
 }
 
