@@ -349,7 +349,12 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   size_t outer = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
   if (outer < B) outer = std::max<size_t>(32, outer & ~size_t(31));
   const bool overlap = !ctx->pending.empty() && B >= 8192 && !(p->flags & NOC_FLAG_ASYNC);
-  const size_t inner_pref = overlap ? ((B / 4 + 31) & ~size_t(31)) : outer;
+  // inner chunks are whole waves of the sweep kernel (instances resident on all SMs at once: 64 per SM for n=12,
+  // 16 for n=24), about eight per call: a chunk that ends mid-wave pays for the full wave, and the smaller the last
+  // chunk, the shorter the copy that nothing hides (B = 65536: 4 x 16384 = 8 waves took 2.53 ms of sweeps, 7 chunks
+  // of one wave take 2.2 ms)
+  const size_t wave = (size_t)ctx->sm_count * (MODEL == 0 ? 64 : 16);
+  const size_t inner_pref = overlap ? std::max<size_t>(1, (B / wave + 4) / 8) * wave : outer;
   void* dxbar = nullptr;
   if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * outer * (N + 1) * n, &dxbar))) return rc;
   (void)rec;
