@@ -39,3 +39,12 @@ def test_facade_matches_oracle_on_gpu():
     _build()
     r = subprocess.run([EXE], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "FACADE OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_jacobian_sparsity_predicates_cover_the_emitters():
+    """quad_jac_nz_* / dual_jac_nz_* (the masks the fused sweeps prune with) == the entries the emitters write."""
+    src = os.path.join(ROOT, "tests", "cpp", "sparsity_test.cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", "sparsity_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", src, "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "SPARSITY OK" in r.stdout, r.stdout + r.stderr

@@ -130,6 +130,34 @@ def test_from_x0_pipeline_bitexact(oracle, solver):
     assert np.array_equal(K0, ref["K0"]) and np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
 
 
+def test_from_x0_wild_states_match_dense_oracle(oracle, solver):
+    """The fused sweep skips the structural zeros of the Jacobian (model.cuh quad_jac_nz_*); the oracle multiplies
+    them.  Both give the same bits as long as the intermediates are finite — also far from hover: angles in every
+    quadrant of the sincos reduction, pitch near +-pi/2 (sec ~ 1e3), body rates of tens of rad/s, and states that make
+    the sweep fail (status NOT_PD, NaN outputs) must fail identically."""
+    from noc_b200 import capi
+    batch, N = 96, 60
+    Q, R, Qf = pb.default_weights()
+    qr = pb.pack_qrqf(Q, R, Qf)
+    rng = np.random.default_rng(77)
+    x0 = pb.sample_x0(batch, seed=43)
+    x0[:, 6:9] = rng.uniform(-3.1, 3.1, size=(batch, 3))
+    x0[:32, 7] = np.pi / 2 + rng.uniform(-2e-3, 2e-3, size=32)
+    x0[:, 9:12] = rng.uniform(-40.0, 40.0, size=(batch, 3))
+    x0[32:40, 9:12] *= 1e3
+    ref = oracle.lqr_from_x0_batch(0, N, 0.02, x0, qr)
+    K = np.empty((batch, N, 4, 12)); K0 = np.empty((batch, 4, 12)); P0 = np.empty((batch, 12, 12)); cost = np.empty(batch)
+    status = np.full(batch, -1, dtype=np.int32)
+    solver.lqr_solve_from_x0(capi.problem(0, N), batch, x0, qr, K=K, K0=K0, P0=P0, cost=cost, status=status)
+    assert np.array_equal(status, ref["status"])
+    ok = status == 0
+    assert ok.sum() >= batch // 2
+    assert np.array_equal(K0, ref["K0"], equal_nan=True) and np.array_equal(P0, ref["P0"], equal_nan=True)
+    assert np.array_equal(cost, ref["cost"], equal_nan=True)
+    refK = oracle.lqr_batch(12, 4, N, oracle.make_ab_batch(0, N, 0.02, x0), qr, x0dev=x0)["K"]
+    assert np.array_equal(K, refK, equal_nan=True)   # all gains, incl. the NaN fill of failed instances
+
+
 def test_device_pointers_and_argmin(oracle, solver):
     """torch CUDA tensors are used in place (no staging); argmin matches numpy and skips NaN."""
     import torch
