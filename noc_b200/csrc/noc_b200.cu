@@ -38,7 +38,9 @@ struct noc_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;   // device->host copies of finished chunks, overlapped with the next chunk
+  cudaStream_t aux_stream = nullptr;    // every other inner chunk of a from-x0 call: neighbouring sweeps overlap at their edges
   cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   std::string err;
   int64_t launches = 0;
   int sm_count = 0;
@@ -372,6 +374,14 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
     }
     NOC_CUDA(ctx, cudaGetLastError());
     const size_t inner = std::min(ob, inner_pref);
+    // inner chunks alternate between the caller's stream and an auxiliary one: each is one wave of CTAs, so the
+    // next chunk's CTAs move onto the SMs as the previous chunk's retire instead of waiting for its last warp
+    cudaStream_t const main_stream = ctx->stream;
+    const bool two_streams = overlap && inner < ob;
+    if (two_streams) {
+      NOC_CUDA(ctx, cudaEventRecord(ctx->fork_ev, main_stream));            // rollout (and the staged inputs) done
+      NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
+    }
     for (size_t i = 0; i < ob; i += inner, ++chunk_no) {
       const size_t off = o + i;
       const long long cb = (long long)std::min(inner, ob - i);
@@ -384,12 +394,15 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
       fa.cost = dcost ? (double*)dcost + off : nullptr;
       fa.status = dstatus ? (int32_t*)dstatus + off : nullptr;
       fa.batch = cb; fa.N = p->N;
+      cudaStream_t const cs = (two_streams && (chunk_no & 1)) ? ctx->aux_stream : main_stream;
+      ctx->stream = cs;
       if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_LQR, true>(ctx, fa);
       else rc = launch_ric24<0, RIC_LQR, true>(ctx, fa);
+      ctx->stream = main_stream;
       if (rc) { ctx->pending.clear(); return rc; }
       if (overlap) {
         cudaEvent_t ev = ctx->chunk_ev[chunk_no & 3];
-        NOC_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+        NOC_CUDA(ctx, cudaEventRecord(ev, cs));
         NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ev, 0));
         for (auto& c : ctx->pending) {
           const size_t per = c.bytes / B;   // every output is [batch][...]
@@ -397,6 +410,10 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
                                         cudaMemcpyDeviceToHost, ctx->copy_stream));
         }
       }
+    }
+    if (two_streams) {   // the next outer chunk's rollout rewrites the scratch the auxiliary stream still reads
+      NOC_CUDA(ctx, cudaEventRecord(ctx->join_ev, ctx->aux_stream));
+      NOC_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->join_ev, 0));
     }
   }
   if (overlap) {
@@ -608,8 +625,11 @@ int noc_create(noc_ctx** out, int device_id) {
   c->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
   for (auto& e : c->chunk_ev)
     if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
+  if (cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
   c->stream = c->own_stream;
   *out = c;
   return NOC_OK;
@@ -625,6 +645,9 @@ void noc_destroy(noc_ctx* ctx) {
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : ctx->chunk_ev)
     if (e) cudaEventDestroy(e);
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+  if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
