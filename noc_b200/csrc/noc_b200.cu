@@ -823,18 +823,31 @@ int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, co
   if (!AB || !QR) return fail(ctx, NOC_ERR_BAD_ARG, "AB and QR are required");
   if (p->max_iter < 1) return fail(ctx, NOC_ERR_BAD_ARG, "max_iter must be >= 1");
   if (batch == 0) return NOC_OK;
-  if (!(p->n == 12 && p->m == 4)) return fail(ctx, NOC_ERR_UNSUPPORTED, "only n=12, m=4 has a DARE kernel");
-  if (misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned");
+  const bool tuned = p->n == 12 && p->m == 4;
+  if (tuned && misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned");
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t B = (size_t)batch, n = 12, m = 4;
+  const size_t B = (size_t)batch, n = (size_t)p->n, m = (size_t)p->m;
   const void *dAB, *dQ;
   void *dP, *dK, *dit, *dst;
-  if ((rc = stage_in(ctx, 0, AB, sizeof(double) * B * 192, &dAB))) return rc;
+  if ((rc = stage_in(ctx, 0, AB, sizeof(double) * B * (n * n + n * m), &dAB))) return rc;
   if ((rc = stage_in(ctx, 1, QR, sizeof(double) * (n * n + m * m), &dQ))) return rc;
   if ((rc = stage_out(ctx, 0, P, sizeof(double) * B * n * n, &dP))) return rc;
   if ((rc = stage_out(ctx, 1, K, sizeof(double) * B * m * n, &dK))) return rc;
   if ((rc = stage_out(ctx, 2, iters, sizeof(int32_t) * B, &dit))) return rc;
   if ((rc = stage_out(ctx, 3, status, sizeof(int32_t) * B, &dst))) return rc;
+  if (!tuned) {
+    // every other dimension (n=24, m=8 included): the thread-per-instance completeness kernel, same arithmetic
+    RicGenArgs g{};
+    g.AB = (const double*)dAB; g.QRQf = (const double*)dQ; g.K0 = (double*)dK; g.P0 = (double*)dP;
+    g.iters = (int32_t*)dit; g.status = (int32_t*)dst; g.batch = batch; g.n = p->n; g.m = p->m; g.N = 1;
+    g.layout = p->layout; g.dare = 1; g.max_iter = p->max_iter; g.tol = p->tol;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+      k_ric_generic<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(g);
+    }
+    NOC_CUDA(ctx, cudaGetLastError());
+    return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
+  }
   Ric12Args a{};
   if ((rc = build_w12(ctx, (const double*)dQ, true, &a.W, &a.Qf))) { ctx->pending.clear(); return rc; }
   a.AB = (const double*)dAB; a.K = (double*)dK; a.P0 = (double*)dP; a.iters = (int32_t*)dit; a.status = (int32_t*)dst;

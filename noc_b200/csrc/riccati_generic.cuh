@@ -1,5 +1,5 @@
-// riccati_generic.cuh — finite-horizon LTV Riccati sweep for ANY 1 <= n <= 24, 1 <= m <= 8 (NOC_MODEL_LTV_USER with
-// dimensions other than the two tuned shapes).  One thread per instance, matrices in thread-local memory: this is
+// riccati_generic.cuh — finite-horizon LTV Riccati sweep, and the DARE fixed-point iteration, for ANY 1 <= n <= 24,
+// 1 <= m <= 8 (NOC_MODEL_LTV_USER with dimensions other than the tuned shapes; DARE: everything but n=12, m=4).  One thread per instance, matrices in thread-local memory: this is
 // the completeness path of the general dense solver the C-ABI promises, not a tuned kernel — (12,4) and (24,8) go to
 // riccati12.cuh / riccati24.cuh.  Same arithmetic contract, same order of operations as
 // oracle/noc_oracle.c (form_H, chol_lower, chol_solve_neg, gains_and_value): bit-identical results.
@@ -22,6 +22,11 @@ struct RicGenArgs {
   int32_t* status;      // [batch] or nullptr
   long long batch;
   int n, m, N, layout;
+  // dare != 0 (noc_dare_solve_batch): AB is one LTI record per instance, QRQf holds Q | R only, the step is iterated
+  // from P = Q until max|P'-P| < tol max|P'| (oracle: noc_oracle_dare); P0 receives P, K0 the stationary gain
+  int dare, max_iter;
+  double tol;
+  int32_t* iters;       // [batch] or nullptr
 };
 
 __global__ void __launch_bounds__(64) k_ric_generic(const RicGenArgs a) {
@@ -30,7 +35,7 @@ __global__ void __launch_bounds__(64) k_ric_generic(const RicGenArgs a) {
   const int n = a.n, m = a.m, nm = n + m, N = a.N;
   const double* Q = a.QRQf;
   const double* R = a.QRQf + n * n;
-  const double* Qf = a.QRQf + n * n + m * m;
+  const double* Qf = a.dare ? Q : a.QRQf + n * n + m * m;
   double P[RG_NMAX * RG_NMAX], G[RG_NMAX * RG_NMMAX], Hxx[RG_NMAX * RG_NMAX], Hux[RG_MMAX * RG_NMAX];
   double Huu[RG_MMAX * RG_MMAX], L[RG_MMAX * RG_MMAX], D[RG_MMAX], rd[RG_MMAX], Kk[RG_MMAX * RG_NMAX];
   for (int e = 0; e < n * n; ++e) P[e] = Qf[e];
@@ -42,8 +47,12 @@ __global__ void __launch_bounds__(64) k_ric_generic(const RicGenArgs a) {
     if (a.layout == 1) return r[l * nm + c];
     return c < n ? r[l * n + c] : r[n * n + l * m + (c - n)];
   };
-  for (int k = N - 1; k >= 0 && !failed; --k) {
-    const double* r = a.AB + ((size_t)b * N + k) * rec;
+  const int steps = a.dare ? a.max_iter : N;
+  int dare_iters = 0;
+  bool converged = false;
+  for (int it = 0; it < steps && !failed; ++it) {
+    const int k = a.dare ? 0 : N - 1 - it;
+    const double* r = a.AB + (a.dare ? (size_t)b : (size_t)b * N + k) * rec;
     for (int i = 0; i < n; ++i)
       for (int j = 0; j < nm; ++j) {
         double acc = 0.0;
@@ -98,13 +107,21 @@ __global__ void __launch_bounds__(64) k_ric_generic(const RicGenArgs a) {
       }
       for (int i = 0; i < m; ++i) Kk[i * n + j] = -z[i];
     }
+    double dmax = 0.0, pmax = 0.0;
     for (int i = 0; i < n; ++i)
       for (int j = i; j < n; ++j) {
         double acc = Hxx[i * n + j];
         for (int c = 0; c < m; ++c) acc = fmad(Hux[c * n + i], Kk[c * n + j], acc);
+        dmax = fmax(dmax, fabs(acc - P[i * n + j]));   // P and P' are symmetric: the upper triangle sees every value
+        pmax = fmax(pmax, fabs(acc));
         P[i * n + j] = acc;
         P[j * n + i] = acc;
       }
+    if (a.dare) {
+      dare_iters = it + 1;
+      if (dmax < a.tol * pmax) { converged = true; break; }
+      continue;
+    }
     if (a.K) {
       double* kp = a.K + ((size_t)b * N + k) * m * n;
       for (int e = 0; e < m * n; ++e) kp[e] = Kk[e];
@@ -115,6 +132,20 @@ __global__ void __launch_bounds__(64) k_ric_generic(const RicGenArgs a) {
     }
   }
   const double nanv = qnan();
+  if (a.dare) {
+    if (failed) dare_iters += 1;   // the failing iteration counts (oracle returns -it)
+    if (a.K0) {
+      double* kp = a.K0 + (size_t)b * m * n;
+      for (int e = 0; e < m * n; ++e) kp[e] = failed ? nanv : Kk[e];
+    }
+    if (a.P0) {
+      double* po = a.P0 + (size_t)b * n * n;
+      for (int e = 0; e < n * n; ++e) po[e] = failed ? nanv : P[e];
+    }
+    if (a.iters) a.iters[b] = dare_iters;
+    if (a.status) a.status[b] = failed ? 1 : (converged ? 0 : 2);
+    return;
+  }
   if (failed) {
     if (a.K)
       for (int k2 = 0; k2 <= kfail; ++k2) {

@@ -72,6 +72,52 @@ def test_dare_max_iter_status(oracle, solver):
         assert it == 17 and np.array_equal(P[b], Pr) and np.array_equal(K[b], Kr)
 
 
+@pytest.mark.parametrize("n,m,layout", [(24, 8, 0), (24, 8, 1), (6, 2, 0), (3, 1, 1)])
+def test_dare_other_dimensions_bitexact(oracle, solver, n, m, layout):
+    """noc_dare_solve_batch beyond the tuned (12,4) shape: the dual-UAV model linearised near hover (n=24, m=8) and
+    small random stable systems, through the thread-per-instance kernel; P, K, iteration count, and the
+    NOT_PD / MAX_ITER outcomes as the oracle's."""
+    from noc_b200 import capi
+    rng = np.random.default_rng(100 + n)
+    batch = 9
+    recs, ABs = [], []
+    for b in range(batch):
+        if n == 24:
+            x = pb.hover_state(1, model=1)[0].copy()
+            x[[6, 7, 18, 19]] = rng.uniform(-0.2, 0.2, 4)
+            x[[8, 20]] = rng.uniform(-np.pi, np.pi, 2)
+            A, B = oracle.linearize(1, x, pb.hover_input(model=1), 0.02)
+        else:
+            A = np.eye(n) + 0.05 * rng.standard_normal((n, n))
+            B = 0.3 * rng.standard_normal((n, m))
+        ABs.append((np.ascontiguousarray(A), np.ascontiguousarray(B)))
+        recs.append(np.concatenate([A.ravel(), B.ravel()]) if layout == 0 else np.concatenate([A, B], axis=1).ravel())
+    AB = np.stack(recs)
+    if n == 24:
+        Q, R, _ = pb.default_weights(1)
+    else:
+        Q = np.diag(rng.uniform(0.5, 2.0, n)); R = np.diag(rng.uniform(0.1, 1.0, m))
+    qr = np.concatenate([Q.ravel(), R.ravel()])
+    for max_iter in (10000, 7):
+        prob = capi.problem(capi.MODEL_LTV_USER, 1, n=n, m=m, layout=layout, tol=1e-12, max_iter=max_iter)
+        P = np.empty((batch, n, n)); K = np.empty((batch, m, n))
+        iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+        solver.dare_solve_batch(prob, batch, AB, qr, P, K, iters, status)
+        for b in range(batch):
+            Pr, Kr, it = oracle.dare(ABs[b][0], ABs[b][1], Q, R, tol=1e-12, max_iter=max_iter)
+            assert it > 0 and iters[b] == it
+            assert status[b] == (2 if (it == max_iter and max_iter == 7) else 0)
+            assert np.array_equal(P[b], Pr) and np.array_equal(K[b], Kr)
+    # an indefinite R makes the first pivot fail: NOT_PD, NaN outputs, the failing iteration is counted
+    Rbad = R.copy(); Rbad[0, 0] = -1e6
+    qrb = np.concatenate([Q.ravel(), Rbad.ravel()])
+    prob = capi.problem(capi.MODEL_LTV_USER, 1, n=n, m=m, layout=layout, tol=1e-12, max_iter=50)
+    solver.dare_solve_batch(prob, batch, AB, qrb, P, K, iters, status)
+    Pr, Kr, it = oracle.dare(ABs[0][0], ABs[0][1], Q, Rbad, tol=1e-12, max_iter=50)
+    assert it < 0 and np.all(status == 1) and np.all(iters == -it)
+    assert np.all(np.isnan(P)) and np.all(np.isnan(K))
+
+
 def _slq_compare(oracle, solver, batch, N, x0, xg, qr, **kw):
     from noc_b200 import capi
     prob = capi.problem(capi.MODEL_QUAD12, N, **kw)
