@@ -713,9 +713,10 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if (rc) return rc;
   if (!AB || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "AB and QRQf are required");
   if (batch == 0) return NOC_OK;
-  if (qr_per_instance) return fail(ctx, NOC_ERR_UNSUPPORTED, "per-instance Q/R/Qf not implemented yet");
+  // per-instance weights run on the thread-per-instance kernel whatever the shape: the tuned kernels keep one W / Qf
+  // per CTA in shared memory (a per-instance copy would halve their occupancy)
   const bool n24 = (p->n == 24 && p->m == 8);
-  const bool generic = !(p->n == 12 && p->m == 4) && !n24;
+  const bool generic = qr_per_instance || (!(p->n == 12 && p->m == 4) && !n24);
   if (generic && (p->n < 1 || p->n > RG_NMAX || p->m < 1 || p->m > RG_MMAX))
     return fail(ctx, NOC_ERR_UNSUPPORTED, "LTV sweep: 1 <= n <= 24 and 1 <= m <= 8 (tuned kernels: (12,4), (24,8))");
   if (misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned (TMA bulk copies)");
@@ -725,7 +726,8 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   const void *dAB, *dQ, *dx0;
   void *dK, *dK0, *dP0, *dcost, *dstatus;
   if ((rc = stage_in(ctx, 0, AB, sizeof(double) * B * N * rec, &dAB))) return rc;
-  if ((rc = stage_in(ctx, 1, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
+  const size_t qr_len = (size_t)(2 * n * n + m * m);
+  if ((rc = stage_in(ctx, 1, QRQf, sizeof(double) * qr_len * (qr_per_instance ? B : 1), &dQ))) return rc;
   if ((rc = stage_in(ctx, 2, x0dev, sizeof(double) * B * n, &dx0))) return rc;
   if ((rc = stage_out(ctx, 0, K, sizeof(double) * B * N * m * n, &dK))) return rc;
   if ((rc = stage_out(ctx, 1, K0, sizeof(double) * B * m * n, &dK0))) return rc;
@@ -737,6 +739,7 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
     g.AB = (const double*)dAB; g.QRQf = (const double*)dQ; g.x0 = (const double*)dx0; g.K = (double*)dK;
     g.K0 = (double*)dK0; g.P0 = (double*)dP0; g.cost = (double*)dcost; g.status = (int32_t*)dstatus;
     g.batch = batch; g.n = n; g.m = m; g.N = N; g.layout = p->layout;
+    g.qr_stride = qr_per_instance ? (long long)(2 * n * n + m * m) : 0;
     {
       LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
       k_ric_generic<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(g);

@@ -13,7 +13,8 @@ constexpr int RG_NMAX = 24, RG_MMAX = 8, RG_NMMAX = RG_NMAX + RG_MMAX;
 
 struct RicGenArgs {
   const double* AB;     // [batch][N][n*n+n*m]
-  const double* QRQf;   // Q[n*n] | R[m*m] | Qf[n*n]
+  const double* QRQf;   // Q[n*n] | R[m*m] | Qf[n*n]; one block shared by the batch, or [batch][...] when qr_stride != 0
+  long long qr_stride;  // doubles between the weight blocks of consecutive instances (0 = shared)
   const double* x0;     // [batch][n] or nullptr
   double* K;            // [batch][N][m*n] or nullptr
   double* K0;           // [batch][m*n] or nullptr
@@ -33,9 +34,9 @@ __global__ void __launch_bounds__(64) k_ric_generic(const RicGenArgs a) {
   const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= a.batch) return;
   const int n = a.n, m = a.m, nm = n + m, N = a.N;
-  const double* Q = a.QRQf;
-  const double* R = a.QRQf + n * n;
-  const double* Qf = a.dare ? Q : a.QRQf + n * n + m * m;
+  const double* Q = a.QRQf + (size_t)b * (size_t)a.qr_stride;
+  const double* R = Q + n * n;
+  const double* Qf = a.dare ? Q : Q + n * n + m * m;
   double P[RG_NMAX * RG_NMAX], G[RG_NMAX * RG_NMMAX], Hxx[RG_NMAX * RG_NMAX], Hux[RG_MMAX * RG_NMAX];
   double Huu[RG_MMAX * RG_MMAX], L[RG_MMAX * RG_MMAX], D[RG_MMAX], rd[RG_MMAX], Kk[RG_MMAX * RG_NMAX];
   for (int e = 0; e < n * n; ++e) P[e] = Qf[e];

@@ -47,9 +47,6 @@ def test_bad_arguments_return_codes(solver):
         solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5, n=30, m=2), 4, np.zeros((4, 5, 960)), _qr())
     assert e.value.code == capi.ERR_UNSUPPORTED
     with pytest.raises(capi.NocError) as e:
-        solver.lqr_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5), 4, np.zeros((4, 5, 192)), _qr(), qr_per_instance=True)
-    assert e.value.code == capi.ERR_UNSUPPORTED
-    with pytest.raises(capi.NocError) as e:
         solver.slq_solve_batch(capi.problem(0, 5, n_alpha=40), 4, x0, x0, _qr())
     assert e.value.code == capi.ERR_BAD_ARG
     with pytest.raises(capi.NocError) as e:

@@ -267,3 +267,32 @@ def test_generic_dimensions_not_pd(oracle, solver):
     assert np.array_equal(status, ref["status"]) and np.array_equal(np.isnan(K), np.isnan(ref["K"]))
     ok = ~np.isnan(ref["K"])
     assert np.array_equal(K[ok], ref["K"][ok]) and np.array_equal(np.isnan(P0), np.isnan(ref["P0"]))
+
+
+@pytest.mark.parametrize("n,m", [(12, 4), (24, 8), (5, 2)])
+def test_per_instance_weights_bitexact(oracle, solver, n, m):
+    """qr_per_instance=1: every instance brings its own Q | R | Qf block; each must equal the oracle run with that
+    instance's weights (also for the tuned shapes, which then take the thread-per-instance kernel)."""
+    from noc_b200 import capi
+    rng = np.random.default_rng(500 + n)
+    batch, N = 7, 12
+    AB = np.empty((batch, N, n * n + n * m))
+    for b in range(batch):
+        for k in range(N):
+            A = np.eye(n) + 0.05 * rng.standard_normal((n, n)); Bm = 0.2 * rng.standard_normal((n, m))
+            AB[b, k] = np.concatenate([A.ravel(), Bm.ravel()])
+    qr = np.empty((batch, 2 * n * n + m * m))
+    for b in range(batch):
+        Q = np.diag(rng.uniform(0.5, 5.0, n)); R = np.diag(rng.uniform(0.05, 1.0, m)); Qf = 10.0 * Q
+        M = 0.1 * rng.standard_normal((n, n)); Q = Q + M @ M.T       # dense symmetric PSD part
+        qr[b] = np.concatenate([Q.ravel(), R.ravel(), Qf.ravel()])
+    x0 = rng.standard_normal((batch, n))
+    K = np.empty((batch, N, m, n)); K0 = np.empty((batch, m, n)); P0 = np.empty((batch, n, n)); cost = np.empty(batch)
+    status = np.full(batch, -1, dtype=np.int32)
+    prob = capi.problem(capi.MODEL_LTV_USER, N, n=n, m=m)
+    solver.lqr_solve_batch(prob, batch, AB, qr, x0dev=x0, K=K, K0=K0, P0=P0, cost=cost, status=status, qr_per_instance=True)
+    for b in range(batch):
+        ref = oracle.lqr_batch(n, m, N, AB[b:b + 1], qr[b], x0dev=x0[b:b + 1])
+        assert status[b] == ref["status"][0] == 0
+        assert np.array_equal(K[b], ref["K"][0]) and np.array_equal(K0[b], ref["K0"][0])
+        assert np.array_equal(P0[b], ref["P0"][0]) and cost[b] == ref["cost"][0]
