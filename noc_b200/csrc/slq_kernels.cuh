@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
 // (alpha = 2^-(c+1)) in ascending k and runs its Armijo test; the first passing candidate in order wins (the
 // oracle's sequential backtracking stops at the same one); then the warp copies the winning trajectory (or, if none
 // passed, the saved nominal) over x, u with coalesced 16-byte accesses.  (One thread per instance did both jobs
-// serially at first: 0.5-0.6 ms per launch for a handful of instances, profiles/launches_cfg3_slq_r01c.csv.)
+// serially at first: 0.5-0.6 ms per launch for a handful of instances, profiles/ncu_r01_k_slq_rollout_v4.txt.)
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
   constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
