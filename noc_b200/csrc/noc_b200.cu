@@ -356,7 +356,9 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   // chunk, the shorter the copy that nothing hides (B = 65536: 4 x 16384 = 8 waves took 2.53 ms of sweeps, 7 chunks
   // of one wave take 2.2 ms)
   const size_t wave = (size_t)ctx->sm_count * (MODEL == 0 ? 64 : 16);
-  const size_t inner_pref = overlap ? std::max<size_t>(1, (B / wave + 4) / 8) * wave : outer;
+  size_t inner_pref = overlap ? std::max<size_t>(1, (B / wave + 4) / 8) * wave : outer;
+  if (const char* e = std::getenv("NOC_B200_CHUNK_WAVES"))   // experiment hook
+    if (overlap) inner_pref = std::max<size_t>(1, (size_t)std::atoll(e)) * wave;
   void* dxbar = nullptr;
   if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * outer * (N + 1) * n, &dxbar))) return rc;
   (void)rec;
@@ -377,7 +379,7 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
     // inner chunks alternate between the caller's stream and an auxiliary one: each is one wave of CTAs, so the
     // next chunk's CTAs move onto the SMs as the previous chunk's retire instead of waiting for its last warp
     cudaStream_t const main_stream = ctx->stream;
-    const bool two_streams = overlap && inner < ob;
+    const bool two_streams = overlap && inner < ob && !std::getenv("NOC_B200_ONE_STREAM");
     if (two_streams) {
       NOC_CUDA(ctx, cudaEventRecord(ctx->fork_ev, main_stream));            // rollout (and the staged inputs) done
       NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));

@@ -145,3 +145,35 @@ def test_outer_chunking_of_the_nominal_scratch(oracle):
     s2.lqr_solve_from_x0(capi.problem(0, N), batch, x0, qr, K0=K0b, cost=costb)
     s2.close()
     assert np.array_equal(K0, K0b) and np.array_equal(cost, costb)
+
+
+def test_inner_chunks_on_two_streams_do_not_change_results(oracle):
+    """Host outputs and batch >= 8192: the batch is cut into one-wave inner chunks that alternate between two streams
+    while a third copies finished chunks back.  Same bits as the single-stream schedule, as two-wave chunks, and as
+    the oracle (NOC_B200_ONE_STREAM / NOC_B200_CHUNK_WAVES are the scheduler's test hooks)."""
+    import os
+    from noc_b200 import capi
+    batch, N = 24000, 20
+    qr = _qr()
+    x0 = pb.sample_x0(batch, seed=8)
+    outs = []
+    for env in ({}, {"NOC_B200_ONE_STREAM": "1"}, {"NOC_B200_CHUNK_WAVES": "2"}):
+        os.environ.update(env)
+        try:
+            s = capi.Solver(0)
+            K0 = np.empty((batch, 4, 12)); P0 = np.empty((batch, 12, 12)); cost = np.empty(batch)
+            st = np.full(batch, -1, dtype=np.int32)
+            for _ in range(2):   # the second call reuses scratch, events and both streams
+                s.lqr_solve_from_x0(capi.problem(0, N), batch, x0, qr, K0=K0, P0=P0, cost=cost, status=st)
+            s.close()
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert np.all(st == 0)
+        outs.append((K0, P0, cost))
+    for K0, P0, cost in outs[1:]:
+        assert np.array_equal(K0, outs[0][0]) and np.array_equal(P0, outs[0][1]) and np.array_equal(cost, outs[0][2])
+    sel = np.arange(0, batch, 211)
+    ref = oracle.lqr_from_x0_batch(0, N, 0.02, x0[sel], qr)
+    assert np.array_equal(outs[0][0][sel], ref["K0"]) and np.array_equal(outs[0][1][sel], ref["P0"])
+    assert np.array_equal(outs[0][2][sel], ref["cost"])

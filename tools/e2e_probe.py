@@ -14,7 +14,7 @@ h_cost = torch.empty(B, dtype=torch.float64).pin_memory()
 h_status = torch.empty(B, dtype=torch.int32).pin_memory()
 p = capi.problem(capi.MODEL_QUAD12, N)
 ts = []
-for i in range(40):
+for i in range(int(os.environ.get('CALLS', 40))):
     t = time.perf_counter()
     s.lqr_solve_from_x0(p, B, h_x0, qr, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
     ts.append((time.perf_counter() - t) * 1e3)
@@ -24,3 +24,6 @@ for i in range(5):
     s.lqr_solve_from_x0(p, B, h_x0, qr, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
 s.profile_enable(False)
 print({k: s.profile_read(v)[0] / 5 for k, v in (("rollout", 1), ("riccati", 3), ("setup", 0))})
+
+a = np.array(ts[2:])
+print("stats ms: median %.3f mean %.3f p90 %.3f max %.3f  slow(>1.15x median) %d of %d" % (np.median(a), a.mean(), np.percentile(a, 90), a.max(), int((a > 1.15 * np.median(a)).sum()), a.size))
