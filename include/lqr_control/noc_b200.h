@@ -82,6 +82,9 @@ typedef struct {
   double tol;              /* SLQ: relative cost decrease; DARE: max|dP|/max|P| */
   double reg0;             /* SLQ: initial Levenberg-Marquardt mu added to the diagonal of Quu */
   double armijo;           /* SLQ: sufficient-decrease constant (1e-4) */
+  double u_min, u_max;     /* SLQ: box on every input component (control-limited DDP: box QP for the feed-forward,
+                              zero feedback on clamped inputs, clamped rollouts).  -INFINITY / +INFINITY
+                              (the defaults) = unconstrained.  NOC_MODEL_QUAD12 only. */
 } noc_problem_t;
 
 /* ---- context ------------------------------------------------------------------------------ */
@@ -109,7 +112,7 @@ int noc_profile_enable(noc_ctx* ctx, int on);
 /* total device milliseconds and launch count of one kernel id since the last reset (synchronises) */
 int noc_profile_read(noc_ctx* ctx, int kernel_id, double* total_ms, int64_t* launches);
 int noc_profile_reset(noc_ctx* ctx);
-/* fill defaults: tol 1e-8, max_iter 50, n_alpha 11, armijo 1e-4, dt 0.02, layout A_THEN_B */
+/* fill defaults: tol 1e-8, max_iter 50, n_alpha 11, armijo 1e-4, dt 0.02, layout A_THEN_B, no input box */
 void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N);
 
 /* ---- SURVEY §8(a) a2+a3: backward Riccati recursion, Cholesky, gains -------------------------

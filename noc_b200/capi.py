@@ -36,7 +36,8 @@ KERNEL_SETUP, KERNEL_ROLLOUT, KERNEL_LINEARIZE, KERNEL_RICCATI, KERNEL_FORWARD, 
 class Problem(C.Structure):
     _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("N", C.c_int32), ("model", C.c_int32),
                 ("layout", C.c_int32), ("max_iter", C.c_int32), ("n_alpha", C.c_int32), ("flags", C.c_int32),
-                ("dt", C.c_double), ("tol", C.c_double), ("reg0", C.c_double), ("armijo", C.c_double)]
+                ("dt", C.c_double), ("tol", C.c_double), ("reg0", C.c_double), ("armijo", C.c_double),
+                ("u_min", C.c_double), ("u_max", C.c_double)]
 
 
 class NocError(RuntimeError):

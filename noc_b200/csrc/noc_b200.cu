@@ -206,9 +206,9 @@ bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u)
 template <int MODE> struct RicCfg { static constexpr int warps = 4, min_ctas = 2; };
 template <> struct RicCfg<RIC_AFFINE> { static constexpr int warps = 7, min_ctas = 1; };
 
-template <int LAYOUT, int MODE, bool FUSED, int W, int MIN_CTAS>
+template <int LAYOUT, int MODE, bool FUSED, int W, int MIN_CTAS, bool BOX = false>
 int launch_ric12_cfg(noc_ctx* ctx, const Ric12Args& a) {
-  auto kern = k_ric12<LAYOUT, MODE, FUSED, W, MIN_CTAS>;
+  auto kern = k_ric12<LAYOUT, MODE, FUSED, W, MIN_CTAS, BOX>;
   const size_t smem = ric12_smem_bytes<MODE, FUSED>(W);
   // function attributes are per device and contexts may live on several devices / host threads: set them on every
   // launch (two cheap driver calls) instead of caching a process-wide flag
@@ -224,15 +224,15 @@ int launch_ric12_cfg(noc_ctx* ctx, const Ric12Args& a) {
   return NOC_OK;
 }
 
-template <int LAYOUT, int MODE, bool FUSED = false>
+template <int LAYOUT, int MODE, bool FUSED = false, bool BOX = false>
 int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
   // short work lists (the tail of an SLQ solve, small batches): one warp per CTA, so that the few warps spread over
   // all SMs instead of sharing a handful — the sweep is then latency-bound and a warp alone on an SM steps ~2x faster
 #if defined(NOC_EXP_MASK)   // experiment build only: one 7/8-warp CTA per SM, warps selected by the mask
   return launch_ric12_cfg<LAYOUT, MODE, FUSED, (MODE == RIC_AFFINE ? 7 : 8), 1>(ctx, a);
 #else
-  if (a.batch <= 8LL * 2 * ctx->sm_count) return launch_ric12_cfg<LAYOUT, MODE, FUSED, 1, 1>(ctx, a);
-  return launch_ric12_cfg<LAYOUT, MODE, FUSED, RicCfg<MODE>::warps, RicCfg<MODE>::min_ctas>(ctx, a);
+  if (a.batch <= 8LL * 2 * ctx->sm_count) return launch_ric12_cfg<LAYOUT, MODE, FUSED, 1, 1, BOX>(ctx, a);
+  return launch_ric12_cfg<LAYOUT, MODE, FUSED, RicCfg<MODE>::warps, RicCfg<MODE>::min_ctas, BOX>(ctx, a);
 #endif
 }
 
@@ -485,6 +485,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   if (MODEL == 0) rc = build_w12(ctx, (const double*)dQ, false, &ra.W, &ra.Qf);
   else rc = build_w24(ctx, (const double*)dQ, &ra.W, &ra.Qf);
   if (rc) { ctx->pending.clear(); return rc; }
+  const bool boxed = std::isfinite(p->u_min) || std::isfinite(p->u_max);   // input box: control-limited backward pass
   int count = (int)batch;
   int32_t* cur = (int32_t*)didx0;
   int32_t* nxt = (int32_t*)didx1;
@@ -495,7 +496,10 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
     ra.xgoal = (const double*)dxg; ra.K = (double*)dK; ra.kff = (double*)dkff; ra.dV = (double*)ddV;
     ra.mu = (double*)dmu; ra.status = (int32_t*)dbst; ra.batch = count; ra.N = p->N;
     ra.dt = p->dt;
-    if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_AFFINE, true>(ctx, ra);
+    if constexpr (MODEL == 0) {
+      ra.u_min = p->u_min; ra.u_max = p->u_max;
+      rc = boxed ? launch_ric12<0, RIC_AFFINE, true, true>(ctx, ra) : launch_ric12<0, RIC_AFFINE, true>(ctx, ra);
+    }
     else rc = launch_ric24<0, RIC_AFFINE, true>(ctx, ra);
     if (rc) { ctx->pending.clear(); return rc; }
     // a4: closed-loop rollouts with backtracking, acceptance, convergence, next work list.  One launch per step
@@ -509,7 +513,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
     fa.bstatus = (const int32_t*)dbst;
     fa.status = (int32_t*)dst; fa.iters = (int32_t*)dit; fa.alpha_idx = (int32_t*)dai; fa.N = p->N;
     fa.iter = it; fa.max_iter = p->max_iter; fa.n_alpha = p->n_alpha; fa.dt = p->dt; fa.tol = p->tol;
-    fa.armijo = p->armijo;
+    fa.armijo = p->armijo; fa.u_min = p->u_min; fa.u_max = p->u_max;
     int32_t hc[2] = {0, 0};
     const int32_t* list = cur;
     int list_count = count;
@@ -610,6 +614,8 @@ void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N) {
   p->tol = 1e-8;
   p->reg0 = 0.0;
   p->armijo = 1e-4;
+  p->u_min = -INFINITY;
+  p->u_max = INFINITY;
 }
 
 int noc_create(noc_ctx** out, int device_id) {
@@ -871,6 +877,9 @@ int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if (!x0 || !xgoal || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0, xgoal and QRQf are required");
   if (p->max_iter < 1 || p->n_alpha < 1 || p->n_alpha > 32)
     return fail(ctx, NOC_ERR_BAD_ARG, "need max_iter >= 1 and 1 <= n_alpha <= 32");
+  if (!(p->u_min < p->u_max)) return fail(ctx, NOC_ERR_BAD_ARG, "need u_min < u_max (-INFINITY / INFINITY = no input box)");
+  if ((std::isfinite(p->u_min) || std::isfinite(p->u_max)) && p->model != NOC_MODEL_QUAD12)
+    return fail(ctx, NOC_ERR_UNSUPPORTED, "the input box is implemented for NOC_MODEL_QUAD12 only");
   if (batch > 0x7fffffffLL) return fail(ctx, NOC_ERR_BAD_ARG, "batch too large for 32-bit work lists");
   if (batch == 0) return NOC_OK;
   return p->model == NOC_MODEL_QUAD12

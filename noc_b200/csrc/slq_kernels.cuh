@@ -144,6 +144,7 @@ struct SlqFwdArgs {
   int max_iter;
   int n_alpha;              // <= 32
   double dt, tol, armijo;
+  double u_min, u_max;      // input box of the closed-loop rollouts (+-inf = none)
 };
 
 // The forward pass is three kernels per step length: (1) k_slq_rollout, the sequential closed-loop rollout, only
@@ -259,7 +260,8 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_rollout(const Sl
         tk = fmad(kv.y, dx[i + 1], tk);
       }
       const double* up = reinterpret_cast<const double*>(st + C::cK + C::cX);
-      ur[r] = (up[c] + alpha * up[m + c]) + tk;
+      const double v = (up[c] + alpha * up[m + c]) + tk;
+      ur[r] = v < a.u_min ? a.u_min : (v > a.u_max ? a.u_max : v);   // the comparisons are false for NaN: a diverged rollout stays NaN
     }
 #pragma unroll
     for (int c = 0; c < m; ++c) uk[c] = __shfl_sync(0xffffffffu, ur[c / 4], (lane & ~3) | (c & 3));

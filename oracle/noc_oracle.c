@@ -377,6 +377,120 @@ static void gains_and_value(step_ws* w, double* K, double* Pn) {
     }
 }
 
+/* ---- input box u_min <= u <= u_max: control-limited DDP (Tassa, Mansard, Todorov 2014), DESIGN.md §2.4b ----
+ * Backward pass: the feed-forward k solves  min 0.5 k'Quu k + Qu'k  s.t.  lo <= k <= hi  (lo = u_min - ubar,
+ * hi = u_max - ubar) by projected Newton; inputs clamped at the solution get zero feedback rows, the free ones
+ * K_f = -Quu_ff^{-1} Qux_f.  Every sum is an ascending fma chain, so the CUDA kernel reproduces it bit for bit. */
+#define QP_MAXIT 16
+#define QP_MAXLS 12
+#define QP_ARMIJO 0.1
+#define QP_GTOL 1e-10
+
+static double huu_sym(const step_ws* w, int a, int b) {
+  return (b <= a) ? w->Huu[a * w->m + b] : w->Huu[b * w->m + a];
+}
+
+/* r = Huu x ; returns f(x) = sum_a x_a (0.5 r_a + g_a) */
+static double qp_eval(const step_ws* w, const double* g, const double* x, double* r) {
+  const int m = w->m;
+  for (int a = 0; a < m; ++a) {
+    double s = 0.0;
+    for (int b = 0; b < m; ++b) s = fma(huu_sym(w, a, b), x[b], s);
+    r[a] = s;
+  }
+  double f = 0.0;
+  for (int a = 0; a < m; ++a) f = fma(x[a], fma(0.5, r[a], g[a]), f);
+  return f;
+}
+
+/* factorisation of Huu with the rows / columns of the clamped inputs replaced by those of the identity */
+static int chol_lower_masked(const step_ws* w, const int* clamped, step_ws* wm) {
+  const int m = w->m;
+  wm->n = w->n; wm->m = m;
+  for (int a = 0; a < m; ++a)
+    for (int b = 0; b <= a; ++b)
+      wm->Huu[a * m + b] = (clamped[a] || clamped[b]) ? (a == b ? 1.0 : 0.0) : w->Huu[a * m + b];
+  return chol_lower(wm);
+}
+
+static double clampd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+/* x: in = start point, out = solution; clamped[a] = 1 for the inputs held at a bound by the solution */
+static void box_qp(const step_ws* w, const double* g, const double* lo, const double* hi, double* x, int* clamped) {
+  const int m = w->m;
+  double r[MMAX], grad[MMAX], rhs[MMAX], dx[MMAX], xc[MMAX], rc[MMAX];
+  step_ws wm;
+  double gmax = 0.0;
+  for (int a = 0; a < m; ++a) { x[a] = clampd(x[a], lo[a], hi[a]); if (fabs(g[a]) > gmax) gmax = fabs(g[a]); }
+  double f = qp_eval(w, g, x, r);
+  for (int it = 0; it < QP_MAXIT; ++it) {
+    int nfree = 0;
+    double gn = 0.0;
+    for (int a = 0; a < m; ++a) {
+      grad[a] = r[a] + g[a];
+      clamped[a] = (x[a] <= lo[a] && grad[a] > 0.0) || (x[a] >= hi[a] && grad[a] < 0.0);
+      if (!clamped[a]) { ++nfree; if (fabs(grad[a]) > gn) gn = fabs(grad[a]); }
+    }
+    if (nfree == 0 || gn < QP_GTOL * (1.0 + gmax)) return;
+    if (chol_lower_masked(w, clamped, &wm) != NOC_O_OK) return;
+    for (int a = 0; a < m; ++a) rhs[a] = clamped[a] ? 0.0 : grad[a];
+    chol_solve_neg(&wm, rhs, 1, dx, 1);           /* Newton step on the free subspace, zero on the clamped one */
+    double sdotg = 0.0;
+    for (int a = 0; a < m; ++a) sdotg = fma(grad[a], dx[a], sdotg);
+    if (!(sdotg < 0.0)) return;
+    double step = 1.0;
+    int ok = 0;
+    for (int ls = 0; ls < QP_MAXLS; ++ls) {
+      for (int a = 0; a < m; ++a) xc[a] = clampd(fma(step, dx[a], x[a]), lo[a], hi[a]);
+      const double fc = qp_eval(w, g, xc, rc);
+      if (fc - f <= QP_ARMIJO * (step * sdotg)) {
+        for (int a = 0; a < m; ++a) { x[a] = xc[a]; r[a] = rc[a]; }
+        f = fc;
+        ok = 1;
+        break;
+      }
+      step = step * 0.5;
+    }
+    if (!ok) return;
+  }
+  /* iteration cap: the clamped set of the last accepted point */
+  for (int a = 0; a < m; ++a) {
+    const double ga = r[a] + g[a];
+    clamped[a] = (x[a] <= lo[a] && ga > 0.0) || (x[a] >= hi[a] && ga < 0.0);
+  }
+}
+
+/* K rows of the free inputs = -Huu_ff^{-1} Hux_f, zero rows for the clamped ones; P' = Hxx + Hux^T K */
+static int gains_and_value_box(step_ws* w, const int* clamped, double* K, double* Pn) {
+  const int n = w->n, m = w->m;
+  step_ws wm;
+  if (chol_lower_masked(w, clamped, &wm) != NOC_O_OK) return NOC_O_NOT_PD;
+  double rhs[MMAX];
+  for (int j = 0; j < n; ++j) {
+    for (int a = 0; a < m; ++a) rhs[a] = clamped[a] ? 0.0 : w->Hux[a * n + j];
+    chol_solve_neg(&wm, rhs, 1, K + j, n);
+  }
+  for (int i = 0; i < n; ++i)
+    for (int j = i; j < n; ++j) {
+      double acc = w->Hxx[i * n + j];
+      for (int a = 0; a < m; ++a) acc = fma(w->Hux[a * n + i], K[a * n + j], acc);
+      Pn[i * n + j] = acc;
+      Pn[j * n + i] = acc;
+    }
+  return NOC_O_OK;
+}
+
+/* test hook: the box QP alone.  Huu[m*m] (lower triangle read), g, lo, hi, x (in: start, out: solution), clamped[m] */
+void noc_oracle_box_qp(int m, const double* Huu, const double* g, const double* lo, const double* hi, double* x,
+                       int32_t* clamped) {
+  step_ws w;
+  w.n = 0; w.m = m;
+  memcpy(w.Huu, Huu, (size_t)m * m * sizeof(double));
+  int cl[MMAX];
+  box_qp(&w, g, lo, hi, x, cl);
+  for (int a = 0; a < m; ++a) clamped[a] = cl[a];
+}
+
 static double quad_form_half(int n, const double* P, const double* x) {
   double c = 0.0;
   for (int i = 0; i < n; ++i) {
@@ -580,6 +694,13 @@ double noc_oracle_traj_cost(int model, int N, const double* x, const double* u, 
 int noc_oracle_backward_affine(int model, int N, double dt, const double* xbar, const double* ubar,
                                const double* xgoal, const double* QRQf, double mu, double* K,
                                double* kff, double* dV) {
+  return noc_oracle_backward_affine_box(model, N, dt, xbar, ubar, xgoal, QRQf, mu, -INFINITY, INFINITY, K, kff, dV);
+}
+
+int noc_oracle_backward_affine_box(int model, int N, double dt, const double* xbar, const double* ubar,
+                                   const double* xgoal, const double* QRQf, double mu, double u_min,
+                                   double u_max, double* K, double* kff, double* dV) {
+  const int boxed = isfinite(u_min) || isfinite(u_max);
   int n, m;
   noc_oracle_model_dims(model, &n, &m);
   const int nm = n + m;
@@ -614,8 +735,22 @@ int noc_oracle_backward_affine(int model, int N, double dt, const double* xbar, 
     if (chol_lower(&w) != NOC_O_OK) return NOC_O_NOT_PD;
     double* Kk = K + (size_t)k * m * n;
     double* kk = kff + (size_t)k * m;
-    gains_and_value(&w, Kk, Pn);
     chol_solve_neg(&w, h + n, 1, kk, 1);
+    int inside = 1;
+    double lo[MMAX], hi[MMAX];
+    if (boxed)
+      for (int a = 0; a < m; ++a) {
+        lo[a] = u_min - uk[a];
+        hi[a] = u_max - uk[a];
+        if (!(kk[a] > lo[a] && kk[a] < hi[a])) inside = 0;
+      }
+    if (inside) {
+      gains_and_value(&w, Kk, Pn);
+    } else {   /* some input would leave the box: constrained feed-forward, zero gains on the clamped inputs */
+      int clamped[MMAX];
+      box_qp(&w, h + n, lo, hi, kk, clamped);
+      if (gains_and_value_box(&w, clamped, Kk, Pn) != NOC_O_OK) return NOC_O_NOT_PD;
+    }
     for (int i = 0; i < n; ++i) {
       double acc = h[i];
       for (int a = 0; a < m; ++a) acc = fma(w.Hux[a * n + i], kk[a], acc);
@@ -644,6 +779,14 @@ int noc_oracle_backward_affine(int model, int N, double dt, const double* xbar, 
 double noc_oracle_forward(int model, int N, double dt, const double* xbar, const double* ubar,
                           const double* xgoal, const double* QRQf, const double* K, const double* kff,
                           double alpha, double* xnew, double* unew) {
+  return noc_oracle_forward_box(model, N, dt, xbar, ubar, xgoal, QRQf, K, kff, alpha, -INFINITY, INFINITY, xnew, unew);
+}
+
+/* Forward pass with the input box: every component of u is projected onto [u_min, u_max] after the feedback law.
+ * The comparisons are false for NaN, so a diverged rollout stays NaN, and infinite bounds change nothing. */
+double noc_oracle_forward_box(int model, int N, double dt, const double* xbar, const double* ubar,
+                              const double* xgoal, const double* QRQf, const double* K, const double* kff,
+                              double alpha, double u_min, double u_max, double* xnew, double* unew) {
   int n, m;
   noc_oracle_model_dims(model, &n, &m);
   const double *Q = QRQf, *R = QRQf + n * n, *Qf = QRQf + n * n + m * m;
@@ -658,7 +801,7 @@ double noc_oracle_forward(int model, int N, double dt, const double* xbar, const
     for (int a = 0; a < m; ++a) {
       double t = 0.0;
       for (int j = 0; j < n; ++j) t = fma(K[(size_t)k * m * n + a * n + j], dx[j], t);
-      uk[a] = (ubar[(size_t)k * m + a] + alpha * kff[(size_t)k * m + a]) + t;
+      uk[a] = clampd((ubar[(size_t)k * m + a] + alpha * kff[(size_t)k * m + a]) + t, u_min, u_max);
     }
     J = J + stage_cost(n, m, xk, uk, xgoal, uh, Q, R);
     noc_oracle_step(model, xk, uk, dt, xk + n);
@@ -689,7 +832,7 @@ int noc_oracle_slq(const noc_oracle_slq_opts* o, const double* x0, const double*
   for (it = 0; it < o->max_iter; ++it) {
     double dV[2];
     int bad = 0;
-    while (noc_oracle_backward_affine(o->model, N, o->dt, x, u, xgoal, QRQf, mu, Kw, kw, dV) != NOC_O_OK) {
+    while (noc_oracle_backward_affine_box(o->model, N, o->dt, x, u, xgoal, QRQf, mu, o->u_min, o->u_max, Kw, kw, dV) != NOC_O_OK) {
       mu = (mu * 10.0 > 1e-6) ? mu * 10.0 : 1e-6;
       if (mu > 1e6) { bad = 1; break; }
     }
@@ -698,7 +841,7 @@ int noc_oracle_slq(const noc_oracle_slq_opts* o, const double* x0, const double*
     double Jn = J;
     double alpha = 1.0;
     for (int j = 0; j < o->n_alpha; ++j) {
-      const double Ja = noc_oracle_forward(o->model, N, o->dt, x, u, xgoal, QRQf, Kw, kw, alpha, xn, un);
+      const double Ja = noc_oracle_forward_box(o->model, N, o->dt, x, u, xgoal, QRQf, Kw, kw, alpha, o->u_min, o->u_max, xn, un);
       const double expected = -(alpha * dV[0] + (alpha * alpha) * dV[1]);
       if (J - Ja >= o->armijo * expected) { accepted = j; Jn = Ja; break; }
       alpha = alpha * 0.5;

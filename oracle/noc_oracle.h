@@ -75,6 +75,7 @@ int noc_oracle_dare(int n, int m, const double* A, const double* B, const double
 typedef struct {
   int model, N, max_iter, n_alpha;
   double dt, tol, reg0, armijo;
+  double u_min, u_max;   /* box on every input component; -INFINITY / INFINITY = unconstrained */
 } noc_oracle_slq_opts;
 /* x[(N+1)*n], u[N*m], K[N*m*n] (may be NULL), kff[N*m] (may be NULL), alpha_idx[max_iter] (filled with -1
  * beyond iters), returns status; *iters, *cost, *reg (final mu) */
@@ -93,6 +94,14 @@ int noc_oracle_backward_affine(int model, int N, double dt, const double* xbar, 
 double noc_oracle_forward(int model, int N, double dt, const double* xbar, const double* ubar,
                           const double* xgoal, const double* QRQf, const double* K, const double* kff,
                           double alpha, double* xnew, double* unew);
+int noc_oracle_backward_affine_box(int model, int N, double dt, const double* xbar, const double* ubar,
+                                   const double* xgoal, const double* QRQf, double mu, double u_min,
+                                   double u_max, double* K, double* kff, double* dV);
+double noc_oracle_forward_box(int model, int N, double dt, const double* xbar, const double* ubar,
+                              const double* xgoal, const double* QRQf, const double* K, const double* kff,
+                              double alpha, double u_min, double u_max, double* xnew, double* unew);
+void noc_oracle_box_qp(int m, const double* Huu, const double* g, const double* lo, const double* hi, double* x,
+                       int32_t* clamped);
 double noc_oracle_traj_cost(int model, int N, const double* x, const double* u, const double* xgoal,
                             const double* QRQf);
 

@@ -36,7 +36,8 @@ def build(force: bool = False) -> str:
 
 class SlqOpts(C.Structure):
     _fields_ = [("model", C.c_int), ("N", C.c_int), ("max_iter", C.c_int), ("n_alpha", C.c_int),
-                ("dt", C.c_double), ("tol", C.c_double), ("reg0", C.c_double), ("armijo", C.c_double)]
+                ("dt", C.c_double), ("tol", C.c_double), ("reg0", C.c_double), ("armijo", C.c_double),
+                ("u_min", C.c_double), ("u_max", C.c_double)]
 
 
 _lib = None
@@ -184,8 +185,8 @@ def dare(A, B, Q, R, tol=1e-12, max_iter=10000):
     return P, K, it
 
 
-def slq_opts(model, N, dt=0.02, tol=1e-8, max_iter=50, n_alpha=11, reg0=0.0, armijo=1e-4):
-    return SlqOpts(model, N, max_iter, n_alpha, dt, tol, reg0, armijo)
+def slq_opts(model, N, dt=0.02, tol=1e-8, max_iter=50, n_alpha=11, reg0=0.0, armijo=1e-4, u_min=-np.inf, u_max=np.inf):
+    return SlqOpts(model, N, max_iter, n_alpha, dt, tol, reg0, armijo, u_min, u_max)
 
 
 def slq(opts, x0, xgoal, QRQf, want_K=True):
@@ -246,3 +247,13 @@ def forward(model, N, dt, xbar, ubar, xgoal, QRQf, K, kff, alpha):
 def traj_cost(model, N, x, u, xgoal, QRQf):
     x, u, xgoal, QRQf = _c(x), _c(u), _c(xgoal), _c(QRQf)
     return lib().noc_oracle_traj_cost(model, N, _p(x), _p(u), _p(xgoal), _p(QRQf))
+
+
+def box_qp(H, g, lo, hi, x0=None):
+    """min 0.5 x'Hx + g'x, lo <= x <= hi by the oracle's projected Newton; returns x, clamped"""
+    H, g, lo, hi = _c(H), _c(g), _c(lo), _c(hi)
+    m = g.shape[0]
+    x = np.zeros(m) if x0 is None else np.array(x0, dtype=np.float64)
+    cl = np.zeros(m, dtype=np.int32)
+    lib().noc_oracle_box_qp(m, _p(H), _p(g), _p(lo), _p(hi), _p(x), _pi(cl))
+    return x, cl.astype(bool)

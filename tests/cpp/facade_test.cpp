@@ -107,7 +107,7 @@ int main() {
     std::vector<int32_t> iters(B), st(B), aidx(B * 50), riters(B), rst(B), raidx(B * 50);
     BatchedSlq slq(ctx, N);
     slq.solve(B, x0.data(), xg.data(), x.data(), u.data(), nullptr, cost.data(), iters.data(), aidx.data(), st.data());
-    noc_oracle_slq_opts o{NOC_O_MODEL_QUAD12, N, 50, 11, 0.02, 1e-8, 0.0, 1e-4};
+    noc_oracle_slq_opts o{NOC_O_MODEL_QUAD12, N, 50, 11, 0.02, 1e-8, 0.0, 1e-4, -INFINITY, INFINITY};
     noc_oracle_slq_batch(&o, B, x0.data(), xg.data(), w.qrqf.data(), rx.data(), ru.data(), nullptr, rcost.data(),
                          riters.data(), raidx.data(), rst.data(), 0);
     CHECK(same(x, rx) && same(u, ru) && same(cost, rcost) && iters == riters && st == rst && aidx == raidx);

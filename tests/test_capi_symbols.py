@@ -45,7 +45,8 @@ def test_problem_struct_layout(lib):
     assert p.dt == 0.02 and p.tol == 1e-8 and p.armijo == 1e-4 and p.reg0 == 0.0
     p = capi.problem(capi.MODEL_DUAL24, 7)
     assert (p.n, p.m, p.N) == (24, 8, 7)
-    assert ctypes.sizeof(capi.Problem) == 8 * 4 + 4 * 8
+    assert p.u_min == -float("inf") and p.u_max == float("inf")        # no input box by default
+    assert ctypes.sizeof(capi.Problem) == 8 * 4 + 6 * 8
 
 
 def test_version_and_no_gpu_fails_loudly(lib):

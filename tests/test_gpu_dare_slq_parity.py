@@ -126,7 +126,7 @@ def _slq_compare(oracle, solver, batch, N, x0, xg, qr, **kw):
     aidx = np.full((batch, prob.max_iter), -7, dtype=np.int32)
     solver.slq_solve_batch(prob, batch, x0, xg, qr, x=x, u=u, K=K, cost=cost, iters=iters, alpha_idx=aidx, status=status)
     opts = oracle.slq_opts(0, N, dt=prob.dt, tol=prob.tol, max_iter=prob.max_iter, n_alpha=prob.n_alpha,
-                           reg0=prob.reg0, armijo=prob.armijo)
+                           reg0=prob.reg0, armijo=prob.armijo, u_min=prob.u_min, u_max=prob.u_max)
     ref = oracle.slq_batch(opts, x0, xg, qr, want_traj=True, want_K=True)
     assert np.array_equal(status, ref["status"])
     assert np.array_equal(iters, ref["iters"])          # iteration counts identical (north_star)
@@ -135,7 +135,7 @@ def _slq_compare(oracle, solver, batch, N, x0, xg, qr, **kw):
     assert np.array_equal(x, ref["x"]) and np.array_equal(u, ref["u"])
     # K of the last backward pass of every instance
     assert np.array_equal(K, ref["K"])
-    return dict(status=status, iters=iters, aidx=aidx, cost=cost)
+    return dict(status=status, iters=iters, aidx=aidx, cost=cost, u=u, K=K)
 
 
 def test_slq_waypoints_bitexact(oracle, solver):
@@ -159,6 +159,37 @@ def test_slq_backtracking_and_max_iter(oracle, solver):
     out = _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=6)
     assert np.any(out["aidx"] > 0)
     assert np.any(out["status"] == 2)
+
+
+@pytest.mark.parametrize("u_min,u_max", [(0.0, 4.0), (1.5, 3.2), (-np.inf, 3.0), (-1e6, 1e6)])
+def test_slq_input_box_bitexact(oracle, solver, u_min, u_max):
+    """Control-limited SLQ: box QP for the feed-forward, zero feedback rows on clamped inputs, clamped
+    rollouts.  Iteration counts, step indices, trajectories, gains and costs as the oracle's, bit for bit; the inputs
+    stay inside the box; several warps and a ragged tail (batch 44)."""
+    batch, N = 44, 60
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.hover_state(batch); xg = pb.sample_goals(batch, seed=15)
+    out = _slq_compare(oracle, solver, batch, N, x0, xg, qr, u_min=u_min, u_max=u_max)
+    assert out["u"].min() >= u_min and out["u"].max() <= u_max
+    if u_max < 100.0:
+        assert np.any(out["u"] == u_max) or np.any(out["u"] == u_min)     # the box is active somewhere
+        assert np.any(np.all(out["K"] == 0.0, axis=-1))                   # ... and some feedback rows are switched off
+    else:
+        ref = _slq_compare(oracle, solver, batch, N, x0, xg, qr)          # a box nobody touches changes nothing
+        assert np.array_equal(out["cost"], ref["cost"]) and np.array_equal(out["iters"], ref["iters"])
+
+
+def test_slq_input_box_with_backtracking_and_failures(oracle, solver):
+    """Aggressive starts under a tight box: alpha < 1, LS_FAIL and MAX_ITER outcomes all occur and match."""
+    batch, N = 24, 40
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    rng = np.random.default_rng(19)
+    x0 = pb.sample_x0(batch, seed=124)
+    x0[:, 6:8] = rng.uniform(-0.9, 0.9, (batch, 2))
+    xg = pb.sample_goals(batch, seed=16) * 2.0
+    out = _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=30, u_min=1.0, u_max=3.5)
+    assert np.any(out["aidx"] > 0)
+    assert {0, 2, 3} <= set(out["status"].tolist())      # converged, MAX_ITER and LS_FAIL all occur
 
 
 def test_slq_regularisation_retry(oracle, solver):

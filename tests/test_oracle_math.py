@@ -383,3 +383,45 @@ def test_slq_vs_independent_numpy_ilqr(oracle):
         assert iters == ref["iters"]                                   # identical iteration counts
         assert alphas == [int(a) for a in ref["alpha_idx"][:iters]]     # identical accepted step lengths
         assert abs(J - ref["cost"]) <= 1e-9 * abs(ref["cost"])          # north_star's tolerance
+
+
+def test_box_qp_vs_scipy(oracle):
+    """The projected-Newton box QP of the control-limited backward pass against scipy's bounded
+    least squares on the Cholesky factor: same minimiser, KKT conditions hold, clamped set consistent."""
+    from scipy.optimize import lsq_linear
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        m = int(rng.choice([4, 8]))
+        M = rng.standard_normal((m, m)); H = M @ M.T + 0.1 * np.eye(m); g = 3 * rng.standard_normal(m)
+        lo = -rng.uniform(0.05, 1.0, m); hi = rng.uniform(0.05, 1.0, m)
+        x, cl = oracle.box_qp(H, g, lo, hi, x0=-np.linalg.solve(H, g))
+        L = np.linalg.cholesky(H)
+        r = lsq_linear(L.T, -np.linalg.solve(L, g), bounds=(lo, hi), tol=1e-14, max_iter=500)
+        assert np.abs(x - r.x).max() < 1e-6
+        grad = H @ x + g
+        for a in range(m):
+            at_lo, at_hi = x[a] <= lo[a], x[a] >= hi[a]
+            assert abs(grad[a]) < 1e-7 or (at_lo and grad[a] > 0) or (at_hi and grad[a] < 0)
+            assert cl[a] == ((at_lo and grad[a] > 0) or (at_hi and grad[a] < 0))
+        assert np.all(x >= lo) and np.all(x <= hi)
+
+
+def test_slq_input_box_behaviour(oracle):
+    """Control-limited SLQ on waypoint problems: inputs stay in the box, every instance still converges, the optimum
+    costs more than the unconstrained one and less the wider the box; an untouched box is bitwise a no-op."""
+    batch, N = 8, 100
+    qr = pb.pack_qrqf(*pb.default_weights())
+    xs = pb.hover_state(batch); xg = pb.sample_goals(batch, seed=33)
+    free = oracle.slq_batch(oracle.slq_opts(0, N), xs, xg, qr, want_traj=True)
+    wide = oracle.slq_batch(oracle.slq_opts(0, N, u_min=-1e6, u_max=1e6), xs, xg, qr, want_traj=True)
+    assert np.array_equal(free["cost"], wide["cost"]) and np.array_equal(free["u"], wide["u"])
+    assert free["u"].min() < 0.0 and free["u"].max() > 6.0          # the unconstrained optimum needs negative thrust
+    b6 = oracle.slq_batch(oracle.slq_opts(0, N, u_min=0.0, u_max=6.0), xs, xg, qr, want_traj=True)
+    b4 = oracle.slq_batch(oracle.slq_opts(0, N, u_min=0.0, u_max=4.0), xs, xg, qr, want_traj=True)
+    for r, hi in ((b6, 6.0), (b4, 4.0)):
+        assert r["u"].min() >= 0.0 and r["u"].max() <= hi
+        assert np.all(np.isin(r["status"], (0, 2)))
+    conv = (free["status"] == 0) & (b6["status"] == 0) & (b4["status"] == 0)
+    assert conv.sum() >= batch // 2
+    assert np.all(b6["cost"][conv] >= free["cost"][conv] * (1 - 1e-9))
+    assert np.all(b4["cost"][conv] >= b6["cost"][conv] * (1 - 1e-6))
