@@ -154,6 +154,8 @@ class BatchedSlq {
   }
   noc_problem_t& problem() { return prob_; }
   void setWeights(const Weights& w) { weights_ = w; }
+  // box on every input component (rotor thrust limits): control-limited backward pass + clamped rollouts
+  void setInputBox(double u_min, double u_max) { prob_.u_min = u_min; prob_.u_max = u_max; }
   void solve(int64_t batch, const double* x0, const double* xgoal, double* x, double* u, double* K, double* cost,
              int32_t* iters, int32_t* alpha_idx, int32_t* status) {
     ctx_->check(noc_slq_solve_batch(ctx_->handle(), &prob_, batch, x0, xgoal, weights_.qrqf.data(), x, u, K, cost,

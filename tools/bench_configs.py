@@ -31,6 +31,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", type=int, default=0, help="run a single config (1, 3, 4 or 5)")
+    ap.add_argument("--box", type=float, nargs=2, default=None, metavar=("U_MIN", "U_MAX"),
+                    help="config 3 with the input box u_min <= u <= u_max (control-limited SLQ, DESIGN.md 2.4b)")
     args = ap.parse_args()
     import torch
     from noc_b200 import capi, problems as pb
@@ -110,7 +112,8 @@ def main():
         d_xs, d_xg = T(xs), T(xg)
         dx = torch.empty(nb, N + 1, n, **f64); du = torch.empty(nb, N, m, **f64); dc = torch.empty(nb, **f64)
         dit = torch.empty(nb, **i32); dst = torch.empty(nb, **i32)
-        p = capi.problem(model, N)
+        box = dict(u_min=args.box[0], u_max=args.box[1]) if (args.box and cfg == 3) else {}
+        p = capi.problem(model, N, **box)
         fn = lambda: s.slq_solve_batch(p, nb, d_xs, d_xg, d_q, x=dx, u=du, cost=dc, iters=dit, status=dst)
         fn()
         s.profile_reset(); s.profile_enable(True)
@@ -120,9 +123,10 @@ def main():
                                                            ("forward", capi.KERNEL_FORWARD), ("rollout", capi.KERNEL_ROLLOUT))}
         its = dit.cpu().numpy(); st = dst.cpu().numpy()
         t0 = time.perf_counter()
-        ref = oracle.slq_batch(oracle.slq_opts(model, N), xs[:smp], xg[:smp], qrm, want_traj=False)
+        ref = oracle.slq_batch(oracle.slq_opts(model, N, **box), xs[:smp], xg[:smp], qrm, want_traj=False)
         cpu_s = time.perf_counter() - t0
-        out.append({"config": cfg, "what": f"SLQ/iLQR n={n} m={m} N={N}, hover start, waypoint goals, tol 1e-8, max 50 it",
+        out.append({"config": cfg, "what": f"SLQ/iLQR n={n} m={m} N={N}, hover start, waypoint goals, tol 1e-8, max 50 it" +
+                    (f", input box [{args.box[0]}, {args.box[1]}]" if box else ""),
                     "gpu_batch": nb, "gpu_ms": ms, "gpu_solves_per_s": nb / ms * 1e3, "gpu_slq_iterations_per_s": float(its.sum()) / ms * 1e3,
                     "iters_mean": float(its.mean()), "iters_max": int(its.max()), "status_counts": {int(k): int((st == k).sum()) for k in np.unique(st)},
                     "kernel_ms_per_solve_call": {k: v[0] / 2 for k, v in prof.items()},

@@ -48,6 +48,13 @@ def main():
                         iters=s["iters"], alpha_idx=s["alpha_idx"], status=s["status"], x_final=s["x"][:, -1],
                         u_first=s["u"][:, 0], x=s["x"], u=s["u"])
 
+    # the same problems with the input box 0 <= u <= 4 N (control-limited SLQ)
+    ob = oracle.slq_opts(0, N, u_min=0.0, u_max=4.0)
+    sb = oracle.slq_batch(ob, xs, xg, qr, want_traj=True, want_K=False)
+    np.savez_compressed(os.path.join(OUT, "slq_box_n12_N40.npz"), x0=xs, xgoal=xg, qrqf=qr, N=N, u_min=0.0, u_max=4.0,
+                        cost=sb["cost"], iters=sb["iters"], alpha_idx=sb["alpha_idx"], status=sb["status"],
+                        x=sb["x"], u=sb["u"])
+
     # model: one step, one linearisation at a generic state (both models)
     for model, name in ((0, "quad12"), (1, "dual24")):
         x = pb.sample_x0(1, seed=7, model=model)[0]
