@@ -84,7 +84,7 @@ typedef struct {
   double armijo;           /* SLQ: sufficient-decrease constant (1e-4) */
   double u_min, u_max;     /* SLQ: box on every input component (control-limited DDP: box QP for the feed-forward,
                               zero feedback on clamped inputs, clamped rollouts).  -INFINITY / +INFINITY
-                              (the defaults) = unconstrained.  NOC_MODEL_QUAD12 only. */
+                              (the defaults) = unconstrained.  Both built-in models. */
 } noc_problem_t;
 
 /* ---- context ------------------------------------------------------------------------------ */

@@ -244,9 +244,9 @@ int launch_ric12_layout(noc_ctx* ctx, int layout, const Ric12Args& a) {
 template <int MODE> struct Ric24Cfg { static constexpr int warps = 8; };
 template <> struct Ric24Cfg<RIC_AFFINE> { static constexpr int warps = 7; };
 
-template <int LAYOUT, int MODE, bool FUSED, int W>
+template <int LAYOUT, int MODE, bool FUSED, int W, bool BOX = false>
 int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a) {
-  auto kern = k_ric24<LAYOUT, MODE, FUSED, W>;
+  auto kern = k_ric24<LAYOUT, MODE, FUSED, W, BOX>;
   const size_t smem = ric24_smem_bytes<MODE, FUSED>(W);
   NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
@@ -260,11 +260,11 @@ int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a) {
   return NOC_OK;
 }
 
-template <int LAYOUT, int MODE, bool FUSED = false>
+template <int LAYOUT, int MODE, bool FUSED = false, bool BOX = false>
 int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
   // short work lists: one warp (two instances) per CTA so that the latency-bound tail spreads over all SMs
-  if (a.batch <= 2LL * 2 * ctx->sm_count) return launch_ric24_cfg<LAYOUT, MODE, FUSED, 1>(ctx, a);
-  return launch_ric24_cfg<LAYOUT, MODE, FUSED, Ric24Cfg<MODE>::warps>(ctx, a);
+  if (a.batch <= 2LL * 2 * ctx->sm_count) return launch_ric24_cfg<LAYOUT, MODE, FUSED, 1, BOX>(ctx, a);
+  return launch_ric24_cfg<LAYOUT, MODE, FUSED, Ric24Cfg<MODE>::warps, BOX>(ctx, a);
 }
 
 // packs the weights for the n=24 kernels into scratch: W[1024] | Qf[576]
@@ -500,7 +500,10 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
       ra.u_min = p->u_min; ra.u_max = p->u_max;
       rc = boxed ? launch_ric12<0, RIC_AFFINE, true, true>(ctx, ra) : launch_ric12<0, RIC_AFFINE, true>(ctx, ra);
     }
-    else rc = launch_ric24<0, RIC_AFFINE, true>(ctx, ra);
+    else {
+      ra.u_min = p->u_min; ra.u_max = p->u_max;
+      rc = boxed ? launch_ric24<0, RIC_AFFINE, true, true>(ctx, ra) : launch_ric24<0, RIC_AFFINE, true>(ctx, ra);
+    }
     if (rc) { ctx->pending.clear(); return rc; }
     // a4: closed-loop rollouts with backtracking, acceptance, convergence, next work list.  One launch per step
     // length: trial 0 on the whole list, trial j+1 only on the instances whose trial j was rejected.
@@ -878,8 +881,6 @@ int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if (p->max_iter < 1 || p->n_alpha < 1 || p->n_alpha > 32)
     return fail(ctx, NOC_ERR_BAD_ARG, "need max_iter >= 1 and 1 <= n_alpha <= 32");
   if (!(p->u_min < p->u_max)) return fail(ctx, NOC_ERR_BAD_ARG, "need u_min < u_max (-INFINITY / INFINITY = no input box)");
-  if ((std::isfinite(p->u_min) || std::isfinite(p->u_max)) && p->model != NOC_MODEL_QUAD12)
-    return fail(ctx, NOC_ERR_UNSUPPORTED, "the input box is implemented for NOC_MODEL_QUAD12 only");
   if (batch > 0x7fffffffLL) return fail(ctx, NOC_ERR_BAD_ARG, "batch too large for 32-bit work lists");
   if (batch == 0) return NOC_OK;
   return p->model == NOC_MODEL_QUAD12

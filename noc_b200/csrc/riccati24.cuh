@@ -53,6 +53,7 @@ struct Ric24Args {
   const double* ubar;    // [batch][N][8]
   const double* xgoal;   // [batch][24]
   double dt;             // FUSED: Euler step of the built-in model
+  double u_min, u_max;   // BOX: input box of the SLQ backward pass
   double* kff;           // [batch][N][8]
   double* dV;            // [batch][2]
   double* mu;            // [batch]
@@ -119,6 +120,73 @@ struct LdlReg {
   }
 };
 
+// ---- input box: the oracle's box_qp for any M, operands in local memory.  A rare, divergent path
+// (only the instances whose feed-forward leaves the box run it), kept out of line so that it does not weigh on the
+// register allocation of the sweep.  U: Quu, row-major M x M, lower triangle valid (shared memory).
+template <int M>
+__device__ __forceinline__ void ldl_mask(const double* U, const bool (&cl)[M], double* Um) {
+  for (int a = 0; a < M; ++a)
+    for (int b = 0; b <= a; ++b) Um[a * M + b] = (cl[a] || cl[b]) ? (a == b ? 1.0 : 0.0) : U[a * M + b];
+}
+template <int M>
+__device__ __forceinline__ double qp_eval_gen(const double* U, const double (&g)[M], const double (&x)[M], double (&r)[M]) {
+  for (int a = 0; a < M; ++a) {
+    double s = 0.0;
+    for (int b = 0; b < M; ++b) s = fmad(b <= a ? U[a * M + b] : U[b * M + a], x[b], s);
+    r[a] = s;
+  }
+  double f = 0.0;
+  for (int a = 0; a < M; ++a) f = fmad(x[a], fmad(0.5, r[a], g[a]), f);
+  return f;
+}
+template <int M>
+__device__ __noinline__ void box_qp_gen(const double* U, const double (&g)[M], const double (&lo)[M], const double (&hi)[M],
+                                        double (&x)[M], bool (&cl)[M]) {
+  double r[M], grad[M], rhs[M], dx[M], xc[M], rc[M], Um[M * M];
+  double gmax = 0.0;
+  for (int a = 0; a < M; ++a) {
+    x[a] = r12_clamp(x[a], lo[a], hi[a]);
+    if (fabs(g[a]) > gmax) gmax = fabs(g[a]);
+  }
+  double f = qp_eval_gen<M>(U, g, x, r);
+  for (int it = 0; it < R12_QP_MAXIT; ++it) {
+    int nfree = 0;
+    double gn = 0.0;
+    for (int a = 0; a < M; ++a) {
+      grad[a] = r[a] + g[a];
+      cl[a] = (x[a] <= lo[a] && grad[a] > 0.0) || (x[a] >= hi[a] && grad[a] < 0.0);
+      if (!cl[a]) { ++nfree; if (fabs(grad[a]) > gn) gn = fabs(grad[a]); }
+    }
+    if (nfree == 0 || gn < R12_QP_GTOL * (1.0 + gmax)) return;
+    ldl_mask<M>(U, cl, Um);
+    LdlReg<M> chm;
+    if (chm.factor(Um)) return;
+    for (int a = 0; a < M; ++a) rhs[a] = cl[a] ? 0.0 : grad[a];
+    chm.solve_neg(rhs, dx);
+    double sdotg = 0.0;
+    for (int a = 0; a < M; ++a) sdotg = fmad(grad[a], dx[a], sdotg);
+    if (!(sdotg < 0.0)) return;
+    double step = 1.0;
+    bool ok = false;
+    for (int ls = 0; ls < R12_QP_MAXLS; ++ls) {
+      for (int a = 0; a < M; ++a) xc[a] = r12_clamp(fmad(step, dx[a], x[a]), lo[a], hi[a]);
+      const double fc = qp_eval_gen<M>(U, g, xc, rc);
+      if (fc - f <= R12_QP_ARMIJO * (step * sdotg)) {
+        for (int a = 0; a < M; ++a) { x[a] = xc[a]; r[a] = rc[a]; }
+        f = fc;
+        ok = true;
+        break;
+      }
+      step = step * 0.5;
+    }
+    if (!ok) return;
+  }
+  for (int a = 0; a < M; ++a) {   // iteration cap: the clamped set of the last accepted point
+    const double ga = r[a] + g[a];
+    cl[a] = (x[a] <= lo[a] && ga > 0.0) || (x[a] >= hi[a] && ga < 0.0);
+  }
+}
+
 template <int LAYOUT>
 __device__ __forceinline__ int r24_foff(int l, int c) {
   if (LAYOUT == 1) return l * 32 + c;
@@ -142,7 +210,7 @@ __device__ __forceinline__ void r24_store_direct(double* Ps, const double* h, in
 // HBM.  Lanes 0..7 of an instance evaluate vehicle 0's Jacobian, lanes 8..15 vehicle 1's (same code, different
 // data); each stores one eighth of the state-dependent entries.  Zeros, the state-independent entries and the
 // (constant) spring-damper coupling entries are written once per sweep.
-template <int LAYOUT, int MODE, bool FUSED, int WARPS>
+template <int LAYOUT, int MODE, bool FUSED, int WARPS, bool BOX = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
   extern __shared__ __align__(128) double smem[];
   static_assert(!FUSED || LAYOUT == 0, "fused linearisation: A_THEN_B records");
@@ -416,6 +484,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
       // (x-lanes: their Hux columns; u-lanes solve dummies).
       LdlReg<8> ch;
       failed |= ch.factor(Us);
+      bool cl[8] = {false, false, false, false, false, false, false, false};   // BOX: inputs held at a bound in this step
+      bool boxed_step = false;
       const double* sA = xl ? Hs + jA : Us + uA;
       const double* sB = xl ? Hs + jB : Us + uB;
       const int ds = xl ? 24 : 8;
@@ -424,6 +494,28 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
 #pragma unroll
         for (int c = 0; c < 8; c += 2) { const double2 v = lds128(base + R24_HU + c); hur[c] = v.x; hur[c + 1] = v.y; }
         ch.solve_neg(hur, kf);
+        if (BOX) {
+          // input box (oracle: noc_oracle_backward_affine_box): ubar_k straight from global memory (the staged copy
+          // has been overwritten by the prefetch of step k-1); a feed-forward that leaves the box is replaced by the
+          // box QP's, and `ch` by the factorisation with the clamped inputs masked out, which the gain solves use
+          double lo[8], hi[8];
+          bool inside = true;
+          const double* ub = a.ubar + ((size_t)b * N + k) * 8;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const double uc = ub[c];
+            lo[c] = a.u_min - uc;
+            hi[c] = a.u_max - uc;
+            if (!(kf[c] > lo[c] && kf[c] < hi[c])) inside = false;
+          }
+          if (!inside) {
+            box_qp_gen<8>(Us, hur, lo, hi, kf, cl);
+            double Um[64];
+            ldl_mask<8>(Us, cl, Um);
+            failed |= ch.factor(Um);
+            boxed_step = true;
+          }
+        }
         if (xl) {
           double sa = hacc[0], sb = hacc[1];
 #pragma unroll
@@ -454,10 +546,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
       {
         double rhs[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) rhs[c] = sA[c * ds];
+        for (int c = 0; c < 8; ++c) rhs[c] = (BOX && boxed_step && cl[c]) ? 0.0 : sA[c * ds];
         ch.solve_neg(rhs, kA);
 #pragma unroll
-        for (int c = 0; c < 8; ++c) rhs[c] = sB[c * ds];
+        for (int c = 0; c < 8; ++c) rhs[c] = (BOX && boxed_step && cl[c]) ? 0.0 : sB[c * ds];
         ch.solve_neg(rhs, kB);
       }
       if (failed && kfail < 0) kfail = k;

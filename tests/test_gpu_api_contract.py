@@ -52,10 +52,6 @@ def test_bad_arguments_return_codes(solver):
     with pytest.raises(capi.NocError) as e:
         solver.slq_solve_batch(capi.problem(0, 5, u_min=3.0, u_max=2.0), 4, x0, x0, _qr())          # empty input box
     assert e.value.code == capi.ERR_BAD_ARG
-    with pytest.raises(capi.NocError) as e:                                                            # box: n=12 only
-        solver.slq_solve_batch(capi.problem(1, 5, u_min=0.0, u_max=5.0), 4, pb.hover_state(4, model=1),
-                               pb.hover_state(4, model=1), pb.pack_qrqf(*pb.default_weights(1)))
-    assert e.value.code == capi.ERR_UNSUPPORTED
     with pytest.raises(capi.NocError) as e:
         solver.slq_solve_batch(capi.problem(capi.MODEL_LTV_USER, 5), 4, x0, x0, _qr())
     assert e.value.code == capi.ERR_BAD_ARG

@@ -77,7 +77,7 @@ def test_from_x0_dual24_bitexact(oracle, solver):
     assert np.array_equal(K0, ref["K0"]) and np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(max_iter=4)])
+@pytest.mark.parametrize("kw", [dict(), dict(max_iter=4), dict(u_min=0.5, u_max=4.0), dict(u_min=1.5, u_max=3.2, max_iter=20)])
 def test_slq_dual24_bitexact(oracle, solver, kw):
     from noc_b200 import capi
     batch, N = 9, 30
@@ -90,11 +90,15 @@ def test_slq_dual24_bitexact(oracle, solver, kw):
     cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
     aidx = np.full((batch, prob.max_iter), -7, dtype=np.int32)
     solver.slq_solve_batch(prob, batch, x0, xg, qr, x=x, u=u, K=K, cost=cost, iters=iters, alpha_idx=aidx, status=status)
-    opts = oracle.slq_opts(M, N, max_iter=prob.max_iter)
+    opts = oracle.slq_opts(M, N, max_iter=prob.max_iter, u_min=prob.u_min, u_max=prob.u_max)
     ref = oracle.slq_batch(opts, x0, xg, qr, want_traj=True, want_K=True)
     assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
     assert np.array_equal(aidx, ref["alpha_idx"]) and np.array_equal(cost, ref["cost"])
     assert np.array_equal(x, ref["x"]) and np.array_equal(u, ref["u"]) and np.array_equal(K, ref["K"])
+    if "u_min" in kw:     # control-limited (DESIGN.md 2.4b, 8x8 box QP): inside the box, at a bound somewhere, gain rows off
+        assert u.min() >= kw["u_min"] and u.max() <= kw["u_max"]
+        assert np.any(u == kw["u_max"]) or np.any(u == kw["u_min"])
+        assert np.any(np.all(K == 0.0, axis=-1))
 
 
 def test_lqr24_multiwarp_config_bitexact(oracle, solver):
@@ -117,15 +121,16 @@ def test_lqr24_multiwarp_config_bitexact(oracle, solver):
     assert np.array_equal(K, ref2["K"])
 
 
-def test_slq_dual24_multiwarp_config(oracle, solver):
+@pytest.mark.parametrize("box", [dict(), dict(u_min=1.0, u_max=3.5)])
+def test_slq_dual24_multiwarp_config(oracle, solver, box):
     from noc_b200 import capi
     batch, N = 1300, 10
     Q, R, Qf = pb.default_weights(M)
     qr = pb.pack_qrqf(Q, R, Qf)
     x0 = pb.hover_state(batch, model=M)
     xg = pb.sample_goals(batch, seed=78, model=M)
-    prob = capi.problem(M, N, max_iter=6)
+    prob = capi.problem(M, N, max_iter=6, **box)
     cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
     solver.slq_solve_batch(prob, batch, x0, xg, qr, cost=cost, iters=iters, status=status)
-    ref = oracle.slq_batch(oracle.slq_opts(M, N, max_iter=6), x0, xg, qr, want_traj=False)
+    ref = oracle.slq_batch(oracle.slq_opts(M, N, max_iter=6, **box), x0, xg, qr, want_traj=False)
     assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"]) and np.array_equal(cost, ref["cost"])

@@ -32,7 +32,7 @@ def main():
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--only", type=int, default=0, help="run a single config (1, 3, 4 or 5)")
     ap.add_argument("--box", type=float, nargs=2, default=None, metavar=("U_MIN", "U_MAX"),
-                    help="config 3 with the input box u_min <= u <= u_max (control-limited SLQ, DESIGN.md 2.4b)")
+                    help="configs 3 and 5 with the input box u_min <= u <= u_max (control-limited SLQ, DESIGN.md 2.4b)")
     args = ap.parse_args()
     import torch
     from noc_b200 import capi, problems as pb
@@ -112,7 +112,7 @@ def main():
         d_xs, d_xg = T(xs), T(xg)
         dx = torch.empty(nb, N + 1, n, **f64); du = torch.empty(nb, N, m, **f64); dc = torch.empty(nb, **f64)
         dit = torch.empty(nb, **i32); dst = torch.empty(nb, **i32)
-        box = dict(u_min=args.box[0], u_max=args.box[1]) if (args.box and cfg == 3) else {}
+        box = dict(u_min=args.box[0], u_max=args.box[1]) if args.box else {}
         p = capi.problem(model, N, **box)
         fn = lambda: s.slq_solve_batch(p, nb, d_xs, d_xg, d_q, x=dx, u=du, cost=dc, iters=dit, status=dst)
         fn()
