@@ -140,7 +140,7 @@ __device__ __forceinline__ double qp_eval_gen(const double* U, const double (&g)
   return f;
 }
 template <int M>
-__device__ __noinline__ void box_qp_gen(const double* U, const double (&g)[M], const double (&lo)[M], const double (&hi)[M],
+__device__ __forceinline__ void box_qp_gen(const double* U, const double (&g)[M], const double (&lo)[M], const double (&hi)[M],
                                         double (&x)[M], bool (&cl)[M]) {
   double r[M], grad[M], rhs[M], dx[M], xc[M], rc[M], Um[M * M];
   double gmax = 0.0;
