@@ -419,8 +419,8 @@ class StdoutToStderr:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="noc", choices=["noc", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="instances per GPU (default: config 2)")
     ap.add_argument("--cpu-sample", type=int, default=32768)
