@@ -111,6 +111,16 @@ int main() {
     noc_oracle_slq_batch(&o, B, x0.data(), xg.data(), w.qrqf.data(), rx.data(), ru.data(), nullptr, rcost.data(),
                          riters.data(), raidx.data(), rst.data(), 0);
     CHECK(same(x, rx) && same(u, ru) && same(cost, rcost) && iters == riters && st == rst && aidx == raidx);
+    // the same problems with rotor-thrust limits (control-limited SLQ): setInputBox
+    slq.setInputBox(0.0, 4.0);
+    slq.solve(B, x0.data(), xg.data(), x.data(), u.data(), nullptr, cost.data(), iters.data(), aidx.data(), st.data());
+    noc_oracle_slq_opts ob{NOC_O_MODEL_QUAD12, N, 50, 11, 0.02, 1e-8, 0.0, 1e-4, 0.0, 4.0};
+    noc_oracle_slq_batch(&ob, B, x0.data(), xg.data(), w.qrqf.data(), rx.data(), ru.data(), nullptr, rcost.data(),
+                         riters.data(), raidx.data(), rst.data(), 0);
+    CHECK(same(x, rx) && same(u, ru) && same(cost, rcost) && iters == riters && st == rst && aidx == raidx);
+    bool in_box = true;
+    for (double v : u) in_box = in_box && v >= 0.0 && v <= 4.0;
+    CHECK(in_box);
   }
   {  // errors surface as exceptions with the library's message
     BatchedLqr lqr(ctx, 10);

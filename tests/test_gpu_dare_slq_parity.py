@@ -200,6 +200,7 @@ def test_slq_regularisation_retry(oracle, solver):
     qr = pb.pack_qrqf(Q, R, Qf)
     x0 = pb.sample_x0(batch, seed=31); xg = pb.sample_goals(batch, seed=7)
     _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=5)
+    _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=5, u_min=1.0, u_max=3.5)   # mu retries under the input box
 
 
 def test_slq_optional_outputs(oracle, solver):
