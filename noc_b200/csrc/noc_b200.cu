@@ -549,38 +549,60 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
       NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       list = rin; list_count = hc[1];
       std::swap(rin, rout);
-      // Speculative round: all remaining step lengths of the rejected instances at once (one launch set instead
-      // of up to n_alpha-1 sequential ones), when the candidate trajectories fit a 2 GB scratch.
+      // Speculative rounds: the remaining step lengths of the rejected instances as parallel candidates (one launch
+      // set instead of up to n_alpha-1 sequential ones), when the candidate trajectories fit a 2 GB scratch.  All
+      // of them at once while few instances backtrack (1 % without input limits); in rounds of four when many do
+      // (two thirds of the instances under a tight input box, accepted anywhere down to 2^-6): an instance leaves
+      // with the first round that holds a passing step length, which is the oracle's sequential search.
       const int J = p->n_alpha - 1 - trial;
       const size_t per_cand = sizeof(double) * ((N + 1) * n + N * m + (N + 1));
-      if (trial == 0 && list_count > 0 && J > 0 && (size_t)list_count * J * per_cand <= ((size_t)2 << 30)) {
-        void *dxc, *duc, *dlcc;
-        const size_t rc_ = (size_t)list_count * J;
-        int e1 = scratch(ctx, SCR_XC, sizeof(double) * rc_ * (N + 1) * n, &dxc);
-        int e2 = e1 ? e1 : scratch(ctx, SCR_UC, sizeof(double) * rc_ * N * m, &duc);
-        int e3 = e2 ? e2 : scratch(ctx, SCR_LCC, sizeof(double) * rc_ * (N + 1), &dlcc);
-        if (e3) { ctx->pending.clear(); return e3; }
-        fa.idx = list; fa.trial = 1; fa.cand_J = J; fa.xc = (double*)dxc; fa.uc = (double*)duc; fa.lcc = (double*)dlcc;
-        fa.count = (int)rc_;
-        {
-          LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-          k_slq_rollout<MODEL><<<(unsigned)((rc_ + FC::inst - 1) / FC::inst), FC::threads, fwd_smem, ctx->stream>>>(fa);
+      if (trial == 0 && list_count > 0 && J > 0) {
+        const int round_J = ((size_t)list_count * J > 2 * (size_t)count) ? std::min(J, 4) : J;
+        if ((size_t)list_count * round_J * per_cand <= ((size_t)2 << 30)) {
+          int first = 1;
+          while (list_count > 0 && first < p->n_alpha) {
+            const int Jr = std::min(round_J, p->n_alpha - first);
+            void *dxc, *duc, *dlcc;
+            const size_t rc_ = (size_t)list_count * Jr;
+            int e1 = scratch(ctx, SCR_XC, sizeof(double) * rc_ * (N + 1) * n, &dxc);
+            int e2 = e1 ? e1 : scratch(ctx, SCR_UC, sizeof(double) * rc_ * N * m, &duc);
+            int e3 = e2 ? e2 : scratch(ctx, SCR_LCC, sizeof(double) * rc_ * (N + 1), &dlcc);
+            if (e3) { ctx->pending.clear(); return e3; }
+            fa.idx = list; fa.trial = first; fa.cand_J = Jr; fa.cand_first = first; fa.cand_last = (first + Jr >= p->n_alpha);
+            fa.xc = (double*)dxc; fa.uc = (double*)duc; fa.lcc = (double*)dlcc;
+            fa.count = (int)rc_;
+            {
+              LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+              k_slq_rollout<MODEL><<<(unsigned)((rc_ + FC::inst - 1) / FC::inst), FC::threads, fwd_smem, ctx->stream>>>(fa);
+            }
+            NOC_CUDA(ctx, cudaGetLastError());
+            {
+              const long long total = (long long)rc_ * (p->N + 1);
+              LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+              k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fa);
+            }
+            NOC_CUDA(ctx, cudaGetLastError());
+            fa.count = list_count;
+            {
+              LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+              k_slq_accept_cand<MODEL><<<(unsigned)((list_count + 3) / 4), 128, 0, ctx->stream>>>(fa);
+            }
+            NOC_CUDA(ctx, cudaGetLastError());
+            first += Jr;
+            if (fa.cand_last) { list_count = 0; break; }   // every rejected instance has been settled
+            {  // instances without a winner so far -> sorted list of the next round
+              LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+              k_compact_flags<<<1, 1024, 0, ctx->stream>>>((int32_t*)dflags, 2, batch, rin, (int32_t*)dcount + 1);
+            }
+            NOC_CUDA(ctx, cudaGetLastError());
+            NOC_CUDA(ctx, cudaMemcpyAsync(hc + 1, (int32_t*)dcount + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            list = rin; list_count = hc[1];
+            std::swap(rin, rout);
+          }
+          fa.cand_J = 0;
+          list_count = 0;
         }
-        NOC_CUDA(ctx, cudaGetLastError());
-        {
-          const long long total = (long long)rc_ * (p->N + 1);
-          LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-          k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fa);
-        }
-        NOC_CUDA(ctx, cudaGetLastError());
-        fa.count = list_count;
-        {
-          LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-          k_slq_accept_cand<MODEL><<<(unsigned)((list_count + 3) / 4), 128, 0, ctx->stream>>>(fa);
-        }
-        NOC_CUDA(ctx, cudaGetLastError());
-        fa.cand_J = 0;
-        list_count = 0;   // every rejected instance has been settled
       }
     }
     {  // instances that go on to the next iteration -> sorted work list

@@ -119,7 +119,10 @@ struct SlqFwdArgs {
   int trial;                // j of this launch: alpha = 2^-j for every instance of the work list
   // speculative round (cand_J > 0): work item = (list position i, candidate c), step length 2^-(c+1); the
   // trajectories go to the candidate scratch instead of x / u and k_slq_accept picks the first accepted c
-  int cand_J;               // candidates per instance (n_alpha - 1), 0 = ordinary round
+  int cand_J;               // candidates per instance in this round, 0 = ordinary round
+  int cand_first;           // trial index of candidate 0 (step length 2^-cand_first); candidates are consecutive trials
+  int cand_last;            // 1: no step lengths remain after this round (an instance without a winner fails);
+                            // 0: it is flagged for the next round instead
   double* xc;               // [count/cand_J][cand_J][N+1][n]
   double* uc;               // [count/cand_J][cand_J][N][m]
   double* lcc;              // [count/cand_J][cand_J][N+1]
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_rollout(const Sl
   const int item = (int)(valid ? item_raw : a.count - 1);
   const bool cand = a.cand_J > 0;
   const long long b = a.idx[cand ? item / a.cand_J : item];
-  const int trial = cand ? item % a.cand_J + 1 : a.trial;
+  const int trial = cand ? a.cand_first + item % a.cand_J : a.trial;
   const int N = a.N;
   if (trial == 0 && a.bstatus[b] != 0) valid = false;   // regularisation exhausted: k_slq_accept records it
   double* xb = cand ? a.xc + (size_t)item * (N + 1) * n : a.x + (size_t)b * (N + 1) * n;   // receives the trajectory
@@ -393,7 +396,7 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
 }
 
 // speculative round (cand_J > 0): one WARP per rejected instance.  Lane c sums the stage costs of candidate c
-// (alpha = 2^-(c+1)) in ascending k and runs its Armijo test; the first passing candidate in order wins (the
+// (alpha = 2^-(cand_first+c)) in ascending k and runs its Armijo test; the first passing candidate in order wins (the
 // oracle's sequential backtracking stops at the same one); then the warp copies the winning trajectory (or, if none
 // passed, the saved nominal) over x, u with coalesced 16-byte accesses.  (One thread per instance did both jobs
 // serially at first: 0.5-0.6 ms per launch for a handful of instances, profiles/ncu_r01_k_slq_rollout_v4.txt.)
@@ -413,13 +416,17 @@ __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
     const double* lc = a.lcc + ((size_t)item * a.cand_J + lane) * (N + 1);
 #pragma unroll 8
     for (int k = 0; k <= N; ++k) Jc = Jc + lc[k];
-    double alpha = 0.5;
-    for (int j = 0; j < lane; ++j) alpha = alpha * 0.5;
+    double alpha = 1.0;
+    for (int j = 0; j < a.cand_first + lane; ++j) alpha = alpha * 0.5;
     const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
     pass = Jold - Jc >= a.armijo * expected;
   }
   const unsigned won = __ballot_sync(0xffffffffu, pass);
   const int c = won ? __ffs((int)won) - 1 : -1;
+  if (c < 0 && !a.cand_last) {   // no winner among these step lengths, shorter ones remain: next round
+    if (lane == 0) a.flags[b] |= 2;
+    return;
+  }
   const double Jacc = __shfl_sync(0xffffffffu, Jc, c < 0 ? 0 : c);
   const size_t slot = (size_t)item * a.cand_J + (c < 0 ? 0 : c);
   const double2* sx = reinterpret_cast<const double2*>(c >= 0 ? a.xc + slot * (N + 1) * n : a.xn + (size_t)b * (N + 1) * n);
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
     a.iters[b] = a.iter + 1;
     return;
   }
-  slq_record_step(a, b, Jold, Jacc, c + 1);
+  slq_record_step(a, b, Jold, Jacc, a.cand_first + c);
 }
 
 // Ordered stream compaction of one flag bit: out = ascending list of the i < n with flags[i] & mask, the bit is
