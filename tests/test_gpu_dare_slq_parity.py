@@ -179,6 +179,18 @@ def test_slq_input_box_bitexact(oracle, solver, u_min, u_max):
         assert np.array_equal(out["cost"], ref["cost"]) and np.array_equal(out["iters"], ref["iters"])
 
 
+@pytest.mark.parametrize("u_min,u_max", [(3.0, 5.0), (0.0, 2.0), (2.4, 2.5)])
+def test_slq_input_box_excluding_or_hugging_hover(oracle, solver, u_min, u_max):
+    """Boxes that exclude the hover thrust the nominal starts from (the first QP starts outside its box, several
+    instances end with LS_FAIL in iteration 1 and keep the infeasible nominal) or barely contain it: same outcomes."""
+    batch, N = 20, 60
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.hover_state(batch); xg = pb.sample_goals(batch, seed=34)
+    out = _slq_compare(oracle, solver, batch, N, x0, xg, qr, u_min=u_min, u_max=u_max)
+    moved = out["iters"] > 1
+    assert moved.any() and out["u"][moved].min() >= u_min and out["u"][moved].max() <= u_max
+
+
 def test_slq_input_box_with_backtracking_and_failures(oracle, solver):
     """Aggressive starts under a tight box: alpha < 1, LS_FAIL and MAX_ITER outcomes all occur and match."""
     batch, N = 24, 40
