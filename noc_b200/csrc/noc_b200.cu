@@ -537,7 +537,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
       NOC_CUDA(ctx, cudaGetLastError());
       {
         LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-        k_slq_accept<MODEL><<<(unsigned)((list_count + 127) / 128), 128, 0, ctx->stream>>>(fa);
+        k_slq_accept<MODEL><<<(unsigned)((list_count + 3) / 4), 128, 0, ctx->stream>>>(fa);
       }
       NOC_CUDA(ctx, cudaGetLastError());
       {  // rejected trials -> sorted retry list

@@ -352,31 +352,40 @@ __device__ __forceinline__ void slq_record_step(const SlqFwdArgs& a, long long b
   if (a.iter + 1 < a.max_iter) a.flags[b] |= 1;
 }
 
-// ordinary round (one step length per launch): one thread per instance
+// ordinary round (one step length per launch): one WARP per instance.  The stage costs are read with coalesced
+// loads, 32 at a time, and summed in ascending k by every lane (shuffle broadcast of lane i's value, then the add —
+// the oracle's chain); lane 0 does the bookkeeping.  (A thread per instance read its 201 costs with a stride of
+// 1.6 KB between lanes: 35 us per launch, profiles/launches_cfg3_slq_r01d.csv.)
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
   constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
-  const int item = blockIdx.x * blockDim.x + threadIdx.x;
-  if (item >= a.count) return;
+  const int lane = threadIdx.x & 31;
+  const int item = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (item >= a.count) return;   // warp-uniform
   const long long b = a.idx[item];
   const int N = a.N;
   if (a.trial == 0 && a.bstatus[b] != 0) {  // regularisation exhausted in the backward pass
-    a.status[b] = 4;
-    a.iters[b] = a.iter + 1;
+    if (lane == 0) {
+      a.status[b] = 4;
+      a.iters[b] = a.iter + 1;
+    }
     return;
+  }
+  const double* lc = a.lc + (size_t)b * (N + 1);
+  double Jacc = 0.0;
+  for (int k0 = 0; k0 <= N; k0 += 32) {
+    const double v = (k0 + lane <= N) ? lc[k0 + lane] : 0.0;
+    const int cnt = (N + 1 - k0 < 32) ? N + 1 - k0 : 32;
+    for (int i = 0; i < cnt; ++i) Jacc = Jacc + __shfl_sync(0xffffffffu, v, i);
   }
   const double Jold = a.J[b];
   const double dV1 = a.dV[b * 2], dV2 = a.dV[b * 2 + 1];
-  double Jacc = 0.0;
-  const double* lc = a.lc + (size_t)b * (N + 1);
-#pragma unroll 8
-  for (int k = 0; k <= N; ++k) Jacc = Jacc + lc[k];
   double alpha = 1.0;
   for (int j = 0; j < a.trial; ++j) alpha = alpha * 0.5;
   const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
   if (!(Jold - Jacc >= a.armijo * expected)) {
     if (a.trial + 1 < a.n_alpha) {   // next step length(s), next launch
-      a.flags[b] |= 2;
+      if (lane == 0) a.flags[b] |= 2;
       return;
     }
     // no step length passed: put the nominal back (oracle: x, u unchanged) and stop this instance
@@ -384,15 +393,15 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
     const double2* su = reinterpret_cast<const double2*>(a.un + (size_t)b * N * m);
     double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
     double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
-#pragma unroll 8
-    for (int i = 0; i < (N + 1) * n / 2; ++i) dxp[i] = sx[i];
-#pragma unroll 8
-    for (int i = 0; i < N * m / 2; ++i) dup[i] = su[i];
-    a.status[b] = 3;  // NOC_STATUS_LS_FAIL
-    a.iters[b] = a.iter + 1;
+    for (int i = lane; i < (N + 1) * n / 2; i += 32) dxp[i] = sx[i];
+    for (int i = lane; i < N * m / 2; i += 32) dup[i] = su[i];
+    if (lane == 0) {
+      a.status[b] = 3;  // NOC_STATUS_LS_FAIL
+      a.iters[b] = a.iter + 1;
+    }
     return;
   }
-  slq_record_step(a, b, Jold, Jacc, a.trial);
+  if (lane == 0) slq_record_step(a, b, Jold, Jacc, a.trial);
 }
 
 // speculative round (cand_J > 0): one WARP per rejected instance.  Lane c sums the stage costs of candidate c
