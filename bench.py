@@ -122,6 +122,8 @@ def cpu_leg(sample: int, threads: int = 0, repeats: int = 1):
     from noc_b200 import problems as pb
     from oracle import pyoracle as oracle
     oracle.build()
+    if threads <= 0:
+        threads = len(os.sched_getaffinity(0))     # not OMP_NUM_THREADS (torchrun sets it to 1)
     Q, R, Qf = pb.default_weights()
     qr = pb.pack_qrqf(Q, R, Qf)
     x0 = pb.sample_x0(sample, seed=0x4E4F43)
@@ -144,16 +146,18 @@ def run_reference(args):
     from noc_b200 import problems as pb
     oracle.build()
     sample = args.ref_sample
-    threads = oracle.max_threads()
+    # all host threads, explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers, which would make the reference
+    # arm single-threaded at N > 1
+    threads = len(os.sched_getaffinity(0))
     Q, R, Qf = pb.default_weights()
     qr = pb.pack_qrqf(Q, R, Qf)
     x0 = pb.sample_x0(sample, seed=0x4E4F43)
     AB = oracle.make_ab_batch(0, HORIZON, pb.DT, x0)
     for _ in range(args.warmup):
-        oracle.lqr_batch(N_X, N_U, HORIZON, AB, qr, x0dev=x0)
+        oracle.lqr_batch(N_X, N_U, HORIZON, AB, qr, x0dev=x0, threads=threads)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.lqr_batch(N_X, N_U, HORIZON, AB, qr, x0dev=x0)
+        oracle.lqr_batch(N_X, N_U, HORIZON, AB, qr, x0dev=x0, threads=threads)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
     sample_txt = (f"{sample} of the {BATCH_PER_GPU} config-2 instances per step (LTV sweep n=12 m=4 N=100, all K_k "
