@@ -98,3 +98,26 @@ def test_config3_size_slq_counts_on_a_sample(oracle, solver):
     ref = oracle.slq_batch(oracle.slq_opts(0, N), xs[:m], xg[:m], qr, want_traj=False)
     assert np.array_equal(iters[:m], ref["iters"]) and np.array_equal(aidx[:m], ref["alpha_idx"])
     assert np.array_equal(cost[:m], ref["cost"]) and np.array_equal(st[:m], ref["status"])
+
+
+@pytest.mark.parametrize("box", [dict(), dict(u_min=0.0, u_max=4.0)])
+def test_config5_size_slq_counts_on_a_sample(oracle, solver, box):
+    """Config 5 shape (dual UAV, n=24, m=8, N=100) at a quarter of its batch, without and with the input box: statuses
+    sane, and the first 16 instances reproduce the oracle's iteration counts, step indices and costs exactly."""
+    from noc_b200 import capi
+    B, N, M = 2048, 100, 1
+    qr = pb.pack_qrqf(*pb.default_weights(M))
+    xs = pb.hover_state(B, model=M); xg = pb.sample_goals(B, seed=35, model=M)
+    prob = capi.problem(M, N, **box)
+    cost = np.empty(B); iters = np.zeros(B, dtype=np.int32); st = np.full(B, -1, dtype=np.int32)
+    aidx = np.zeros((B, prob.max_iter), dtype=np.int32)
+    u = np.empty((B, N, 8))
+    solver.slq_solve_batch(prob, B, xs, xg, qr, u=u, cost=cost, iters=iters, alpha_idx=aidx, status=st)
+    assert set(np.unique(st)).issubset({0, 2, 3}) and (st == 0).mean() > 0.8
+    assert np.all(iters >= 1) and np.all(iters <= prob.max_iter) and np.all(np.isfinite(cost))
+    if box:
+        assert u.min() >= box["u_min"] and u.max() <= box["u_max"]
+    m = 16
+    ref = oracle.slq_batch(oracle.slq_opts(M, N, **box), xs[:m], xg[:m], qr, want_traj=False)
+    assert np.array_equal(iters[:m], ref["iters"]) and np.array_equal(aidx[:m], ref["alpha_idx"])
+    assert np.array_equal(cost[:m], ref["cost"]) and np.array_equal(st[:m], ref["status"])
