@@ -56,3 +56,26 @@ def test_version_and_no_gpu_fails_loudly(lib):
     if not torch.cuda.is_available():
         with pytest.raises(capi.NocError):
             capi.Solver(0)
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under noc_b200/ (python or CUDA sources) may import, include, link
+    or dlopen anything under oracle/, and the product library must not depend on libnoc_oracle."""
+    import re
+    import subprocess
+    pkg = os.path.join(ROOT, "noc_b200")
+    bad = []
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if not f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")) and f != "Makefile":
+                continue
+            text = open(os.path.join(dirpath, f)).read()
+            code = re.sub(r"//[^\n]*|/\*.*?\*/", "", text, flags=re.S)       # comments cite the oracle's functions; code may not
+            if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or re.search(r'#include\s+"[^"]*oracle', code) \
+                    or re.search(r"noc_oracle_\w+\s*\(", code) or "lnoc_oracle" in code or "libnoc_oracle" in code:
+                bad.append(os.path.join(dirpath, f))
+    assert not bad, bad
+    from noc_b200 import capi
+    if os.path.exists(capi.LIB_PATH):
+        deps = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
+        assert "oracle" not in deps
