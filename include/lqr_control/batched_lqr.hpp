@@ -138,6 +138,13 @@ class InfiniteHorizonLqr {
     // the C-ABI takes Q | R only; they are the leading part of the packed weights
     ctx_->check(noc_dare_solve_batch(ctx_->handle(), &prob_, batch, AB, weights_.qrqf.data(), P, K, iters, status));
   }
+  // the built-in quadrotor linearised at the operating points xbar [batch][12], ubar [batch][4] (nullptr = hover thrust)
+  void solveAt(int64_t batch, const double* xbar, const double* ubar, double* P, double* K, int32_t* iters,
+               int32_t* status) {
+    noc_problem_t p = prob_;
+    p.model = NOC_MODEL_QUAD12; p.n = 12; p.m = 4;
+    ctx_->check(noc_dare_solve_at(ctx_->handle(), &p, batch, xbar, ubar, weights_.qrqf.data(), P, K, iters, status));
+  }
 
  private:
   std::shared_ptr<Context> ctx_;

@@ -157,6 +157,13 @@ int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch
 int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* AB,
                          const double* QR, double* P, double* K, int32_t* iters, int32_t* status);
 
+/* The same iteration for the built-in quadrotor model linearised at given operating points (BASELINE.json config 1:
+ * "hover linearisation"): xbar [batch][12], ubar [batch][4] or NULL (= hover thrust).  The record is built in the
+ * kernel and the structural zeros of the Jacobian are skipped, so no AB array exists; results are bit-identical to
+ * noc_linearize_batch + noc_dare_solve_batch.  prob->model must be NOC_MODEL_QUAD12.                            */
+int noc_dare_solve_at(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* xbar, const double* ubar,
+                      const double* QR, double* P, double* K, int32_t* iters, int32_t* status);
+
 /* ---- SLQ / iLQR with the built-in nonlinear models ---------------------------
  *   x0, xgoal [batch][n]; QRQf shared.
  *   x [batch][N+1][n], u [batch][N][m], K [batch][N][m*n] (NULL ok), cost [batch],

@@ -27,7 +27,7 @@ FLAG_NONE, FLAG_ASYNC = 0, 1
 EXPORTS = [
     "noc_create", "noc_destroy", "noc_last_error", "noc_version", "noc_set_stream", "noc_synchronize",
     "noc_launch_count", "noc_problem_defaults", "noc_lqr_solve_batch", "noc_linearize_batch",
-    "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_dare_solve_batch", "noc_slq_solve_batch",
+    "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_dare_solve_batch", "noc_dare_solve_at", "noc_slq_solve_batch",
     "noc_argmin_cost", "noc_profile_enable", "noc_profile_read", "noc_profile_reset", "noc_selftest_rcp",
 ]
 KERNEL_SETUP, KERNEL_ROLLOUT, KERNEL_LINEARIZE, KERNEL_RICCATI, KERNEL_FORWARD, KERNEL_ARGMIN = range(6)
@@ -79,6 +79,7 @@ def load_library():
     lib.noc_rollout_open_loop.argtypes = [vp, pp, i64, dp, dp, dp]
     lib.noc_lqr_solve_from_x0.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_dare_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp]
+    lib.noc_dare_solve_at.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_slq_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_argmin_cost.argtypes = [vp, dp, i64, C.POINTER(i64), C.POINTER(C.c_double)]
     lib.noc_profile_enable.argtypes = [vp, C.c_int]
@@ -190,6 +191,10 @@ class Solver:
     def dare_solve_batch(self, prob, batch, AB, QR, P, K, iters, status):
         self._check(self._lib.noc_dare_solve_batch(self._h, C.byref(prob), batch, _ptr(AB), _ptr(QR), _ptr(P),
                                                    _ptr(K), _ptr(iters), _ptr(status)))
+
+    def dare_solve_at(self, prob, batch, xbar, ubar, QR, P, K, iters, status):
+        self._check(self._lib.noc_dare_solve_at(self._h, C.byref(prob), batch, _ptr(xbar), _ptr(ubar), _ptr(QR),
+                                                _ptr(P), _ptr(K), _ptr(iters), _ptr(status)))
 
     def slq_solve_batch(self, prob, batch, x0, xgoal, QRQf, x=None, u=None, K=None, cost=None, iters=None,
                         alpha_idx=None, status=None):

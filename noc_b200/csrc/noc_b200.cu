@@ -893,6 +893,36 @@ int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, co
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
 
+int noc_dare_solve_at(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* xbar, const double* ubar,
+                      const double* QR, double* P, double* K, int32_t* iters, int32_t* status) {
+  int rc = check_prob(ctx, p, batch);
+  if (rc) return rc;
+  if (!xbar || !QR) return fail(ctx, NOC_ERR_BAD_ARG, "xbar and QR are required");
+  if (p->max_iter < 1) return fail(ctx, NOC_ERR_BAD_ARG, "max_iter must be >= 1");
+  if (p->model != NOC_MODEL_QUAD12) return fail(ctx, NOC_ERR_UNSUPPORTED, "noc_dare_solve_at: NOC_MODEL_QUAD12 only");
+  if (batch == 0) return NOC_OK;
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t B = (size_t)batch, n = 12, m = 4;
+  const void *dxb, *dub, *dQ;
+  void *dP, *dK, *dit, *dst;
+  if ((rc = stage_in(ctx, 0, xbar, sizeof(double) * B * n, &dxb))) return rc;
+  if ((rc = stage_in(ctx, 1, QR, sizeof(double) * (n * n + m * m), &dQ))) return rc;
+  if ((rc = stage_in(ctx, 2, ubar, sizeof(double) * B * m, &dub))) return rc;
+  if (misaligned16(dxb) || (dub && misaligned16(dub))) return fail(ctx, NOC_ERR_BAD_ARG, "device xbar / ubar must be 16-byte aligned");
+  if ((rc = stage_out(ctx, 0, P, sizeof(double) * B * n * n, &dP))) return rc;
+  if ((rc = stage_out(ctx, 1, K, sizeof(double) * B * m * n, &dK))) return rc;
+  if ((rc = stage_out(ctx, 2, iters, sizeof(int32_t) * B, &dit))) return rc;
+  if ((rc = stage_out(ctx, 3, status, sizeof(int32_t) * B, &dst))) return rc;
+  Ric12Args a{};
+  if ((rc = build_w12(ctx, (const double*)dQ, true, &a.W, &a.Qf))) { ctx->pending.clear(); return rc; }
+  a.xbar = (const double*)dxb; a.xbar_sb = 12; a.xbar_sk = 12; a.ubar = (const double*)dub; a.dt = p->dt;
+  a.K = (double*)dK; a.P0 = (double*)dP; a.iters = (int32_t*)dit; a.status = (int32_t*)dst;
+  a.tol = p->tol; a.max_iter = p->max_iter; a.batch = batch; a.N = 1;
+  rc = launch_ric12<0, RIC_DARE, true>(ctx, a);
+  if (rc) { ctx->pending.clear(); return rc; }
+  return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
+}
+
 int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
                         const double* QRQf, double* x, double* u, double* K, double* cost, int32_t* iters,
                         int32_t* alpha_idx, int32_t* status) {

@@ -97,6 +97,11 @@ int main() {
     const int rit = noc_oracle_dare(12, 4, A, Bm, w.qrqf.data(), w.qrqf.data() + 144, 1e-12, 10000, rP, rK);
     CHECK(st == 0 && it == rit && std::memcmp(P, rP, sizeof(P)) == 0 && std::memcmp(K, rK, sizeof(K)) == 0);
     std::printf("hover DARE: %d iterations\n", it);
+    // the same through solveAt: the operating point instead of its linearisation
+    double P2[144], K2[48];
+    int32_t it2 = 0, st2 = -1;
+    dare.solveAt(1, x, nullptr, P2, K2, &it2, &st2);
+    CHECK(st2 == 0 && it2 == rit && std::memcmp(P2, rP, sizeof(P2)) == 0 && std::memcmp(K2, rK, sizeof(K2)) == 0);
   }
   {  // SLQ to waypoints
     const int64_t B = 6;

@@ -55,6 +55,30 @@ def test_dare_bitexact_and_iteration_counts(oracle, solver, layout):
     assert 150 < iters.min() and iters.max() < 400   # 218 at exact hover
 
 
+@pytest.mark.parametrize("with_u", [False, True])
+def test_dare_at_operating_points_bitexact(oracle, solver, with_u):
+    """noc_dare_solve_at: the built-in model linearised in the kernel (pruned Jacobian) == linearise + DARE of the
+    oracle, bit for bit, iteration counts included; several warps, ragged tail."""
+    from noc_b200 import capi
+    rng = np.random.default_rng(21)
+    batch = 77
+    Q, R, _ = pb.default_weights()
+    xb = np.zeros((batch, 12))
+    xb[:, 6:8] = rng.uniform(-0.25, 0.25, (batch, 2)); xb[:, 8] = rng.uniform(-np.pi, np.pi, batch)
+    xb[:, 9:12] = rng.uniform(-0.3, 0.3, (batch, 3))
+    ub = (pb.hover_input()[None, :] + rng.uniform(-0.2, 0.2, (batch, 4))) if with_u else None
+    qr = np.concatenate([Q.ravel(), R.ravel()])
+    prob = capi.problem(capi.MODEL_QUAD12, 1, tol=1e-12, max_iter=10000)
+    P = np.empty((batch, 12, 12)); K = np.empty((batch, 4, 12))
+    iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    solver.dare_solve_at(prob, batch, xb, ub, qr, P, K, iters, status)
+    for b in range(batch):
+        A, B = oracle.linearize(0, xb[b], ub[b] if with_u else pb.hover_input(), 0.02)
+        Pr, Kr, it = oracle.dare(A, B, Q, R, tol=1e-12, max_iter=10000)
+        assert status[b] == 0 and iters[b] == it
+        assert np.array_equal(P[b], Pr) and np.array_equal(K[b], Kr)
+
+
 def test_dare_max_iter_status(oracle, solver):
     from noc_b200 import capi
     rng = np.random.default_rng(12)

@@ -60,19 +60,28 @@ def main():
         cpu_us = (time.perf_counter() - t0) / 20 * 1e6
         nb = 65536 if not args.quick else 4096
         rng = np.random.default_rng(1)
-        recs = np.empty((nb, 192))
+        recs = np.empty((nb, 192)); xop = np.zeros((nb, 12))
         for b in range(min(nb, 512)):
             x = np.zeros(12); x[6:8] = rng.uniform(-0.2, 0.2, 2); x[8] = rng.uniform(-np.pi, np.pi)
             Ab, Bb = oracle.linearize(0, x, pb.hover_input(), pb.DT)
-            recs[b] = np.concatenate([Ab.ravel(), Bb.ravel()])
+            recs[b] = np.concatenate([Ab.ravel(), Bb.ravel()]); xop[b] = x
         recs[512:] = recs[np.arange(512, nb) % 512] if nb > 512 else recs[:0]
+        xop[512:] = xop[np.arange(512, nb) % 512] if nb > 512 else xop[:0]
         d_rec = T(recs); d_qr = T(np.concatenate([Q.ravel(), R.ravel()]))
         dP = torch.empty(nb, 144, **f64); dK = torch.empty(nb, 48, **f64); dit = torch.empty(nb, **i32); dst = torch.empty(nb, **i32)
         p = capi.problem(capi.MODEL_LTV_USER, 1, tol=1e-12, max_iter=10000, flags=capi.FLAG_ASYNC)
         fn = lambda: s.dare_solve_batch(p, nb, d_rec, d_qr, dP, dK, dit, dst)
         fn(); ms = ev_time(torch, stream, fn, 3)
         its = dit.cpu().numpy()
+        # the same operating points through noc_dare_solve_at: linearised in the kernel, structural zeros skipped
+        d_xop = T(xop); dP2 = torch.empty_like(dP); dK2 = torch.empty_like(dK); dit2 = torch.empty_like(dit); dst2 = torch.empty_like(dst)
+        pm = capi.problem(capi.MODEL_QUAD12, 1, tol=1e-12, max_iter=10000, flags=capi.FLAG_ASYNC)
+        fn2 = lambda: s.dare_solve_at(pm, nb, d_xop, None, d_qr, dP2, dK2, dit2, dst2)
+        fn2(); ms2 = ev_time(torch, stream, fn2, 3)
+        same = bool(torch.equal(dP, dP2) and torch.equal(dK, dK2) and torch.equal(dit, dit2))
         out.append({"config": 1, "what": "DARE fixed point, quadrotor hover, tol 1e-12", "cpu_oracle_us_per_solve_1thread": cpu_us,
+                    "gpu_at_operating_points_ms": ms2, "gpu_at_operating_points_solves_per_s": nb / ms2 * 1e3,
+                    "at_operating_points_bit_identical": same,
                     "cpu_iterations": int(it), "gpu_batch": nb, "gpu_ms": ms, "gpu_solves_per_s": nb / ms * 1e3,
                     "gpu_riccati_steps_per_s": float(its.sum()) / ms * 1e3, "gpu_iters_min_max": [int(its.min()), int(its.max())],
                     "status_ok": int((dst.cpu().numpy() == 0).sum())})
