@@ -102,6 +102,13 @@ class BatchedLqr {
     ctx_->check(noc_lqr_solve_from_x0(ctx_->handle(), &prob_, batch, x0, weights_.qrqf.data(), K, K0, P0, cost,
                                       status));
   }
+  // time-varying LQR along the open-loop rollout of the nominal inputs ubar [batch][N][m] (nullptr = hover thrust);
+  // xbar [batch][N+1][n] receives that nominal if given
+  void solveAlong(int64_t batch, const double* x0, const double* ubar, double* xbar, double* K, double* K0, double* P0,
+                  double* cost, int32_t* status) {
+    ctx_->check(noc_lqr_solve_along(ctx_->handle(), &prob_, batch, x0, ubar, weights_.qrqf.data(), xbar, K, K0, P0,
+                                    cost, status));
+  }
   void linearize(int64_t batch, const double* xbar, const double* ubar, double* AB) {
     ctx_->check(noc_linearize_batch(ctx_->handle(), &prob_, batch, xbar, ubar, AB));
   }

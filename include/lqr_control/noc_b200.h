@@ -148,6 +148,13 @@ int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch
                           const double* QRQf, double* K, double* K0, double* P0, double* cost,
                           int32_t* status);
 
+/* Time-varying LQR along a nominal input sequence (tracking controller around a planned trajectory): as
+ * noc_lqr_solve_from_x0, but the nominal is the open-loop rollout of ubar [batch][N][m] (NULL = hover thrust) from x0,
+ * and it is returned in xbar [batch][N+1][n] if that pointer is given.  Linearisation is fused into the sweep.     */
+int noc_lqr_solve_along(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* x0, const double* ubar,
+                        const double* QRQf, double* xbar, double* K, double* K0, double* P0, double* cost,
+                        int32_t* status);
+
 /* ---- infinite-horizon LQR by fixed-point iteration ----------------------------
  *   AB [batch][n*n+n*m] one LTI record per instance; QR [n*n+m*m] shared.
  *   Iterates the sweep step from P = Q until max|P'-P| < tol * max|P'| or max_iter.

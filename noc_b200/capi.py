@@ -27,7 +27,7 @@ FLAG_NONE, FLAG_ASYNC = 0, 1
 EXPORTS = [
     "noc_create", "noc_destroy", "noc_last_error", "noc_version", "noc_set_stream", "noc_synchronize",
     "noc_launch_count", "noc_problem_defaults", "noc_lqr_solve_batch", "noc_linearize_batch",
-    "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_dare_solve_batch", "noc_dare_solve_at", "noc_slq_solve_batch",
+    "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_lqr_solve_along", "noc_dare_solve_batch", "noc_dare_solve_at", "noc_slq_solve_batch",
     "noc_argmin_cost", "noc_profile_enable", "noc_profile_read", "noc_profile_reset", "noc_selftest_rcp",
 ]
 KERNEL_SETUP, KERNEL_ROLLOUT, KERNEL_LINEARIZE, KERNEL_RICCATI, KERNEL_FORWARD, KERNEL_ARGMIN = range(6)
@@ -78,6 +78,7 @@ def load_library():
     lib.noc_linearize_batch.argtypes = [vp, pp, i64, dp, dp, dp]
     lib.noc_rollout_open_loop.argtypes = [vp, pp, i64, dp, dp, dp]
     lib.noc_lqr_solve_from_x0.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp]
+    lib.noc_lqr_solve_along.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_dare_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp]
     lib.noc_dare_solve_at.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_slq_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
@@ -187,6 +188,10 @@ class Solver:
     def lqr_solve_from_x0(self, prob, batch, x0, QRQf, K=None, K0=None, P0=None, cost=None, status=None):
         self._check(self._lib.noc_lqr_solve_from_x0(self._h, C.byref(prob), batch, _ptr(x0), _ptr(QRQf), _ptr(K),
                                                     _ptr(K0), _ptr(P0), _ptr(cost), _ptr(status)))
+
+    def lqr_solve_along(self, prob, batch, x0, ubar, QRQf, xbar=None, K=None, K0=None, P0=None, cost=None, status=None):
+        self._check(self._lib.noc_lqr_solve_along(self._h, C.byref(prob), batch, _ptr(x0), _ptr(ubar), _ptr(QRQf),
+                                                  _ptr(xbar), _ptr(K), _ptr(K0), _ptr(P0), _ptr(cost), _ptr(status)))
 
     def dare_solve_batch(self, prob, batch, AB, QR, P, K, iters, status):
         self._check(self._lib.noc_dare_solve_batch(self._h, C.byref(prob), batch, _ptr(AB), _ptr(QR), _ptr(P),

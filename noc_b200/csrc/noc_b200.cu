@@ -321,15 +321,20 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
 }
 
 template <int MODEL>
-int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* QRQf,
-                 double* K, double* K0, double* P0, double* cost, int32_t* status) {
+int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* ubar,
+                 const double* QRQf, double* xbar_out, double* K, double* K0, double* P0, double* cost,
+                 int32_t* status) {
   int rc;
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t B = (size_t)batch, n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, N = p->N, rec = n * n + n * m;
-  const void *dx0, *dQ;
-  void *dK, *dK0, *dP0, *dcost, *dstatus;
+  const void *dx0, *dQ, *dub;
+  void *dK, *dK0, *dP0, *dcost, *dstatus, *dxout;
   if ((rc = stage_in(ctx, 0, x0, sizeof(double) * B * n, &dx0))) return rc;
   if ((rc = stage_in(ctx, 1, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
+  if ((rc = stage_in(ctx, 2, ubar, sizeof(double) * B * N * m, &dub))) return rc;   // nominal inputs (NULL = hover thrust)
+  if (dub && misaligned16(dub)) return fail(ctx, NOC_ERR_BAD_ARG, "device ubar must be 16-byte aligned");
+  if ((rc = stage_out(ctx, 5, xbar_out, sizeof(double) * B * (N + 1) * n, &dxout))) return rc;
+  if (dxout && misaligned16(dxout)) return fail(ctx, NOC_ERR_BAD_ARG, "device xbar must be 16-byte aligned");
   if ((rc = stage_out(ctx, 0, K, sizeof(double) * B * N * m * n, &dK))) return rc;
   if ((rc = stage_out(ctx, 1, K0, sizeof(double) * B * m * n, &dK0))) return rc;
   if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
@@ -350,6 +355,7 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   const size_t per_inst = sizeof(double) * (N + 1) * n;
   size_t outer = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
   if (outer < B) outer = std::max<size_t>(32, outer & ~size_t(31));
+  if (dxout) outer = B;   // the caller's xbar array (instance-major) holds the nominal: no scratch, no outer chunks
   const bool overlap = !ctx->pending.empty() && B >= 8192 && !(p->flags & NOC_FLAG_ASYNC);
   // inner chunks are whole waves of the sweep kernel (instances resident on all SMs at once: 64 per SM for n=12,
   // 16 for n=24), about eight per call: a chunk that ends mid-wave pays for the full wave, and the smaller the last
@@ -360,7 +366,7 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   if (const char* e = std::getenv("NOC_B200_CHUNK_WAVES"))   // experiment hook
     if (overlap) inner_pref = std::max<size_t>(1, (size_t)std::atoll(e)) * wave;
   void* dxbar = nullptr;
-  if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * outer * (N + 1) * n, &dxbar))) return rc;
+  if (!dxout && (rc = scratch(ctx, SCR_XBAR, sizeof(double) * outer * (N + 1) * n, &dxbar))) return rc;
   (void)rec;
   typename std::conditional<MODEL == 0, Ric12Args, Ric24Args>::type fa{};
   if (MODEL == 0) rc = build_w12(ctx, (const double*)dQ, false, &fa.W, &fa.Qf);
@@ -371,8 +377,14 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
     const size_t ob = std::min(outer, B - o);
     {
       LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
-      k_rollout_open_loop<MODEL><<<(unsigned)((ob + 127) / 128), 128, 0, ctx->stream>>>(
-          (const double*)dx0 + o * n, nullptr, (double*)dxbar, (long long)ob, p->N, p->dt, (long long)n, (long long)(ob * n));
+      const double* ub = dub ? (const double*)dub + o * N * m : nullptr;
+      if (dxout)
+        k_rollout_open_loop<MODEL><<<(unsigned)((ob + 127) / 128), 128, 0, ctx->stream>>>(
+            (const double*)dx0 + o * n, ub, (double*)dxout + o * (N + 1) * n, (long long)ob, p->N, p->dt,
+            (long long)((N + 1) * n), (long long)n);
+      else
+        k_rollout_open_loop<MODEL><<<(unsigned)((ob + 127) / 128), 128, 0, ctx->stream>>>(
+            (const double*)dx0 + o * n, ub, (double*)dxbar, (long long)ob, p->N, p->dt, (long long)n, (long long)(ob * n));
     }
     NOC_CUDA(ctx, cudaGetLastError());
     const size_t inner = std::min(ob, inner_pref);
@@ -387,8 +399,9 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
     for (size_t i = 0; i < ob; i += inner, ++chunk_no) {
       const size_t off = o + i;
       const long long cb = (long long)std::min(inner, ob - i);
-      fa.xbar = (const double*)dxbar + i * n; fa.xbar_sb = (long long)n; fa.xbar_sk = (long long)(ob * n);   // step-major scratch
-      fa.ubar = nullptr; fa.dt = p->dt;
+      if (dxout) { fa.xbar = (const double*)dxout + off * (N + 1) * n; fa.xbar_sb = 0; fa.xbar_sk = 0; }   // dense, instance-major
+      else { fa.xbar = (const double*)dxbar + i * n; fa.xbar_sb = (long long)n; fa.xbar_sk = (long long)(ob * n); }   // step-major scratch
+      fa.ubar = dub ? (const double*)dub + off * N * m : nullptr; fa.dt = p->dt;
       fa.x0 = (const double*)dx0 + off * n;
       fa.K = dK ? (double*)dK + off * N * m * n : nullptr;
       fa.K0 = dK0 ? (double*)dK0 + off * m * n : nullptr;
@@ -848,8 +861,20 @@ int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
   if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "from_x0 pipeline needs a built-in model");
   if (!x0 || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0 and QRQf are required");
   if (batch == 0) return NOC_OK;
-  return p->model == NOC_MODEL_QUAD12 ? from_x0_impl<0>(ctx, p, batch, x0, QRQf, K, K0, P0, cost, status)
-                                      : from_x0_impl<1>(ctx, p, batch, x0, QRQf, K, K0, P0, cost, status);
+  return p->model == NOC_MODEL_QUAD12 ? from_x0_impl<0>(ctx, p, batch, x0, nullptr, QRQf, nullptr, K, K0, P0, cost, status)
+                                      : from_x0_impl<1>(ctx, p, batch, x0, nullptr, QRQf, nullptr, K, K0, P0, cost, status);
+}
+
+int noc_lqr_solve_along(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* ubar,
+                        const double* QRQf, double* xbar, double* K, double* K0, double* P0, double* cost,
+                        int32_t* status) {
+  int rc = check_prob(ctx, p, batch);
+  if (rc) return rc;
+  if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "noc_lqr_solve_along needs a built-in model");
+  if (!x0 || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0 and QRQf are required");
+  if (batch == 0) return NOC_OK;
+  return p->model == NOC_MODEL_QUAD12 ? from_x0_impl<0>(ctx, p, batch, x0, ubar, QRQf, xbar, K, K0, P0, cost, status)
+                                      : from_x0_impl<1>(ctx, p, batch, x0, ubar, QRQf, xbar, K, K0, P0, cost, status);
 }
 
 int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* AB, const double* QR,

@@ -296,3 +296,48 @@ def test_per_instance_weights_bitexact(oracle, solver, n, m):
         assert status[b] == ref["status"][0] == 0
         assert np.array_equal(K[b], ref["K"][0]) and np.array_equal(K0[b], ref["K0"][0])
         assert np.array_equal(P0[b], ref["P0"][0]) and cost[b] == ref["cost"][0]
+
+
+@pytest.mark.parametrize("model", [0, 1])
+@pytest.mark.parametrize("want_xbar", [False, True])
+def test_lqr_along_nominal_inputs_bitexact(oracle, solver, model, want_xbar):
+    """noc_lqr_solve_along: time-varying LQR around the open-loop rollout of a given input sequence (fused
+    linearisation) == oracle rollout + linearisation + sweep, bit for bit; with and without the nominal returned."""
+    from noc_b200 import capi
+    n, m = pb.dims(model)
+    batch, N = 21, 30
+    rng = np.random.default_rng(60 + model)
+    qr = pb.pack_qrqf(*pb.default_weights(model))
+    x0 = pb.sample_x0(batch, seed=61, model=model)
+    ubar = pb.hover_input(model)[None, None, :] + 0.4 * rng.standard_normal((batch, N, m))
+    xbar = np.empty((batch, N + 1, n)) if want_xbar else None
+    K = np.empty((batch, N, m, n)); K0 = np.empty((batch, m, n)); P0 = np.empty((batch, n, n)); cost = np.empty(batch)
+    status = np.full(batch, -1, dtype=np.int32)
+    solver.lqr_solve_along(capi.problem(model, N), batch, x0, ubar, qr, xbar=xbar, K=K, K0=K0, P0=P0, cost=cost, status=status)
+    for b in range(batch):
+        xr = oracle.rollout_open_loop(model, N, 0.02, x0[b], ubar[b])
+        AB = oracle.linearize_traj(model, N, 0.02, xr, ubar[b])
+        ref = oracle.lqr_batch(n, m, N, AB[None], qr, x0dev=x0[b:b + 1])
+        assert status[b] == 0 == ref["status"][0]
+        assert np.array_equal(K[b], ref["K"][0]) and np.array_equal(K0[b], ref["K0"][0])
+        assert np.array_equal(P0[b], ref["P0"][0]) and cost[b] == ref["cost"][0]
+        if want_xbar:
+            assert np.array_equal(xbar[b], xr)
+
+
+def test_lqr_along_large_host_batch_chunks(oracle, solver):
+    """The overlap schedule (host outputs, batch >= 8192, two streams) with a nominal input sequence and the nominal
+    returned: sample of instances against the oracle."""
+    from noc_b200 import capi
+    batch, N = 20000, 12
+    rng = np.random.default_rng(70)
+    qr = pb.pack_qrqf(*pb.default_weights())
+    x0 = pb.sample_x0(batch, seed=71)
+    ubar = pb.hover_input()[None, None, :] + 0.3 * rng.standard_normal((batch, N, 4))
+    xbar = np.empty((batch, N + 1, 12)); K0 = np.empty((batch, 4, 12)); st = np.full(batch, -1, dtype=np.int32)
+    solver.lqr_solve_along(capi.problem(0, N), batch, x0, ubar, qr, xbar=xbar, K0=K0, status=st)
+    assert np.all(st == 0)
+    for b in range(0, batch, 997):
+        xr = oracle.rollout_open_loop(0, N, 0.02, x0[b], ubar[b])
+        ref = oracle.lqr_batch(12, 4, N, oracle.linearize_traj(0, N, 0.02, xr, ubar[b])[None], qr)
+        assert np.array_equal(xbar[b], xr) and np.array_equal(K0[b], ref["K0"][0])
