@@ -175,6 +175,12 @@ class BatchedSlq {
     ctx_->check(noc_slq_solve_batch(ctx_->handle(), &prob_, batch, x0, xgoal, weights_.qrqf.data(), x, u, K, cost,
                                     iters, alpha_idx, status));
   }
+  // warm start from the input sequences u_init [batch][N][m] (e.g. the previous MPC solution shifted by one step)
+  void solveWarm(int64_t batch, const double* x0, const double* xgoal, const double* u_init, double* x, double* u,
+                 double* K, double* cost, int32_t* iters, int32_t* alpha_idx, int32_t* status) {
+    ctx_->check(noc_slq_solve_warm(ctx_->handle(), &prob_, batch, x0, xgoal, weights_.qrqf.data(), u_init, x, u, K, cost,
+                                   iters, alpha_idx, status));
+  }
 
  private:
   std::shared_ptr<Context> ctx_;

@@ -178,6 +178,11 @@ int noc_dare_solve_at(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, co
 int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* x0,
                         const double* xgoal, const double* QRQf, double* x, double* u, double* K,
                         double* cost, int32_t* iters, int32_t* alpha_idx, int32_t* status);
+/* The same, started from the input sequence u_init [batch][N][m] instead of hover thrust (receding-horizon MPC: the
+ * previous solution shifted by one step).  u_init may be the `u` output array itself.  NULL = hover thrust.        */
+int noc_slq_solve_warm(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* x0, const double* xgoal,
+                       const double* QRQf, const double* u_init, double* x, double* u, double* K, double* cost,
+                       int32_t* iters, int32_t* alpha_idx, int32_t* status);
 
 /* ---- "pick the best rollout" on this GPU: index and value of the smallest finite cost ------------
  * (the cross-GPU step is one all-gather of (cost,index) pairs in the host layer)          */

@@ -27,7 +27,7 @@ FLAG_NONE, FLAG_ASYNC = 0, 1
 EXPORTS = [
     "noc_create", "noc_destroy", "noc_last_error", "noc_version", "noc_set_stream", "noc_synchronize",
     "noc_launch_count", "noc_problem_defaults", "noc_lqr_solve_batch", "noc_linearize_batch",
-    "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_lqr_solve_along", "noc_dare_solve_batch", "noc_dare_solve_at", "noc_slq_solve_batch",
+    "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_lqr_solve_along", "noc_dare_solve_batch", "noc_dare_solve_at", "noc_slq_solve_batch", "noc_slq_solve_warm",
     "noc_argmin_cost", "noc_profile_enable", "noc_profile_read", "noc_profile_reset", "noc_selftest_rcp",
 ]
 KERNEL_SETUP, KERNEL_ROLLOUT, KERNEL_LINEARIZE, KERNEL_RICCATI, KERNEL_FORWARD, KERNEL_ARGMIN = range(6)
@@ -82,6 +82,7 @@ def load_library():
     lib.noc_dare_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp]
     lib.noc_dare_solve_at.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_slq_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
+    lib.noc_slq_solve_warm.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_argmin_cost.argtypes = [vp, dp, i64, C.POINTER(i64), C.POINTER(C.c_double)]
     lib.noc_profile_enable.argtypes = [vp, C.c_int]
     lib.noc_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
@@ -202,10 +203,10 @@ class Solver:
                                                 _ptr(P), _ptr(K), _ptr(iters), _ptr(status)))
 
     def slq_solve_batch(self, prob, batch, x0, xgoal, QRQf, x=None, u=None, K=None, cost=None, iters=None,
-                        alpha_idx=None, status=None):
-        self._check(self._lib.noc_slq_solve_batch(self._h, C.byref(prob), batch, _ptr(x0), _ptr(xgoal), _ptr(QRQf),
-                                                  _ptr(x), _ptr(u), _ptr(K), _ptr(cost), _ptr(iters),
-                                                  _ptr(alpha_idx), _ptr(status)))
+                        alpha_idx=None, status=None, u_init=None):
+        self._check(self._lib.noc_slq_solve_warm(self._h, C.byref(prob), batch, _ptr(x0), _ptr(xgoal), _ptr(QRQf),
+                                                 _ptr(u_init), _ptr(x), _ptr(u), _ptr(K), _ptr(cost), _ptr(iters),
+                                                 _ptr(alpha_idx), _ptr(status)))
 
     def selftest_rcp(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)

@@ -442,16 +442,17 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
 
 template <int MODEL>
 int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
-             const double* QRQf, double* x, double* u, double* K, double* cost, int32_t* iters, int32_t* alpha_idx,
-             int32_t* status) {
+             const double* QRQf, const double* u_init, double* x, double* u, double* K, double* cost, int32_t* iters,
+             int32_t* alpha_idx, int32_t* status) {
   int rc;
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t B = (size_t)batch, n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, N = p->N, rec = n * n + n * m;
-  const void *dx0, *dxg, *dQ;
+  const void *dx0, *dxg, *dQ, *dui;
   void *dx, *du, *dK, *dJ, *dit, *dai, *dst;
   if ((rc = stage_in(ctx, 0, x0, sizeof(double) * B * n, &dx0))) return rc;
   if ((rc = stage_in(ctx, 1, xgoal, sizeof(double) * B * n, &dxg))) return rc;
   if ((rc = stage_in(ctx, 2, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
+  if ((rc = stage_in(ctx, 3, u_init, sizeof(double) * B * N * m, &dui))) return rc;   // warm start (NULL = hover thrust)
   // outputs double as the solver's working state; the ones the caller does not want live in scratch
   auto out_or_scratch = [&](int oslot, int sslot, void* host, size_t bytes, void** dev) -> int {
     if (host) return stage_out(ctx, oslot, host, bytes, dev);
@@ -490,7 +491,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   {
     LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
     k_slq_init<MODEL><<<(unsigned)((batch + 127) / 128), 128, wbytes, ctx->stream>>>(
-        (const double*)dx0, (const double*)dxg, (const double*)dQ, (double*)dx, (double*)du, (double*)dJ, (double*)dmu,
+        (const double*)dx0, (const double*)dxg, (const double*)dQ, (const double*)dui, (double*)dx, (double*)du, (double*)dJ, (double*)dmu,
         (int32_t*)dst, (int32_t*)dit, (int32_t*)dai, (int32_t*)didx0, batch, p->N, p->dt, p->reg0, p->max_iter);
   }
   NOC_CUDA(ctx, cudaGetLastError());
@@ -951,6 +952,12 @@ int noc_dare_solve_at(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const
 int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
                         const double* QRQf, double* x, double* u, double* K, double* cost, int32_t* iters,
                         int32_t* alpha_idx, int32_t* status) {
+  return noc_slq_solve_warm(ctx, p, batch, x0, xgoal, QRQf, nullptr, x, u, K, cost, iters, alpha_idx, status);
+}
+
+int noc_slq_solve_warm(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
+                       const double* QRQf, const double* u_init, double* x, double* u, double* K, double* cost,
+                       int32_t* iters, int32_t* alpha_idx, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
   if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "SLQ needs a built-in nonlinear model");
@@ -961,8 +968,8 @@ int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if (batch > 0x7fffffffLL) return fail(ctx, NOC_ERR_BAD_ARG, "batch too large for 32-bit work lists");
   if (batch == 0) return NOC_OK;
   return p->model == NOC_MODEL_QUAD12
-             ? slq_impl<0>(ctx, p, batch, x0, xgoal, QRQf, x, u, K, cost, iters, alpha_idx, status)
-             : slq_impl<1>(ctx, p, batch, x0, xgoal, QRQf, x, u, K, cost, iters, alpha_idx, status);
+             ? slq_impl<0>(ctx, p, batch, x0, xgoal, QRQf, u_init, x, u, K, cost, iters, alpha_idx, status)
+             : slq_impl<1>(ctx, p, batch, x0, xgoal, QRQf, u_init, x, u, K, cost, iters, alpha_idx, status);
 }
 
 int noc_selftest_rcp(noc_ctx* ctx, const double* x, double* y_fast, double* y_ieee, int64_t n) {

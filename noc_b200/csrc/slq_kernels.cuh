@@ -68,7 +68,9 @@ __device__ __forceinline__ void load_weights(double* sw, const double* __restric
 // also resets the per-instance solver state.  One thread per instance.
 template <int MODEL>
 __global__ void __launch_bounds__(128) k_slq_init(const double* __restrict__ x0, const double* __restrict__ xgoal,
-                                                  const double* __restrict__ qrqf, double* __restrict__ x,
+                                                  const double* __restrict__ qrqf,
+                                                  const double* __restrict__ u_init,   // [batch][N][m] or nullptr (hover)
+                                                  double* __restrict__ x,
                                                   double* __restrict__ u, double* __restrict__ J,
                                                   double* __restrict__ mu, int32_t* __restrict__ status,
                                                   int32_t* __restrict__ iters, int32_t* __restrict__ alpha_idx,
@@ -89,6 +91,10 @@ __global__ void __launch_bounds__(128) k_slq_init(const double* __restrict__ x0,
   double* uo = u + (size_t)b * N * m;
   double cost = 0.0;
   for (int k = 0; k < N; ++k) {
+    if (u_init) {
+#pragma unroll
+      for (int c = 0; c < m; ++c) uk[c] = u_init[((size_t)b * N + k) * m + c];
+    }
 #pragma unroll
     for (int i = 0; i < n; ++i) xo[(size_t)k * n + i] = xk[i];
 #pragma unroll

@@ -813,6 +813,13 @@ double noc_oracle_forward_box(int model, int N, double dt, const double* xbar, c
 int noc_oracle_slq(const noc_oracle_slq_opts* o, const double* x0, const double* xgoal,
                    const double* QRQf, double* x, double* u, double* K, double* kff, double* cost,
                    int32_t* iters, int32_t* alpha_idx, double* reg) {
+  return noc_oracle_slq_warm(o, x0, xgoal, QRQf, NULL, x, u, K, kff, cost, iters, alpha_idx, reg);
+}
+
+/* as noc_oracle_slq, starting from the input sequence u_init[N*m] (MPC warm start) instead of hover thrust */
+int noc_oracle_slq_warm(const noc_oracle_slq_opts* o, const double* x0, const double* xgoal,
+                        const double* QRQf, const double* u_init, double* x, double* u, double* K, double* kff,
+                        double* cost, int32_t* iters, int32_t* alpha_idx, double* reg) {
   int n, m;
   noc_oracle_model_dims(o->model, &n, &m);
   const int N = o->N;
@@ -822,7 +829,8 @@ int noc_oracle_slq(const noc_oracle_slq_opts* o, const double* x0, const double*
   double* kw = kff ? kff : (double*)malloc((size_t)N * m * sizeof(double));
   double* xn = (double*)malloc((size_t)(N + 1) * n * sizeof(double));
   double* un = (double*)malloc((size_t)N * m * sizeof(double));
-  for (int k = 0; k < N; ++k) memcpy(u + (size_t)k * m, uh, (size_t)m * sizeof(double));
+  if (u_init) memcpy(u, u_init, (size_t)N * m * sizeof(double));
+  else for (int k = 0; k < N; ++k) memcpy(u + (size_t)k * m, uh, (size_t)m * sizeof(double));
   noc_oracle_rollout_open_loop(o->model, N, o->dt, x0, u, x);
   double J = noc_oracle_traj_cost(o->model, N, x, u, xgoal, QRQf);
   double mu = o->reg0;
@@ -868,6 +876,13 @@ void noc_oracle_slq_batch(const noc_oracle_slq_opts* o, int64_t batch, const dou
                           const double* xgoal, const double* QRQf, double* x, double* u, double* K,
                           double* cost, int32_t* iters, int32_t* alpha_idx, int32_t* status,
                           int threads) {
+  noc_oracle_slq_batch_warm(o, batch, x0, xgoal, QRQf, NULL, x, u, K, cost, iters, alpha_idx, status, threads);
+}
+
+void noc_oracle_slq_batch_warm(const noc_oracle_slq_opts* o, int64_t batch, const double* x0,
+                               const double* xgoal, const double* QRQf, const double* u_init, double* x, double* u,
+                               double* K, double* cost, int32_t* iters, int32_t* alpha_idx, int32_t* status,
+                               int threads) {
   int n, m;
   noc_oracle_model_dims(o->model, &n, &m);
   const int N = o->N;
@@ -877,8 +892,9 @@ void noc_oracle_slq_batch(const noc_oracle_slq_opts* o, int64_t batch, const dou
     double* ub = u ? u + (size_t)b * N * m : (double*)malloc((size_t)N * m * sizeof(double));
     int32_t* ai = alpha_idx ? alpha_idx + (size_t)b * o->max_iter : (int32_t*)malloc((size_t)o->max_iter * sizeof(int32_t));
     double c; int32_t itn;
-    const int st = noc_oracle_slq(o, x0 + (size_t)b * n, xgoal + (size_t)b * n, QRQf, xb, ub,
-                                  K ? K + (size_t)b * N * m * n : NULL, NULL, &c, &itn, ai, NULL);
+    const int st = noc_oracle_slq_warm(o, x0 + (size_t)b * n, xgoal + (size_t)b * n, QRQf,
+                                       u_init ? u_init + (size_t)b * N * m : NULL, xb, ub,
+                                       K ? K + (size_t)b * N * m * n : NULL, NULL, &c, &itn, ai, NULL);
     if (cost) cost[b] = c;
     if (iters) iters[b] = itn;
     if (status) status[b] = st;

@@ -86,6 +86,13 @@ void noc_oracle_slq_batch(const noc_oracle_slq_opts* o, int64_t batch, const dou
                           const double* xgoal, const double* QRQf, double* x, double* u, double* K,
                           double* cost, int32_t* iters, int32_t* alpha_idx, int32_t* status,
                           int threads);
+int noc_oracle_slq_warm(const noc_oracle_slq_opts* o, const double* x0, const double* xgoal,
+                        const double* QRQf, const double* u_init, double* x, double* u, double* K, double* kff,
+                        double* cost, int32_t* iters, int32_t* alpha_idx, double* reg);
+void noc_oracle_slq_batch_warm(const noc_oracle_slq_opts* o, int64_t batch, const double* x0,
+                               const double* xgoal, const double* QRQf, const double* u_init, double* x, double* u,
+                               double* K, double* cost, int32_t* iters, int32_t* alpha_idx, int32_t* status,
+                               int threads);
 /* one backward pass (affine) for unit tests: returns 0 or NOT_PD */
 int noc_oracle_backward_affine(int model, int N, double dt, const double* xbar, const double* ubar,
                                const double* xgoal, const double* QRQf, double mu, double* K,

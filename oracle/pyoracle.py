@@ -206,7 +206,7 @@ def slq(opts, x0, xgoal, QRQf, want_K=True):
                 reg=reg.value)
 
 
-def slq_batch(opts, x0, xgoal, QRQf, want_traj=True, want_K=False, threads=0):
+def slq_batch(opts, x0, xgoal, QRQf, want_traj=True, want_K=False, threads=0, u_init=None):
     n, m = dims(opts.model)
     N = opts.N
     x0, xgoal, QRQf = _c(x0), _c(xgoal), _c(QRQf)
@@ -218,8 +218,9 @@ def slq_batch(opts, x0, xgoal, QRQf, want_traj=True, want_K=False, threads=0):
     iters = np.zeros(B, dtype=np.int32)
     status = np.zeros(B, dtype=np.int32)
     aidx = np.full((B, opts.max_iter), -1, dtype=np.int32)
-    lib().noc_oracle_slq_batch(C.byref(opts), C.c_int64(B), _p(x0), _p(xgoal), _p(QRQf), _p(x), _p(u), _p(K),
-                               _p(cost), _pi(iters), _pi(aidx), _pi(status), threads)
+    u_init = _c(u_init)
+    lib().noc_oracle_slq_batch_warm(C.byref(opts), C.c_int64(B), _p(x0), _p(xgoal), _p(QRQf), _p(u_init), _p(x), _p(u),
+                                    _p(K), _p(cost), _pi(iters), _pi(aidx), _pi(status), threads)
     return dict(x=x, u=u, K=K, cost=cost, iters=iters, alpha_idx=aidx, status=status)
 
 

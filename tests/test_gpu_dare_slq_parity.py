@@ -266,3 +266,29 @@ def test_slq_multiwarp_config_and_worklist_compaction(oracle, solver):
     assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
     assert np.array_equal(aidx, ref["alpha_idx"]) and np.array_equal(cost, ref["cost"])
     assert len(set(iters.tolist())) > 3
+
+
+@pytest.mark.parametrize("model", [0, 1])
+def test_slq_warm_start_bitexact_and_pays_off(oracle, solver, model):
+    """noc_slq_solve_warm: start from a given input sequence (receding-horizon MPC: the previous solution shifted by
+    one step, the state advanced by one step).  Same bits as the oracle started from the same sequence, and the
+    warm-started solve needs fewer iterations than the cold one; u_init may alias the u output."""
+    from noc_b200 import capi
+    n, m = pb.dims(model)
+    batch, N = 12, 40
+    qr = pb.pack_qrqf(*pb.default_weights(model))
+    x0 = pb.hover_state(batch, model=model); xg = pb.sample_goals(batch, seed=91, model=model)
+    prob = capi.problem(model, N)
+    cold = oracle.slq_batch(oracle.slq_opts(model, N), x0, xg, qr, want_traj=True)
+    # one MPC step later: state x_1 of the solution, inputs shifted, last input repeated
+    x1 = np.ascontiguousarray(cold["x"][:, 1]); u_init = np.concatenate([cold["u"][:, 1:], cold["u"][:, -1:]], axis=1)
+    ref = oracle.slq_batch(oracle.slq_opts(model, N), x1, xg, qr, want_traj=True, u_init=u_init)
+    x = np.empty((batch, N + 1, n)); u = u_init.copy(); cost = np.empty(batch)
+    iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    aidx = np.full((batch, prob.max_iter), -7, dtype=np.int32)
+    solver.slq_solve_batch(prob, batch, x1, xg, qr, x=x, u=u, cost=cost, iters=iters, alpha_idx=aidx, status=status, u_init=u)
+    assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
+    assert np.array_equal(aidx, ref["alpha_idx"]) and np.array_equal(cost, ref["cost"])
+    assert np.array_equal(x, ref["x"]) and np.array_equal(u, ref["u"])
+    cold1 = oracle.slq_batch(oracle.slq_opts(model, N), x1, xg, qr, want_traj=False)
+    assert iters.sum() < cold1["iters"].sum()
