@@ -43,7 +43,8 @@ typedef enum {
   NOC_ERR_UNSUPPORTED = -2, /* (n,m) / model / layout combination without a kernel */
   NOC_ERR_CUDA = -3,        /* a CUDA runtime call failed; text in noc_last_error() */
   NOC_ERR_NO_DEVICE = -4,   /* no CUDA device / not sm_100: there is no CPU fallback */
-  NOC_ERR_OOM = -5          /* device allocation failed */
+  NOC_ERR_OOM = -5,         /* device allocation failed */
+  NOC_ERR_NCCL = -6         /* NCCL could not be loaded or a collective failed (multi-GPU plane only) */
 } noc_error;
 
 /* per-instance outcome, written to status[] */
@@ -95,6 +96,21 @@ const char* noc_version(void);
 /* Launch on a caller-owned CUDA stream (cudaStream_t cast to void*); NULL restores the context's own. */
 int noc_set_stream(noc_ctx* ctx, void* cuda_stream);
 int noc_synchronize(noc_ctx* ctx);
+/* Scheduler options of a context (defaults 0 = automatic).  They change how a batch is cut into chunks, never a result. */
+typedef enum {
+  NOC_OPT_SCRATCH_LIMIT_BYTES = 0, /* cap on the library-owned scratch one chunk of a call may use (0: 60 % of the free HBM);
+                                      batches that need more are processed in several outer chunks */
+  NOC_OPT_CHUNK_WAVES = 1,         /* from-x0 pipeline with host outputs: inner chunk = this many waves of the sweep kernel */
+  NOC_OPT_SINGLE_STREAM = 2,       /* 1: inner chunks on one stream (default: two alternating streams) */
+  NOC_OPT_COUNT = 3
+} noc_option;
+int noc_set_option(noc_ctx* ctx, int option, int64_t value);
+/* Device memory for callers that do not link the CUDA runtime themselves (the C++ facade, cgo / ctypes bindings):
+ * buffers on the context's GPU, and a stream-ordered copy in any direction (host<->device, device<->device) on the
+ * context's stream.  noc_memcpy is asynchronous: noc_synchronize() before reading a host destination.            */
+int noc_device_alloc(noc_ctx* ctx, uint64_t bytes, void** out);
+int noc_device_free(noc_ctx* ctx, void* p);
+int noc_memcpy(noc_ctx* ctx, void* dst, const void* src, uint64_t bytes);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int64_t noc_launch_count(const noc_ctx* ctx);
 /* Per-kernel device time, measured with CUDA events on the launching stream (bench.py's roofline).
@@ -185,9 +201,52 @@ int noc_slq_solve_warm(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, c
                        int32_t* iters, int32_t* alpha_idx, int32_t* status);
 
 /* ---- "pick the best rollout" on this GPU: index and value of the smallest finite cost ------------
- * (the cross-GPU step is one all-gather of (cost,index) pairs in the host layer)          */
+ * Multi-CTA reduction; NaN / inf costs (failed instances) are skipped, ties go to the smallest index, no finite
+ * cost -> index -1, cost NaN.  The host variant synchronises; the _async variant leaves {double cost; int64 index}
+ * (16 bytes, `noc_cost_index_t`) in DEVICE memory at best_dev and returns without a host round trip.           */
+typedef struct { double cost; int64_t index; } noc_cost_index_t;
 int noc_argmin_cost(noc_ctx* ctx, const double* cost, int64_t batch, int64_t* best_index,
                     double* best_cost);
+int noc_argmin_cost_async(noc_ctx* ctx, const double* cost_dev, int64_t batch, int64_t index_offset,
+                          noc_cost_index_t* best_dev);
+
+/* ---- the multi-GPU plane (shard, gather, pick the best) ----------------------------------
+ * The batch shards over the GPUs of one box with no data-path collective; NCCL over NVLink is used only to gather
+ * per-instance costs and gains and to pick the best rollout.  A noc_comm is one NCCL rank bound to one noc_ctx
+ * (collectives run on the context's stream).  NCCL is loaded at run time (dlopen "libnccl.so.2"): the library has no
+ * link-time NCCL dependency, and inside a PyTorch process it shares torch's NCCL.  All pointers are DEVICE pointers
+ * of the comm's GPU; every rank contributes the same count.  Calls are asynchronous on the context's stream unless
+ * a host result pointer is given.
+ *   one process, several GPUs:  noc_comm_create_all(comms, ctxs, n)   (ncclCommInitAll; then one host thread per
+ *                               comm, or any thread between noc_comm_group_begin / _end)
+ *   one process per GPU:        rank 0 calls noc_comm_unique_id(), the launcher distributes the 128 bytes
+ *                               (torch.distributed / MPI / a file), every rank calls noc_comm_create_rank()    */
+typedef struct noc_comm noc_comm;
+#define NOC_COMM_ID_BYTES 128
+int noc_comm_unique_id(void* id128);
+int noc_comm_create_rank(noc_comm** out, noc_ctx* ctx, const void* id128, int rank, int nranks);
+int noc_comm_create_all(noc_comm** out, noc_ctx* const* ctxs, int n);
+void noc_comm_destroy(noc_comm* comm);
+int noc_comm_rank(const noc_comm* comm);
+int noc_comm_size(const noc_comm* comm);
+const char* noc_comm_last_error(const noc_comm* comm);
+int noc_comm_group_begin(void);   /* ncclGroupStart / ncclGroupEnd for single-thread multi-GPU callers */
+int noc_comm_group_end(void);
+/* all-gather of `count` elements of `elem_bytes` each per rank: dst [nranks][count] on every rank (costs: elem 8;
+ * first-step gains K0: elem 8*m*n; whole gain sequences: elem 8*N*m*n)                                        */
+int noc_comm_allgather(noc_comm* comm, const void* src_dev, void* dst_dev, int64_t count, int64_t elem_bytes);
+/* pick the best rollout over ALL ranks: multi-CTA local argmin (global index = index_offset + local index),
+ * all-gather of the ranks' 16-byte (cost, index) pairs, final argmin.  best_dev (device, 16 B) receives the winner on
+ * every rank; best_host (may be NULL) additionally receives it on the host, which synchronises the stream.     */
+int noc_comm_best_rollout(noc_comm* comm, const double* cost_dev, int64_t count, int64_t index_offset,
+                          noc_cost_index_t* best_dev, noc_cost_index_t* best_host);
+/* Sharded configs 2 / 4 in one call: this rank's slice x0 [count][n] -> nominal -> fused linearise + sweep in
+ * wave-sized chunks, and while chunk i+1 is swept, chunk i's costs and first-step gains are gathered over NVLink
+ * on a second stream into cost_all [nranks][count] and K0_all [nranks][count][m*n] (either may be NULL) — the
+ * gather hides under the sweep instead of following it.  Then the best rollout as above.  status [count] is local. */
+int noc_comm_lqr_solve_from_x0(noc_comm* comm, const noc_problem_t* prob, int64_t count, const double* x0_dev,
+                               const double* QRQf_dev, double* cost_all_dev, double* K0_all_dev,
+                               int32_t* status_dev, noc_cost_index_t* best_dev, noc_cost_index_t* best_host);
 
 /* ---- diagnostics -----------------------------------------------------------------------------------
  * The pivots' reciprocals inside the sweep use a branch-free correctly-rounded sequence valid on

@@ -18,17 +18,22 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libnoc_b200.so")
 
 # enums (mirror the header)
-OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM = 0, -1, -2, -3, -4, -5
+OK, ERR_BAD_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE, ERR_OOM, ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
+COMM_ID_BYTES = 128
 STATUS_OK, STATUS_NOT_PD, STATUS_MAX_ITER, STATUS_LS_FAIL, STATUS_REG_FAIL = 0, 1, 2, 3, 4
 MODEL_QUAD12, MODEL_DUAL24, MODEL_LTV_USER = 0, 1, 2
 LAYOUT_A_THEN_B, LAYOUT_ROWS_AB = 0, 1
 FLAG_NONE, FLAG_ASYNC = 0, 1
+OPT_SCRATCH_LIMIT_BYTES, OPT_CHUNK_WAVES, OPT_SINGLE_STREAM = 0, 1, 2
 
 EXPORTS = [
-    "noc_create", "noc_destroy", "noc_last_error", "noc_version", "noc_set_stream", "noc_synchronize",
-    "noc_launch_count", "noc_problem_defaults", "noc_lqr_solve_batch", "noc_linearize_batch",
+    "noc_create", "noc_destroy", "noc_last_error", "noc_version", "noc_set_stream", "noc_synchronize", "noc_set_option",
+    "noc_launch_count", "noc_device_alloc", "noc_device_free", "noc_memcpy", "noc_problem_defaults", "noc_lqr_solve_batch", "noc_linearize_batch",
     "noc_rollout_open_loop", "noc_lqr_solve_from_x0", "noc_lqr_solve_along", "noc_dare_solve_batch", "noc_dare_solve_at", "noc_slq_solve_batch", "noc_slq_solve_warm",
-    "noc_argmin_cost", "noc_profile_enable", "noc_profile_read", "noc_profile_reset", "noc_selftest_rcp",
+    "noc_argmin_cost", "noc_argmin_cost_async", "noc_comm_unique_id", "noc_comm_create_rank", "noc_comm_create_all",
+    "noc_comm_destroy", "noc_comm_rank", "noc_comm_size", "noc_comm_last_error", "noc_comm_group_begin",
+    "noc_comm_group_end", "noc_comm_allgather", "noc_comm_best_rollout", "noc_comm_lqr_solve_from_x0",
+    "noc_profile_enable", "noc_profile_read", "noc_profile_reset", "noc_selftest_rcp",
 ]
 KERNEL_SETUP, KERNEL_ROLLOUT, KERNEL_LINEARIZE, KERNEL_RICCATI, KERNEL_FORWARD, KERNEL_ARGMIN = range(6)
 
@@ -38,6 +43,11 @@ class Problem(C.Structure):
                 ("layout", C.c_int32), ("max_iter", C.c_int32), ("n_alpha", C.c_int32), ("flags", C.c_int32),
                 ("dt", C.c_double), ("tol", C.c_double), ("reg0", C.c_double), ("armijo", C.c_double),
                 ("u_min", C.c_double), ("u_max", C.c_double)]
+
+
+class CostIndex(C.Structure):
+    """noc_cost_index_t: the winner of a "pick the best rollout" (16 bytes, also the device-side layout)."""
+    _fields_ = [("cost", C.c_double), ("index", C.c_int64)]
 
 
 class NocError(RuntimeError):
@@ -70,6 +80,7 @@ def load_library():
     lib.noc_version.restype = C.c_char_p
     lib.noc_set_stream.argtypes = [vp, vp]
     lib.noc_synchronize.argtypes = [vp]
+    lib.noc_set_option.argtypes = [vp, C.c_int, i64]
     lib.noc_launch_count.argtypes = [vp]
     lib.noc_launch_count.restype = i64
     lib.noc_problem_defaults.argtypes = [pp, i32, i32]
@@ -84,6 +95,19 @@ def load_library():
     lib.noc_slq_solve_batch.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_slq_solve_warm.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp, dp]
     lib.noc_argmin_cost.argtypes = [vp, dp, i64, C.POINTER(i64), C.POINTER(C.c_double)]
+    lib.noc_argmin_cost_async.argtypes = [vp, dp, i64, i64, dp]
+    lib.noc_comm_unique_id.argtypes = [C.c_char_p]
+    lib.noc_comm_create_rank.argtypes = [C.POINTER(vp), vp, C.c_char_p, C.c_int, C.c_int]
+    lib.noc_comm_create_all.argtypes = [C.POINTER(vp), C.POINTER(vp), C.c_int]
+    lib.noc_comm_destroy.argtypes = [vp]
+    lib.noc_comm_destroy.restype = None
+    lib.noc_comm_rank.argtypes = [vp]
+    lib.noc_comm_size.argtypes = [vp]
+    lib.noc_comm_last_error.argtypes = [vp]
+    lib.noc_comm_last_error.restype = C.c_char_p
+    lib.noc_comm_allgather.argtypes = [vp, dp, dp, i64, i64]
+    lib.noc_comm_best_rollout.argtypes = [vp, dp, i64, i64, dp, C.POINTER(CostIndex)]
+    lib.noc_comm_lqr_solve_from_x0.argtypes = [vp, pp, i64, dp, dp, dp, dp, dp, dp, C.POINTER(CostIndex)]
     lib.noc_profile_enable.argtypes = [vp, C.c_int]
     lib.noc_profile_read.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(i64)]
     lib.noc_profile_reset.argtypes = [vp]
@@ -102,21 +126,38 @@ def problem(model=MODEL_QUAD12, N=100, **kw) -> Problem:
     return p
 
 
-def _ptr(a, dtype=None):
-    """Raw pointer of a numpy array (host) or torch tensor (host or CUDA); None -> NULL."""
+def _ptr(a, dtype=np.float64, count=None, name="argument"):
+    """Raw pointer of a numpy array (host) or torch tensor (host or CUDA); None -> NULL.  The library reads / writes
+    `count` elements of `dtype` behind the pointer and cannot see the array, so type and size are checked here."""
     if a is None:
         return None
+    want = np.dtype(dtype)
     if isinstance(a, np.ndarray):
-        if dtype is not None and a.dtype != dtype:
-            raise TypeError(f"expected {dtype}, got {a.dtype}")
+        if a.dtype != want:
+            raise TypeError(f"{name}: expected {want}, got {a.dtype}")
         if not a.flags["C_CONTIGUOUS"]:
-            raise ValueError("array must be C-contiguous")
+            raise ValueError(f"{name}: array must be C-contiguous")
+        if count is not None and a.size < count:
+            raise ValueError(f"{name}: needs at least {count} elements, got {a.size}")
         return a.ctypes.data
     if hasattr(a, "data_ptr"):  # torch tensor
+        tname = str(a.dtype).replace("torch.", "")
+        if tname != want.name:
+            raise TypeError(f"{name}: expected {want}, got {a.dtype}")
         if not a.is_contiguous():
-            raise ValueError("tensor must be contiguous")
+            raise ValueError(f"{name}: tensor must be contiguous")
+        if count is not None and a.numel() < count:
+            raise ValueError(f"{name}: needs at least {count} elements, got {a.numel()}")
         return a.data_ptr()
-    raise TypeError(type(a))
+    raise TypeError(f"{name}: {type(a)}")
+
+
+def _f(a, count, name):
+    return _ptr(a, np.float64, count, name)
+
+
+def _i(a, count, name):
+    return _ptr(a, np.int32, count, name)
 
 
 class Solver:
@@ -173,40 +214,65 @@ class Solver:
     def version():
         return load_library().noc_version().decode()
 
-    # -- hot path
+    def set_option(self, option, value):
+        self._check(self._lib.noc_set_option(self._h, option, int(value)))
+
+    # -- hot path (every array is checked for dtype and minimum size before its pointer crosses the C-ABI)
     def lqr_solve_batch(self, prob, batch, AB, QRQf, x0dev=None, K=None, K0=None, P0=None, cost=None,
                         status=None, qr_per_instance=False):
-        self._check(self._lib.noc_lqr_solve_batch(self._h, C.byref(prob), batch, _ptr(AB), _ptr(QRQf),
-                                                  int(qr_per_instance), _ptr(x0dev), _ptr(K), _ptr(K0), _ptr(P0),
-                                                  _ptr(cost), _ptr(status)))
+        n, m, N, B = prob.n, prob.m, prob.N, batch
+        qr = 2 * n * n + m * m
+        self._check(self._lib.noc_lqr_solve_batch(
+            self._h, C.byref(prob), batch, _f(AB, B * N * (n * n + n * m), "AB"),
+            _f(QRQf, qr * (B if qr_per_instance else 1), "QRQf"), int(qr_per_instance), _f(x0dev, B * n, "x0dev"),
+            _f(K, B * N * m * n, "K"), _f(K0, B * m * n, "K0"), _f(P0, B * n * n, "P0"), _f(cost, B, "cost"),
+            _i(status, B, "status")))
 
     def linearize_batch(self, prob, batch, xbar, ubar, AB):
-        self._check(self._lib.noc_linearize_batch(self._h, C.byref(prob), batch, _ptr(xbar), _ptr(ubar), _ptr(AB)))
+        n, m, N, B = prob.n, prob.m, prob.N, batch
+        self._check(self._lib.noc_linearize_batch(self._h, C.byref(prob), batch, _f(xbar, B * (N + 1) * n, "xbar"),
+                                                  _f(ubar, B * N * m, "ubar"), _f(AB, B * N * (n * n + n * m), "AB")))
 
     def rollout_open_loop(self, prob, batch, x0, ubar, xbar):
-        self._check(self._lib.noc_rollout_open_loop(self._h, C.byref(prob), batch, _ptr(x0), _ptr(ubar), _ptr(xbar)))
+        n, m, N, B = prob.n, prob.m, prob.N, batch
+        self._check(self._lib.noc_rollout_open_loop(self._h, C.byref(prob), batch, _f(x0, B * n, "x0"),
+                                                    _f(ubar, B * N * m, "ubar"), _f(xbar, B * (N + 1) * n, "xbar")))
 
     def lqr_solve_from_x0(self, prob, batch, x0, QRQf, K=None, K0=None, P0=None, cost=None, status=None):
-        self._check(self._lib.noc_lqr_solve_from_x0(self._h, C.byref(prob), batch, _ptr(x0), _ptr(QRQf), _ptr(K),
-                                                    _ptr(K0), _ptr(P0), _ptr(cost), _ptr(status)))
+        n, m, N, B = prob.n, prob.m, prob.N, batch
+        self._check(self._lib.noc_lqr_solve_from_x0(
+            self._h, C.byref(prob), batch, _f(x0, B * n, "x0"), _f(QRQf, 2 * n * n + m * m, "QRQf"),
+            _f(K, B * N * m * n, "K"), _f(K0, B * m * n, "K0"), _f(P0, B * n * n, "P0"), _f(cost, B, "cost"),
+            _i(status, B, "status")))
 
     def lqr_solve_along(self, prob, batch, x0, ubar, QRQf, xbar=None, K=None, K0=None, P0=None, cost=None, status=None):
-        self._check(self._lib.noc_lqr_solve_along(self._h, C.byref(prob), batch, _ptr(x0), _ptr(ubar), _ptr(QRQf),
-                                                  _ptr(xbar), _ptr(K), _ptr(K0), _ptr(P0), _ptr(cost), _ptr(status)))
+        n, m, N, B = prob.n, prob.m, prob.N, batch
+        self._check(self._lib.noc_lqr_solve_along(
+            self._h, C.byref(prob), batch, _f(x0, B * n, "x0"), _f(ubar, B * N * m, "ubar"),
+            _f(QRQf, 2 * n * n + m * m, "QRQf"), _f(xbar, B * (N + 1) * n, "xbar"), _f(K, B * N * m * n, "K"),
+            _f(K0, B * m * n, "K0"), _f(P0, B * n * n, "P0"), _f(cost, B, "cost"), _i(status, B, "status")))
 
     def dare_solve_batch(self, prob, batch, AB, QR, P, K, iters, status):
-        self._check(self._lib.noc_dare_solve_batch(self._h, C.byref(prob), batch, _ptr(AB), _ptr(QR), _ptr(P),
-                                                   _ptr(K), _ptr(iters), _ptr(status)))
+        n, m, B = prob.n, prob.m, batch
+        self._check(self._lib.noc_dare_solve_batch(
+            self._h, C.byref(prob), batch, _f(AB, B * (n * n + n * m), "AB"), _f(QR, n * n + m * m, "QR"),
+            _f(P, B * n * n, "P"), _f(K, B * m * n, "K"), _i(iters, B, "iters"), _i(status, B, "status")))
 
     def dare_solve_at(self, prob, batch, xbar, ubar, QR, P, K, iters, status):
-        self._check(self._lib.noc_dare_solve_at(self._h, C.byref(prob), batch, _ptr(xbar), _ptr(ubar), _ptr(QR),
-                                                _ptr(P), _ptr(K), _ptr(iters), _ptr(status)))
+        n, m, B = prob.n, prob.m, batch
+        self._check(self._lib.noc_dare_solve_at(
+            self._h, C.byref(prob), batch, _f(xbar, B * n, "xbar"), _f(ubar, B * m, "ubar"),
+            _f(QR, n * n + m * m, "QR"), _f(P, B * n * n, "P"), _f(K, B * m * n, "K"), _i(iters, B, "iters"),
+            _i(status, B, "status")))
 
     def slq_solve_batch(self, prob, batch, x0, xgoal, QRQf, x=None, u=None, K=None, cost=None, iters=None,
                         alpha_idx=None, status=None, u_init=None):
-        self._check(self._lib.noc_slq_solve_warm(self._h, C.byref(prob), batch, _ptr(x0), _ptr(xgoal), _ptr(QRQf),
-                                                 _ptr(u_init), _ptr(x), _ptr(u), _ptr(K), _ptr(cost), _ptr(iters),
-                                                 _ptr(alpha_idx), _ptr(status)))
+        n, m, N, B = prob.n, prob.m, prob.N, batch
+        self._check(self._lib.noc_slq_solve_warm(
+            self._h, C.byref(prob), batch, _f(x0, B * n, "x0"), _f(xgoal, B * n, "xgoal"),
+            _f(QRQf, 2 * n * n + m * m, "QRQf"), _f(u_init, B * N * m, "u_init"), _f(x, B * (N + 1) * n, "x"),
+            _f(u, B * N * m, "u"), _f(K, B * N * m * n, "K"), _f(cost, B, "cost"), _i(iters, B, "iters"),
+            _i(alpha_idx, B * prob.max_iter, "alpha_idx"), _i(status, B, "status")))
 
     def selftest_rcp(self, x):
         x = np.ascontiguousarray(x, dtype=np.float64)
@@ -214,7 +280,77 @@ class Solver:
         self._check(self._lib.noc_selftest_rcp(self._h, _ptr(x), _ptr(fast), _ptr(ieee), x.size))
         return fast, ieee
 
+    def argmin_cost_async(self, cost_dev, batch, best_dev, index_offset=0):
+        """Device-resident pick: best_dev is a 16-byte device buffer (e.g. a 2-element float64 CUDA tensor viewed as
+        {double cost; int64 index}); no host synchronisation."""
+        self._check(self._lib.noc_argmin_cost_async(self._h, _f(cost_dev, batch, "cost"), batch, index_offset,
+                                                    best_dev.data_ptr()))
+
     def argmin_cost(self, cost, batch):
         idx, val = C.c_int64(), C.c_double()
-        self._check(self._lib.noc_argmin_cost(self._h, _ptr(cost), batch, C.byref(idx), C.byref(val)))
+        self._check(self._lib.noc_argmin_cost(self._h, _f(cost, batch, "cost"), batch, C.byref(idx), C.byref(val)))
         return idx.value, val.value
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL id, created on rank 0 and distributed by the launcher (torch.distributed, MPI, a file)."""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    rc = load_library().noc_comm_unique_id(buf)
+    if rc != OK:
+        raise NocError(rc, "noc_comm_unique_id failed (NCCL not loadable?)")
+    return buf.raw
+
+
+class Comm:
+    """One NCCL rank bound to a Solver (noc_comm): the in-library multi-GPU plane — device-resident gathers of costs
+    and gains over NVLink and the cross-GPU "pick the best rollout" (SURVEY.md §8e)."""
+
+    def __init__(self, solver: Solver, unique_id: bytes, rank: int, nranks: int):
+        self._lib = load_library()
+        self.solver = solver
+        h = C.c_void_p()
+        rc = self._lib.noc_comm_create_rank(C.byref(h), solver._h, unique_id, rank, nranks)
+        solver._check(rc)
+        self._h = h
+        self.rank, self.nranks = rank, nranks
+
+    @classmethod
+    def from_torch_distributed(cls, solver: Solver, dist, device):
+        """Rank 0 creates the id, torch.distributed broadcasts its 128 bytes (that is all torch is used for here)."""
+        import torch
+        rank, world = dist.get_rank(), dist.get_world_size()
+        t = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8, device=device)
+        if rank == 0:
+            t.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(t, 0)
+        return cls(solver, bytes(t.cpu().numpy().tobytes()), rank, world)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.noc_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def allgather(self, src_dev, dst_dev, count, elem_bytes=8):
+        self.solver._check(self._lib.noc_comm_allgather(self._h, src_dev.data_ptr(), dst_dev.data_ptr(), count, elem_bytes))
+
+    def best_rollout(self, cost_dev, count, index_offset, best_dev, want_host=False):
+        host = CostIndex() if want_host else None
+        self.solver._check(self._lib.noc_comm_best_rollout(self._h, _f(cost_dev, count, "cost"), count, index_offset,
+                                                           best_dev.data_ptr(), C.byref(host) if want_host else None))
+        return (host.index, host.cost) if want_host else None
+
+    def lqr_solve_from_x0(self, prob, count, x0_dev, qr_dev, best_dev, cost_all=None, K0_all=None, status=None,
+                          want_host=False):
+        n, m = prob.n, prob.m
+        host = CostIndex() if want_host else None
+        self.solver._check(self._lib.noc_comm_lqr_solve_from_x0(
+            self._h, C.byref(prob), count, _f(x0_dev, count * n, "x0"), _f(qr_dev, 2 * n * n + m * m, "QRQf"),
+            _f(cost_all, self.nranks * count, "cost_all"), _f(K0_all, self.nranks * count * m * n, "K0_all"),
+            _i(status, count, "status"), best_dev.data_ptr(), C.byref(host) if want_host else None))
+        return (host.index, host.cost) if want_host else None

@@ -3,13 +3,18 @@
 // There is no CPU fallback anywhere in this file: every entry point either launches CUDA kernels or fails.
 #include "../../include/lqr_control/noc_b200.h"
 
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library is loaded with dlopen at run time
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <type_traits>
+#include <unordered_set>
 #include <vector>
 
 #include "pipeline_kernels.cuh"
@@ -41,6 +46,7 @@ struct noc_ctx {
   cudaStream_t aux_stream = nullptr;    // every other inner chunk of a from-x0 call: neighbouring sweeps overlap at their edges
   cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  cudaEvent_t pipe_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // host-AB pipeline: in / swept / out x 2 buffers
   std::string err;
   int64_t launches = 0;
   int sm_count = 0;
@@ -53,6 +59,10 @@ struct noc_ctx {
   size_t ev_next = 0;
   double prof_ms[NOC_KERNEL_COUNT] = {0};
   int64_t prof_launches[NOC_KERNEL_COUNT] = {0};
+  // scheduler options (noc_set_option)
+  int64_t opt[NOC_OPT_COUNT] = {0};
+  // kernels whose function attributes (dynamic shared memory, carve-out) have been set on this context's device
+  std::unordered_set<const void*> configured;
 };
 
 namespace {
@@ -90,6 +100,27 @@ struct LaunchScope {
   }
   ~LaunchScope() {
     if (stop) cudaEventRecord(stop, c->stream);
+  }
+};
+
+// Every entry point that stages host outputs holds one of these: whatever path the call leaves by (a failed
+// allocation, a CUDA error, an argument check after staging), no host copy-back of THIS call survives into the
+// next one (the caller may free its arrays after an error).  flush_out() empties the list itself on success.
+struct PendingGuard {
+  noc_ctx* c;
+  explicit PendingGuard(noc_ctx* ctx) : c(ctx) { c->pending.clear(); }
+  ~PendingGuard() { c->pending.clear(); }
+};
+
+// Calls that fan work out over the context's auxiliary / copy streams hold one of these: on ANY exit (errors included)
+// the side streams are drained, so no copy into the caller's host arrays is still in flight when the call returns.
+struct SideStreamDrain {
+  noc_ctx* c;
+  bool armed;
+  ~SideStreamDrain() {
+    if (!armed) return;
+    cudaStreamSynchronize(c->aux_stream);
+    cudaStreamSynchronize(c->copy_stream);
   }
 };
 
@@ -138,10 +169,11 @@ int stage_out(noc_ctx* ctx, int slot, void* p, size_t bytes, void** out) {
 }
 
 int flush_out(noc_ctx* ctx, bool async) {
-  for (auto& c : ctx->pending)
+  std::vector<PendingCopy> todo;
+  todo.swap(ctx->pending);   // the list is empty from here on, also when a copy below fails
+  for (auto& c : todo)
     NOC_CUDA(ctx, cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  const bool had_host = !ctx->pending.empty();
-  ctx->pending.clear();
+  const bool had_host = !todo.empty();
   if (!async || had_host) NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NOC_OK;
 }
@@ -155,7 +187,9 @@ int scratch(noc_ctx* ctx, int slot, size_t bytes, void** out) {
 }
 
 enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
-       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC, SCR_FLAGS, SCR_XC, SCR_UC, SCR_LCC };
+       SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC, SCR_FLAGS, SCR_XC, SCR_UC, SCR_LCC,
+       SCR_PIPE_AB0, SCR_PIPE_AB1, SCR_PIPE_X0, SCR_PIPE_X1, SCR_PIPE_QR0, SCR_PIPE_QR1, SCR_PIPE_OUT0,
+       SCR_PIPE_OUT_LAST = SCR_PIPE_OUT0 + 9, SCR_ARGMIN_PART, SCR_COMM_PAIRS, SCR_COMM_COST, SCR_END };
 
 // W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
 // Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
@@ -196,6 +230,19 @@ int check_prob(noc_ctx* ctx, const noc_problem_t* p, int64_t batch) {
   if (p->model == NOC_MODEL_DUAL24 && (p->n != 24 || p->m != 8))
     return fail(ctx, NOC_ERR_BAD_ARG, "NOC_MODEL_DUAL24 requires n=24, m=8");
   if (p->model < 0 || p->model > NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "unknown model");
+  if (p->n < 1 || p->m < 1) return fail(ctx, NOC_ERR_BAD_ARG, "n and m must be >= 1");
+  if (p->n > RG_NMAX || p->m > RG_MMAX)
+    return fail(ctx, NOC_ERR_UNSUPPORTED, "supported dimensions: 1 <= n <= 24, 1 <= m <= 8");
+  return NOC_OK;
+}
+
+// Function attributes are per device; a context is bound to one device, so each kernel is configured once per
+// context (the SLQ loop launches the same instantiations hundreds of times per call).
+int configure_kernel(noc_ctx* ctx, const void* kern, size_t smem, bool carveout) {
+  if (ctx->configured.count(kern)) return NOC_OK;
+  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (carveout) NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  ctx->configured.insert(kern);
   return NOC_OK;
 }
 
@@ -210,10 +257,8 @@ template <int LAYOUT, int MODE, bool FUSED, int W, int MIN_CTAS, bool BOX = fals
 int launch_ric12_cfg(noc_ctx* ctx, const Ric12Args& a) {
   auto kern = k_ric12<LAYOUT, MODE, FUSED, W, MIN_CTAS, BOX>;
   const size_t smem = ric12_smem_bytes<MODE, FUSED>(W);
-  // function attributes are per device and contexts may live on several devices / host threads: set them on every
-  // launch (two cheap driver calls) instead of caching a process-wide flag
-  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int rc = configure_kernel(ctx, (const void*)kern, smem, true);
+  if (rc) return rc;
   const long long per_cta = 8LL * W;
   const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
   {
@@ -228,12 +273,8 @@ template <int LAYOUT, int MODE, bool FUSED = false, bool BOX = false>
 int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
   // short work lists (the tail of an SLQ solve, small batches): one warp per CTA, so that the few warps spread over
   // all SMs instead of sharing a handful — the sweep is then latency-bound and a warp alone on an SM steps ~2x faster
-#if defined(NOC_EXP_MASK)   // experiment build only: one 7/8-warp CTA per SM, warps selected by the mask
-  return launch_ric12_cfg<LAYOUT, MODE, FUSED, (MODE == RIC_AFFINE ? 7 : 8), 1>(ctx, a);
-#else
   if (a.batch <= 8LL * 2 * ctx->sm_count) return launch_ric12_cfg<LAYOUT, MODE, FUSED, 1, 1, BOX>(ctx, a);
   return launch_ric12_cfg<LAYOUT, MODE, FUSED, RicCfg<MODE>::warps, RicCfg<MODE>::min_ctas, BOX>(ctx, a);
-#endif
 }
 
 template <int MODE>
@@ -248,8 +289,8 @@ template <int LAYOUT, int MODE, bool FUSED, int W, bool BOX = false>
 int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a) {
   auto kern = k_ric24<LAYOUT, MODE, FUSED, W, BOX>;
   const size_t smem = ric24_smem_bytes<MODE, FUSED>(W);
-  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+  int rc = configure_kernel(ctx, (const void*)kern, smem, true);
+  if (rc) return rc;
   const long long per_cta = 2LL * W;
   const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
   {
@@ -320,6 +361,104 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   return launch_ric12_layout<RIC_LQR>(ctx, p->layout, a);
 }
 
+// device-pointer core of noc_lqr_solve_batch: tuned kernels for (12,4) / (24,8) with shared weights, the
+// thread-per-instance kernel for everything else
+int lqr_batch_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, bool generic, const double* dAB,
+                     const double* dQ, int qr_per_instance, const double* dx0, double* dK, double* dK0, double* dP0,
+                     double* dcost, int32_t* dstatus) {
+  if (generic) {
+    RicGenArgs g{};
+    g.AB = dAB; g.QRQf = dQ; g.x0 = dx0; g.K = dK; g.K0 = dK0; g.P0 = dP0; g.cost = dcost; g.status = dstatus;
+    g.batch = batch; g.n = p->n; g.m = p->m; g.N = p->N; g.layout = p->layout;
+    g.qr_stride = qr_per_instance ? (long long)(2 * p->n * p->n + p->m * p->m) : 0;
+    {
+      LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+      k_ric_generic<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(g);
+    }
+    return (cudaGetLastError() == cudaSuccess) ? NOC_OK : fail(ctx, NOC_ERR_CUDA, "k_ric_generic launch failed");
+  }
+  return (p->n == 24 ? lqr24_device : lqr12_device)(ctx, p, batch, dAB, dQ, dx0, dK, dK0, dP0, dcost, dstatus);
+}
+
+// Host-resident A_k,B_k (and outputs): two device buffers; chunk c+1 is copied in on the auxiliary stream while
+// chunk c is swept on the caller's stream and chunk c-1's outputs are copied out on the copy stream.  The chunk
+// size is bounded by the scratch budget (NOC_OPT_SCRATCH_LIMIT_BYTES or 60 % of the free HBM), so a stream larger
+// than the GPU's memory is processed instead of failing with NOC_ERR_OOM.  Outputs that are DEVICE pointers are
+// written in place.
+int lqr_batch_host_pipeline(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, bool generic, const double* AB,
+                            const double* QRQf, int qr_per_instance, const double* x0dev, double* K, double* K0,
+                            double* P0, double* cost, int32_t* status) {
+  int rc;
+  const size_t n = p->n, m = p->m, N = p->N, rec = n * n + n * m, B = (size_t)batch;
+  const size_t qr_len = 2 * n * n + m * m;
+  struct Out { void* user; size_t per; bool host; void* dev[2]; };
+  Out outs[5] = {{K, sizeof(double) * N * m * n, false, {nullptr, nullptr}}, {K0, sizeof(double) * m * n, false, {nullptr, nullptr}},
+                 {P0, sizeof(double) * n * n, false, {nullptr, nullptr}}, {cost, sizeof(double), false, {nullptr, nullptr}},
+                 {status, sizeof(int32_t), false, {nullptr, nullptr}}};
+  size_t per_inst = sizeof(double) * N * rec;   // bytes of device scratch per instance and buffer
+  const bool x0_host = x0dev && !is_device_ptr(x0dev), qr_host = !is_device_ptr(QRQf);
+  if (x0_host) per_inst += sizeof(double) * n;
+  if (qr_per_instance && qr_host) per_inst += sizeof(double) * qr_len;
+  for (auto& o : outs) { o.host = o.user && !is_device_ptr(o.user); if (o.host) per_inst += o.per; }
+  size_t free_b = 0, total_b = 0;
+  NOC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  size_t have = 0;
+  for (auto& b : ctx->scratch) have += b.cap;   // regrown below if too small: count what is already ours
+  size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
+  if (ctx->opt[NOC_OPT_SCRATCH_LIMIT_BYTES] > 0) budget = std::max<size_t>((size_t)ctx->opt[NOC_OPT_SCRATCH_LIMIT_BYTES], (size_t)1 << 20);
+  // about eight chunks per call so that the first copy-in and the last copy-out (which nothing hides) stay short
+  size_t chunk = std::min<size_t>(std::max<size_t>(B / 8, 256), std::max<size_t>(1, budget / (2 * per_inst)));
+  chunk = std::min(chunk, B);
+  if (chunk >= 64) chunk &= ~size_t(31);
+  void *dab[2], *dx0c[2] = {nullptr, nullptr}, *dqc[2] = {nullptr, nullptr};
+  for (int s2 = 0; s2 < 2; ++s2) {
+    if ((rc = scratch(ctx, SCR_PIPE_AB0 + s2, sizeof(double) * chunk * N * rec, &dab[s2]))) return rc;
+    if (x0_host && (rc = scratch(ctx, SCR_PIPE_X0 + s2, sizeof(double) * chunk * n, &dx0c[s2]))) return rc;
+    if (qr_per_instance && qr_host && (rc = scratch(ctx, SCR_PIPE_QR0 + s2, sizeof(double) * chunk * qr_len, &dqc[s2]))) return rc;
+    for (int o = 0; o < 5; ++o)
+      if (outs[o].host && (rc = scratch(ctx, SCR_PIPE_OUT0 + 2 * o + s2, outs[o].per * chunk, &outs[o].dev[s2]))) return rc;
+  }
+  const void* dQshared = nullptr;
+  if (!qr_per_instance && (rc = stage_in(ctx, 1, QRQf, sizeof(double) * qr_len, &dQshared))) return rc;
+  cudaStream_t const main_stream = ctx->stream, in_stream = ctx->aux_stream, out_stream = ctx->copy_stream;
+  // the pipeline's events order three streams; whatever happens below, drain them before the buffers can be reused
+  struct Drain { noc_ctx* c; ~Drain() { cudaStreamSynchronize(c->aux_stream); cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); } } drain{ctx};
+  NOC_CUDA(ctx, cudaEventRecord(ctx->fork_ev, main_stream));   // weights staged / earlier work of the caller's stream
+  NOC_CUDA(ctx, cudaStreamWaitEvent(in_stream, ctx->fork_ev, 0));
+  size_t c = 0;
+  for (size_t off = 0; off < B; off += chunk, ++c) {
+    const int s2 = (int)(c & 1);
+    const size_t cb = std::min(chunk, B - off);
+    cudaEvent_t ev_in = ctx->pipe_ev[s2], ev_swept = ctx->pipe_ev[2 + s2], ev_out = ctx->pipe_ev[4 + s2];
+    if (c >= 2) NOC_CUDA(ctx, cudaStreamWaitEvent(in_stream, ev_swept, 0));   // the sweep of chunk c-2 has consumed buffer s2
+    NOC_CUDA(ctx, cudaMemcpyAsync(dab[s2], AB + off * N * rec, sizeof(double) * cb * N * rec, cudaMemcpyHostToDevice, in_stream));
+    if (x0_host) NOC_CUDA(ctx, cudaMemcpyAsync(dx0c[s2], x0dev + off * n, sizeof(double) * cb * n, cudaMemcpyHostToDevice, in_stream));
+    if (dqc[s2]) NOC_CUDA(ctx, cudaMemcpyAsync(dqc[s2], QRQf + off * qr_len, sizeof(double) * cb * qr_len, cudaMemcpyHostToDevice, in_stream));
+    NOC_CUDA(ctx, cudaEventRecord(ev_in, in_stream));
+    NOC_CUDA(ctx, cudaStreamWaitEvent(main_stream, ev_in, 0));
+    if (c >= 2) NOC_CUDA(ctx, cudaStreamWaitEvent(main_stream, ev_out, 0));   // chunk c-2's outputs have left buffer s2
+    auto dst = [&](int o) -> void* {
+      if (!outs[o].user) return nullptr;
+      return outs[o].host ? outs[o].dev[s2] : (void*)((char*)outs[o].user + off * outs[o].per);
+    };
+    const double* dq = qr_per_instance ? (dqc[s2] ? (const double*)dqc[s2] : QRQf + off * qr_len) : (const double*)dQshared;
+    const double* dx = x0dev ? (x0_host ? (const double*)dx0c[s2] : x0dev + off * n) : nullptr;
+    rc = lqr_batch_device(ctx, p, (int64_t)cb, generic, (const double*)dab[s2], dq, qr_per_instance, dx, (double*)dst(0),
+                          (double*)dst(1), (double*)dst(2), (double*)dst(3), (int32_t*)dst(4));
+    if (rc) return rc;
+    NOC_CUDA(ctx, cudaEventRecord(ev_swept, main_stream));
+    NOC_CUDA(ctx, cudaStreamWaitEvent(out_stream, ev_swept, 0));
+    for (auto& o : outs)
+      if (o.host)
+        NOC_CUDA(ctx, cudaMemcpyAsync((char*)o.user + off * o.per, o.dev[s2], cb * o.per, cudaMemcpyDeviceToHost, out_stream));
+    NOC_CUDA(ctx, cudaEventRecord(ev_out, out_stream));
+  }
+  NOC_CUDA(ctx, cudaStreamSynchronize(in_stream));
+  NOC_CUDA(ctx, cudaStreamSynchronize(out_stream));
+  NOC_CUDA(ctx, cudaStreamSynchronize(main_stream));
+  return NOC_OK;
+}
+
 template <int MODEL>
 int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* ubar,
                  const double* QRQf, double* xbar_out, double* K, double* K0, double* P0, double* cost,
@@ -340,6 +479,8 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
   if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
   if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
+  if (misaligned16(dK) || misaligned16(dK0) || misaligned16(dP0))
+    return fail(ctx, NOC_ERR_BAD_ARG, "device K / K0 / P0 must be 16-byte aligned");
   // Both built-in models linearise inside the sweep (k_ric12 / k_ric24 <…, FUSED>): only the nominal trajectory is
   // staged in scratch, no A_k,B_k stream exists.  Batch scheduler: an OUTER chunk bounds the scratch to a share of
   // the free HBM and gets one rollout launch (latency-bound: one launch for everything costs as much as one for a
@@ -350,28 +491,28 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   size_t have = 0;
   if (ctx->scratch.size() > SCR_XBAR) have = ctx->scratch[SCR_XBAR].cap;
   size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
-  if (const char* cap = std::getenv("NOC_B200_SCRATCH_MB"))   // test hook: force several outer chunks
-    budget = std::max<size_t>((size_t)std::atoll(cap) << 20, (size_t)1 << 20);
+  if (ctx->opt[NOC_OPT_SCRATCH_LIMIT_BYTES] > 0)   // caller's cap (tests use it to force several outer chunks)
+    budget = std::max<size_t>((size_t)ctx->opt[NOC_OPT_SCRATCH_LIMIT_BYTES], (size_t)1 << 20);
   const size_t per_inst = sizeof(double) * (N + 1) * n;
   size_t outer = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
   if (outer < B) outer = std::max<size_t>(32, outer & ~size_t(31));
   if (dxout) outer = B;   // the caller's xbar array (instance-major) holds the nominal: no scratch, no outer chunks
   const bool overlap = !ctx->pending.empty() && B >= 8192 && !(p->flags & NOC_FLAG_ASYNC);
+  SideStreamDrain drain{ctx, overlap};
   // inner chunks are whole waves of the sweep kernel (instances resident on all SMs at once: 64 per SM for n=12,
   // 16 for n=24), about eight per call: a chunk that ends mid-wave pays for the full wave, and the smaller the last
   // chunk, the shorter the copy that nothing hides (B = 65536: 4 x 16384 = 8 waves took 2.53 ms of sweeps, 7 chunks
   // of one wave take 2.2 ms)
   const size_t wave = (size_t)ctx->sm_count * (MODEL == 0 ? 64 : 16);
   size_t inner_pref = overlap ? std::max<size_t>(1, (B / wave + 4) / 8) * wave : outer;
-  if (const char* e = std::getenv("NOC_B200_CHUNK_WAVES"))   // experiment hook
-    if (overlap) inner_pref = std::max<size_t>(1, (size_t)std::atoll(e)) * wave;
+  if (overlap && ctx->opt[NOC_OPT_CHUNK_WAVES] > 0) inner_pref = (size_t)ctx->opt[NOC_OPT_CHUNK_WAVES] * wave;
   void* dxbar = nullptr;
   if (!dxout && (rc = scratch(ctx, SCR_XBAR, sizeof(double) * outer * (N + 1) * n, &dxbar))) return rc;
   (void)rec;
   typename std::conditional<MODEL == 0, Ric12Args, Ric24Args>::type fa{};
   if (MODEL == 0) rc = build_w12(ctx, (const double*)dQ, false, &fa.W, &fa.Qf);
   else rc = build_w24(ctx, (const double*)dQ, &fa.W, &fa.Qf);
-  if (rc) { ctx->pending.clear(); return rc; }
+  if (rc) return rc;
   int chunk_no = 0;
   for (size_t o = 0; o < B; o += outer) {
     const size_t ob = std::min(outer, B - o);
@@ -391,7 +532,7 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
     // inner chunks alternate between the caller's stream and an auxiliary one: each is one wave of CTAs, so the
     // next chunk's CTAs move onto the SMs as the previous chunk's retire instead of waiting for its last warp
     cudaStream_t const main_stream = ctx->stream;
-    const bool two_streams = overlap && inner < ob && !std::getenv("NOC_B200_ONE_STREAM");
+    const bool two_streams = overlap && inner < ob && !ctx->opt[NOC_OPT_SINGLE_STREAM];
     if (two_streams) {
       NOC_CUDA(ctx, cudaEventRecord(ctx->fork_ev, main_stream));            // rollout (and the staged inputs) done
       NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
@@ -414,7 +555,7 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
       if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_LQR, true>(ctx, fa);
       else rc = launch_ric24<0, RIC_LQR, true>(ctx, fa);
       ctx->stream = main_stream;
-      if (rc) { ctx->pending.clear(); return rc; }
+      if (rc) return rc;
       if (overlap) {
         cudaEvent_t ev = ctx->chunk_ev[chunk_no & 3];
         NOC_CUDA(ctx, cudaEventRecord(ev, cs));
@@ -441,7 +582,7 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
 }
 
 template <int MODEL>
-int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
+int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
              const double* QRQf, const double* u_init, double* x, double* u, double* K, double* cost, int32_t* iters,
              int32_t* alpha_idx, int32_t* status) {
   int rc;
@@ -486,7 +627,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   NOC_CUDA(ctx, cudaMemsetAsync(dflags, 0, sizeof(int32_t) * B, ctx->stream));
   using FC = FwdCfg<MODEL>;
   const size_t fwd_smem = FC::ring_bytes;
-  NOC_CUDA(ctx, cudaFuncSetAttribute(k_slq_rollout<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem));
+  if ((rc = configure_kernel(ctx, (const void*)k_slq_rollout<MODEL>, fwd_smem, false))) return rc;
   const size_t wbytes = sizeof(double) * (2 * n * n + m * m);
   {
     LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
@@ -498,7 +639,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   typename std::conditional<MODEL == 0, Ric12Args, Ric24Args>::type ra{};
   if (MODEL == 0) rc = build_w12(ctx, (const double*)dQ, false, &ra.W, &ra.Qf);
   else rc = build_w24(ctx, (const double*)dQ, &ra.W, &ra.Qf);
-  if (rc) { ctx->pending.clear(); return rc; }
+  if (rc) return rc;
   const bool boxed = std::isfinite(p->u_min) || std::isfinite(p->u_max);   // input box: control-limited backward pass
   int count = (int)batch;
   int32_t* cur = (int32_t*)didx0;
@@ -518,7 +659,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
       ra.u_min = p->u_min; ra.u_max = p->u_max;
       rc = boxed ? launch_ric24<0, RIC_AFFINE, true, true>(ctx, ra) : launch_ric24<0, RIC_AFFINE, true>(ctx, ra);
     }
-    if (rc) { ctx->pending.clear(); return rc; }
+    if (rc) return rc;
     // a4: closed-loop rollouts with backtracking, acceptance, convergence, next work list.  One launch per step
     // length: trial 0 on the whole list, trial j+1 only on the instances whose trial j was rejected.
     SlqFwdArgs fa{};
@@ -581,7 +722,7 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
             int e1 = scratch(ctx, SCR_XC, sizeof(double) * rc_ * (N + 1) * n, &dxc);
             int e2 = e1 ? e1 : scratch(ctx, SCR_UC, sizeof(double) * rc_ * N * m, &duc);
             int e3 = e2 ? e2 : scratch(ctx, SCR_LCC, sizeof(double) * rc_ * (N + 1), &dlcc);
-            if (e3) { ctx->pending.clear(); return e3; }
+            if (e3) return e3;
             fa.idx = list; fa.trial = first; fa.cand_J = Jr; fa.cand_first = first; fa.cand_last = (first + Jr >= p->n_alpha);
             fa.xc = (double*)dxc; fa.uc = (double*)duc; fa.lcc = (double*)dlcc;
             fa.count = (int)rc_;
@@ -632,6 +773,76 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
   return flush_out(ctx, false);
 }
 
+// Device-resident from-x0 solve in wave-sized chunks with a callback after each chunk's sweep (the multi-GPU plane
+// hangs its NVLink gathers there).  One rollout launch for the slice; `chunked` = false sweeps it in one launch.
+template <int MODEL, class AfterChunk>
+int from_x0_device_chunks(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* dx0, const double* dQ,
+                          double* dK0, double* dcost, int32_t* dstatus, bool chunked, AfterChunk&& after_chunk) {
+  int rc;
+  const size_t B = (size_t)batch, n = model::Dims<MODEL>::n, N = p->N;
+  void* dxbar = nullptr;
+  if ((rc = scratch(ctx, SCR_XBAR, sizeof(double) * B * (N + 1) * n, &dxbar))) return rc;
+  typename std::conditional<MODEL == 0, Ric12Args, Ric24Args>::type fa{};
+  if (MODEL == 0) rc = build_w12(ctx, dQ, false, &fa.W, &fa.Qf);
+  else rc = build_w24(ctx, dQ, &fa.W, &fa.Qf);
+  if (rc) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
+    k_rollout_open_loop<MODEL><<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(dx0, nullptr, (double*)dxbar, (long long)B, p->N, p->dt,
+                                                                                     (long long)n, (long long)(B * n));
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  const size_t wave = (size_t)ctx->sm_count * (MODEL == 0 ? 64 : 16);
+  const size_t inner = chunked ? std::max<size_t>(1, (B / wave + 4) / 8) * wave : B;
+  int chunk_no = 0;
+  for (size_t off = 0; off < B; off += inner, ++chunk_no) {
+    const size_t cb = std::min(inner, B - off);
+    fa.xbar = (const double*)dxbar + off * n; fa.xbar_sb = (long long)n; fa.xbar_sk = (long long)(B * n);
+    fa.ubar = nullptr; fa.dt = p->dt;
+    fa.x0 = dx0 + off * n;
+    fa.K = nullptr;
+    fa.K0 = dK0 ? dK0 + off * model::Dims<MODEL>::m * n : nullptr;
+    fa.P0 = nullptr;
+    fa.cost = dcost ? dcost + off : nullptr;
+    fa.status = dstatus ? dstatus + off : nullptr;
+    fa.batch = (long long)cb; fa.N = p->N;
+    if constexpr (MODEL == 0) rc = launch_ric12<0, RIC_LQR, true>(ctx, fa);
+    else rc = launch_ric24<0, RIC_LQR, true>(ctx, fa);
+    if (rc) return rc;
+    if ((rc = after_chunk(off, cb, chunk_no))) return rc;
+  }
+  return NOC_OK;
+}
+
+// Outer chunks of an SLQ call: the solver's working set (trajectories, gains, the saved nominal, stage costs) is
+// ~136 KB per instance at n=12, N=200, so a batch that would not fit the scratch budget is solved slice by slice.
+template <int MODEL>
+int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* xgoal,
+             const double* QRQf, const double* u_init, double* x, double* u, double* K, double* cost, int32_t* iters,
+             int32_t* alpha_idx, int32_t* status) {
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, N = p->N, B = (size_t)batch;
+  const size_t per_inst = sizeof(double) * (2 * (N + 1) * n + 3 * N * m + N * m * n + (N + 1) + 8) + 4 * (size_t)(8 + p->max_iter);
+  size_t free_b = 0, total_b = 0, have = 0;
+  NOC_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+  for (auto* v : {&ctx->scratch, &ctx->out_slots, &ctx->in_slots})
+    for (auto& b : *v) have += b.cap;
+  size_t budget = std::max<size_t>((size_t)((free_b + have) * 0.6), (size_t)64 << 20);
+  if (ctx->opt[NOC_OPT_SCRATCH_LIMIT_BYTES] > 0) budget = std::max<size_t>((size_t)ctx->opt[NOC_OPT_SCRATCH_LIMIT_BYTES], (size_t)1 << 20);
+  size_t outer = std::max<size_t>(1, std::min<size_t>(B, budget / per_inst));
+  if (outer < B && outer >= 64) outer &= ~size_t(31);
+  for (size_t o = 0; o < B; o += outer) {
+    const size_t ob = std::min(outer, B - o);
+    ctx->pending.clear();
+    int rc = slq_chunk<MODEL>(ctx, p, (int64_t)ob, x0 + o * n, xgoal + o * n, QRQf, u_init ? u_init + o * N * m : nullptr,
+                              x ? x + o * (N + 1) * n : nullptr, u ? u + o * N * m : nullptr, K ? K + o * N * m * n : nullptr,
+                              cost ? cost + o : nullptr, iters ? iters + o : nullptr,
+                              alpha_idx ? alpha_idx + o * (size_t)p->max_iter : nullptr, status ? status + o : nullptr);
+    if (rc) return rc;
+  }
+  return NOC_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -665,19 +876,25 @@ int noc_create(noc_ctx** out, int device_id) {
   if (device_id < 0 || device_id >= count) return NOC_ERR_BAD_ARG;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess) return NOC_ERR_CUDA;
-  if (prop.major != 10) return NOC_ERR_NO_DEVICE;  // sm_100a cubins only
+  // the library carries an sm_100a cubin only (arch-specific, no PTX): exactly compute capability 10.0
+  if (prop.major != 10 || prop.minor != 0) return NOC_ERR_NO_DEVICE;
   if (cudaSetDevice(device_id) != cudaSuccess) return NOC_ERR_CUDA;
   noc_ctx* c = new noc_ctx();
   c->device = device_id;
   c->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
-  if (cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
-  for (auto& e : c->chunk_ev)
-    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
-  if (cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) != cudaSuccess) { delete c; return NOC_ERR_CUDA; }
+  bool ok = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
   c->stream = c->own_stream;
+  ok = ok && cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (auto& e : c->chunk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) == cudaSuccess;
+  for (auto& e : c->pipe_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {   // noc_destroy releases whatever was created (every handle starts as nullptr)
+    cudaGetLastError();
+    noc_destroy(c);
+    return NOC_ERR_CUDA;
+  }
   *out = c;
   return NOC_OK;
 }
@@ -685,12 +902,14 @@ int noc_create(noc_ctx** out, int device_id) {
 void noc_destroy(noc_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   for (auto* v : {&ctx->in_slots, &ctx->out_slots, &ctx->scratch})
     for (auto& b : *v)
       if (b.p) cudaFree(b.p);
   for (auto& e : ctx->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
   for (auto& e : ctx->chunk_ev)
+    if (e) cudaEventDestroy(e);
+  for (auto& e : ctx->pipe_ev)
     if (e) cudaEventDestroy(e);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
@@ -708,6 +927,14 @@ int noc_set_stream(noc_ctx* ctx, void* cuda_stream) {
   return NOC_OK;
 }
 
+int noc_set_option(noc_ctx* ctx, int option, int64_t value) {
+  if (!ctx) return NOC_ERR_BAD_ARG;
+  if (option < 0 || option >= NOC_OPT_COUNT) return fail(ctx, NOC_ERR_BAD_ARG, "unknown option");
+  if (value < 0) return fail(ctx, NOC_ERR_BAD_ARG, "option values are >= 0");
+  ctx->opt[option] = value;
+  return NOC_OK;
+}
+
 int noc_synchronize(noc_ctx* ctx) {
   if (!ctx) return NOC_ERR_BAD_ARG;
   NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -715,6 +942,33 @@ int noc_synchronize(noc_ctx* ctx) {
 }
 
 int64_t noc_launch_count(const noc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int noc_device_alloc(noc_ctx* ctx, uint64_t bytes, void** out) {
+  if (!ctx || !out) return NOC_ERR_BAD_ARG;
+  *out = nullptr;
+  if (bytes == 0) return NOC_OK;
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  NOC_CUDA(ctx, cudaMalloc(out, (size_t)bytes));
+  return NOC_OK;
+}
+
+int noc_device_free(noc_ctx* ctx, void* p) {
+  if (!ctx) return NOC_ERR_BAD_ARG;
+  if (!p) return NOC_OK;
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  NOC_CUDA(ctx, cudaFree(p));
+  return NOC_OK;
+}
+
+int noc_memcpy(noc_ctx* ctx, void* dst, const void* src, uint64_t bytes) {
+  if (!ctx) return NOC_ERR_BAD_ARG;
+  if (bytes == 0) return NOC_OK;
+  if (!dst || !src) return fail(ctx, NOC_ERR_BAD_ARG, "noc_memcpy: NULL pointer");
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  NOC_CUDA(ctx, cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, ctx->stream));
+  return NOC_OK;
+}
 
 int noc_profile_enable(noc_ctx* ctx, int on) {
   if (!ctx) return NOC_ERR_BAD_ARG;
@@ -758,6 +1012,7 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
                         int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
+  PendingGuard pending_guard(ctx);
   if (!AB || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "AB and QRQf are required");
   if (batch == 0) return NOC_OK;
   // per-instance weights run on the thread-per-instance kernel whatever the shape: the tuned kernels keep one W / Qf
@@ -770,6 +1025,10 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const int n = p->n, m = p->m, N = p->N;
   const size_t rec = (size_t)n * n + (size_t)n * m, B = (size_t)batch;
+  // A host-resident A_k,B_k stream is the largest thing this library ever stages (12.6 GB at config 2): it goes
+  // through a two-buffer pipeline bounded to the scratch budget instead of one monolithic copy
+  if (!is_device_ptr(AB) && sizeof(double) * B * N * rec > ((size_t)32 << 20) && !(p->flags & NOC_FLAG_ASYNC))
+    return lqr_batch_host_pipeline(ctx, p, batch, generic, AB, QRQf, qr_per_instance, x0dev, K, K0, P0, cost, status);
   const void *dAB, *dQ, *dx0;
   void *dK, *dK0, *dP0, *dcost, *dstatus;
   if ((rc = stage_in(ctx, 0, AB, sizeof(double) * B * N * rec, &dAB))) return rc;
@@ -781,22 +1040,9 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
   if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
   if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
-  if (generic) {
-    RicGenArgs g{};
-    g.AB = (const double*)dAB; g.QRQf = (const double*)dQ; g.x0 = (const double*)dx0; g.K = (double*)dK;
-    g.K0 = (double*)dK0; g.P0 = (double*)dP0; g.cost = (double*)dcost; g.status = (int32_t*)dstatus;
-    g.batch = batch; g.n = n; g.m = m; g.N = N; g.layout = p->layout;
-    g.qr_stride = qr_per_instance ? (long long)(2 * n * n + m * m) : 0;
-    {
-      LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
-      k_ric_generic<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->stream>>>(g);
-    }
-    rc = (cudaGetLastError() == cudaSuccess) ? NOC_OK : fail(ctx, NOC_ERR_CUDA, "k_ric_generic launch failed");
-  } else {
-    rc = (n24 ? lqr24_device : lqr12_device)(ctx, p, batch, (const double*)dAB, (const double*)dQ, (const double*)dx0,
-                                             (double*)dK, (double*)dK0, (double*)dP0, (double*)dcost, (int32_t*)dstatus);
-  }
-  if (rc) { ctx->pending.clear(); return rc; }
+  rc = lqr_batch_device(ctx, p, batch, generic, (const double*)dAB, (const double*)dQ, qr_per_instance, (const double*)dx0,
+                        (double*)dK, (double*)dK0, (double*)dP0, (double*)dcost, (int32_t*)dstatus);
+  if (rc) return rc;
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
 
@@ -804,6 +1050,7 @@ int noc_rollout_open_loop(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
                           double* xbar) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
+  PendingGuard pending_guard(ctx);
   if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "rollout needs a built-in model");
   if (!x0 || !xbar) return fail(ctx, NOC_ERR_BAD_ARG, "x0 and xbar are required");
   if (batch == 0) return NOC_OK;
@@ -832,6 +1079,7 @@ int noc_linearize_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
                         double* AB) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
+  PendingGuard pending_guard(ctx);
   if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "linearisation needs a built-in model");
   if (!xbar || !AB) return fail(ctx, NOC_ERR_BAD_ARG, "xbar and AB are required");
   if (batch == 0) return NOC_OK;
@@ -859,6 +1107,7 @@ int noc_lqr_solve_from_x0(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
                           double* K, double* K0, double* P0, double* cost, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
+  PendingGuard pending_guard(ctx);
   if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "from_x0 pipeline needs a built-in model");
   if (!x0 || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0 and QRQf are required");
   if (batch == 0) return NOC_OK;
@@ -871,6 +1120,7 @@ int noc_lqr_solve_along(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
                         int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
+  PendingGuard pending_guard(ctx);
   if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "noc_lqr_solve_along needs a built-in model");
   if (!x0 || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0 and QRQf are required");
   if (batch == 0) return NOC_OK;
@@ -882,6 +1132,7 @@ int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, co
                          double* P, double* K, int32_t* iters, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
+  PendingGuard pending_guard(ctx);
   if (!AB || !QR) return fail(ctx, NOC_ERR_BAD_ARG, "AB and QR are required");
   if (p->max_iter < 1) return fail(ctx, NOC_ERR_BAD_ARG, "max_iter must be >= 1");
   if (batch == 0) return NOC_OK;
@@ -911,11 +1162,11 @@ int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, co
     return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
   }
   Ric12Args a{};
-  if ((rc = build_w12(ctx, (const double*)dQ, true, &a.W, &a.Qf))) { ctx->pending.clear(); return rc; }
+  if ((rc = build_w12(ctx, (const double*)dQ, true, &a.W, &a.Qf))) return rc;
   a.AB = (const double*)dAB; a.K = (double*)dK; a.P0 = (double*)dP; a.iters = (int32_t*)dit; a.status = (int32_t*)dst;
   a.tol = p->tol; a.max_iter = p->max_iter; a.batch = batch; a.N = 1;
   rc = launch_ric12_layout<RIC_DARE>(ctx, p->layout, a);
-  if (rc) { ctx->pending.clear(); return rc; }
+  if (rc) return rc;
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
 
@@ -923,6 +1174,7 @@ int noc_dare_solve_at(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const
                       const double* QR, double* P, double* K, int32_t* iters, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
+  PendingGuard pending_guard(ctx);
   if (!xbar || !QR) return fail(ctx, NOC_ERR_BAD_ARG, "xbar and QR are required");
   if (p->max_iter < 1) return fail(ctx, NOC_ERR_BAD_ARG, "max_iter must be >= 1");
   if (p->model != NOC_MODEL_QUAD12) return fail(ctx, NOC_ERR_UNSUPPORTED, "noc_dare_solve_at: NOC_MODEL_QUAD12 only");
@@ -940,12 +1192,12 @@ int noc_dare_solve_at(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const
   if ((rc = stage_out(ctx, 2, iters, sizeof(int32_t) * B, &dit))) return rc;
   if ((rc = stage_out(ctx, 3, status, sizeof(int32_t) * B, &dst))) return rc;
   Ric12Args a{};
-  if ((rc = build_w12(ctx, (const double*)dQ, true, &a.W, &a.Qf))) { ctx->pending.clear(); return rc; }
+  if ((rc = build_w12(ctx, (const double*)dQ, true, &a.W, &a.Qf))) return rc;
   a.xbar = (const double*)dxb; a.xbar_sb = 12; a.xbar_sk = 12; a.ubar = (const double*)dub; a.dt = p->dt;
   a.K = (double*)dK; a.P0 = (double*)dP; a.iters = (int32_t*)dit; a.status = (int32_t*)dst;
   a.tol = p->tol; a.max_iter = p->max_iter; a.batch = batch; a.N = 1;
   rc = launch_ric12<0, RIC_DARE, true>(ctx, a);
-  if (rc) { ctx->pending.clear(); return rc; }
+  if (rc) return rc;
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
 
@@ -960,6 +1212,7 @@ int noc_slq_solve_warm(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, cons
                        int32_t* iters, int32_t* alpha_idx, int32_t* status) {
   int rc = check_prob(ctx, p, batch);
   if (rc) return rc;
+  PendingGuard pending_guard(ctx);
   if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "SLQ needs a built-in nonlinear model");
   if (!x0 || !xgoal || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "x0, xgoal and QRQf are required");
   if (p->max_iter < 1 || p->n_alpha < 1 || p->n_alpha > 32)
@@ -975,6 +1228,7 @@ int noc_slq_solve_warm(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, cons
 int noc_selftest_rcp(noc_ctx* ctx, const double* x, double* y_fast, double* y_ieee, int64_t n) {
   if (!ctx) return NOC_ERR_BAD_ARG;
   if (!x || !y_fast || !y_ieee || n < 1) return fail(ctx, NOC_ERR_BAD_ARG, "x, outputs and n>=1 required");
+  PendingGuard pending_guard(ctx);
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const void* dx;
   void *df, *di;
@@ -990,27 +1244,292 @@ int noc_selftest_rcp(noc_ctx* ctx, const double* x, double* y_fast, double* y_ie
   return flush_out(ctx, false);
 }
 
+// local pick: multi-CTA reduction, result {cost, index + index_offset} left at best_dev (device)
+static int argmin_device(noc_ctx* ctx, const double* dcost, int64_t batch, int64_t index_offset, CostIndex* best_dev) {
+  void* part;
+  int rc;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((batch + 4095) / 4096, 2 * (int64_t)ctx->sm_count));
+  // partial pairs | ticket (zeroed once at allocation; the kernel's last CTA resets it)
+  const size_t need = sizeof(CostIndex) * 2 * (size_t)ctx->sm_count + 16;
+  const bool fresh = (int)ctx->scratch.size() <= SCR_ARGMIN_PART || ctx->scratch[SCR_ARGMIN_PART].cap < need;
+  if ((rc = scratch(ctx, SCR_ARGMIN_PART, need, &part))) return rc;
+  unsigned* ticket = (unsigned*)((char*)part + sizeof(CostIndex) * 2 * (size_t)ctx->sm_count);
+  if (fresh) NOC_CUDA(ctx, cudaMemsetAsync(ticket, 0, 16, ctx->stream));
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_ARGMIN);
+    k_argmin_cost<<<grid, 1024, 0, ctx->stream>>>(dcost, batch, index_offset, (CostIndex*)part, ticket, best_dev);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  return NOC_OK;
+}
+
+int noc_argmin_cost_async(noc_ctx* ctx, const double* cost_dev, int64_t batch, int64_t index_offset,
+                          noc_cost_index_t* best_dev) {
+  if (!ctx) return NOC_ERR_BAD_ARG;
+  if (!cost_dev || !best_dev || batch < 1) return fail(ctx, NOC_ERR_BAD_ARG, "cost, best_dev and batch>=1 required");
+  if (!is_device_ptr(cost_dev) || !is_device_ptr(best_dev)) return fail(ctx, NOC_ERR_BAD_ARG, "noc_argmin_cost_async: device pointers only");
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  return argmin_device(ctx, cost_dev, batch, index_offset, (CostIndex*)best_dev);
+}
+
 int noc_argmin_cost(noc_ctx* ctx, const double* cost, int64_t batch, int64_t* best_index, double* best_cost) {
   if (!ctx) return NOC_ERR_BAD_ARG;
   if (!cost || !best_index || !best_cost || batch < 1) return fail(ctx, NOC_ERR_BAD_ARG, "cost, outputs and batch>=1 required");
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  PendingGuard pending_guard(ctx);
   const void* dc;
   int rc;
   if ((rc = stage_in(ctx, 0, cost, sizeof(double) * (size_t)batch, &dc))) return rc;
   void* s;
-  if ((rc = scratch(ctx, SCR_ARGMIN, 16, &s))) return rc;
+  if ((rc = scratch(ctx, SCR_ARGMIN, sizeof(CostIndex), &s))) return rc;
+  if ((rc = argmin_device(ctx, (const double*)dc, batch, 0, (CostIndex*)s))) return rc;
+  CostIndex h;
+  NOC_CUDA(ctx, cudaMemcpyAsync(&h, s, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *best_index = h.index;
+  *best_cost = h.cost;
+  return NOC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Multi-GPU plane: NCCL over NVLink, loaded at run time.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi;
+NcclApi* nccl_api();
+std::string nccl_api_error();
+struct NcclApi {
+  void* handle = nullptr;
+  std::string err;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommInitAll) CommInitAll = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclBroadcast) Broadcast = nullptr;
+  decltype(&ncclGroupStart) GroupStart = nullptr;
+  decltype(&ncclGroupEnd) GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+};
+
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    // inside a PyTorch process this returns torch's already-loaded libnccl.so.2 (same soname); otherwise the system's
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) { api.err = std::string("dlopen libnccl.so.2: ") + dlerror(); return; }
+    bool ok = true;
+    auto sym = [&](const char* name) { void* p = dlsym(api.handle, name); if (!p) { ok = false; api.err = std::string("missing NCCL symbol ") + name; } return p; };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) { dlclose(api.handle); api.handle = nullptr; }
+  });
+  return api.handle ? &api : nullptr;
+}
+std::string nccl_api_error() {
+  // nccl_api() keeps the failure text of its one dlopen attempt in the static object; fetch it through a second handle
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (h) { dlclose(h); return "libnccl.so.2 is loaded but lacks a required symbol"; }
+  return "libnccl.so.2 not found by the dynamic loader";
+}
+}  // namespace
+
+struct noc_comm {
+  noc_ctx* ctx = nullptr;
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  std::string err;
+};
+
+#define NOC_NCCL(cm, call)                                                                    \
+  do {                                                                                        \
+    ncclResult_t r_ = (call);                                                                 \
+    if (r_ != ncclSuccess) {                                                                  \
+      (cm)->err = std::string(#call) + ": " + nccl_api()->GetErrorString(r_);                 \
+      (cm)->ctx->err = (cm)->err;                                                             \
+      return NOC_ERR_NCCL;                                                                    \
+    }                                                                                         \
+  } while (0)
+
+int noc_comm_unique_id(void* id128) {
+  static_assert(sizeof(ncclUniqueId) == NOC_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  NcclApi* api = nccl_api();
+  if (!api || !id128) return api ? NOC_ERR_BAD_ARG : NOC_ERR_NCCL;
+  ncclUniqueId id;
+  if (api->GetUniqueId(&id) != ncclSuccess) return NOC_ERR_NCCL;
+  std::memcpy(id128, &id, sizeof(id));
+  return NOC_OK;
+}
+
+int noc_comm_create_rank(noc_comm** out, noc_ctx* ctx, const void* id128, int rank, int nranks) {
+  if (!out || !ctx) return NOC_ERR_BAD_ARG;
+  *out = nullptr;
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, NOC_ERR_BAD_ARG, "noc_comm_create_rank: id, 0 <= rank < nranks");
+  NcclApi* api = nccl_api();
+  if (!api) return fail(ctx, NOC_ERR_NCCL, "NCCL is not available: " + nccl_api_error());
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  noc_comm* c = new noc_comm();
+  c->ctx = ctx; c->rank = rank; c->nranks = nranks;
+  ncclResult_t r = api->CommInitRank(&c->comm, nranks, id, rank);
+  if (r != ncclSuccess) {
+    ctx->err = std::string("ncclCommInitRank: ") + api->GetErrorString(r);
+    delete c;
+    return NOC_ERR_NCCL;
+  }
+  *out = c;
+  return NOC_OK;
+}
+
+int noc_comm_create_all(noc_comm** out, noc_ctx* const* ctxs, int n) {
+  if (!out || !ctxs || n < 1) return NOC_ERR_BAD_ARG;
+  for (int i = 0; i < n; ++i) { out[i] = nullptr; if (!ctxs[i]) return NOC_ERR_BAD_ARG; }
+  NcclApi* api = nccl_api();
+  if (!api) return fail(ctxs[0], NOC_ERR_NCCL, "NCCL is not available: " + nccl_api_error());
+  std::vector<int> devs(n);
+  std::vector<ncclComm_t> comms(n);
+  for (int i = 0; i < n; ++i) devs[i] = ctxs[i]->device;
+  ncclResult_t r = api->CommInitAll(comms.data(), n, devs.data());
+  if (r != ncclSuccess) return fail(ctxs[0], NOC_ERR_NCCL, std::string("ncclCommInitAll: ") + api->GetErrorString(r));
+  for (int i = 0; i < n; ++i) {
+    noc_comm* c = new noc_comm();
+    c->ctx = ctxs[i]; c->comm = comms[i]; c->rank = i; c->nranks = n;
+    out[i] = c;
+  }
+  return NOC_OK;
+}
+
+void noc_comm_destroy(noc_comm* comm) {
+  if (!comm) return;
+  if (comm->comm && nccl_api()) {
+    cudaSetDevice(comm->ctx->device);
+    cudaStreamSynchronize(comm->ctx->stream);
+    cudaStreamSynchronize(comm->ctx->aux_stream);
+    nccl_api()->CommDestroy(comm->comm);
+  }
+  delete comm;
+}
+
+int noc_comm_rank(const noc_comm* comm) { return comm ? comm->rank : -1; }
+int noc_comm_size(const noc_comm* comm) { return comm ? comm->nranks : 0; }
+const char* noc_comm_last_error(const noc_comm* comm) { return comm ? comm->err.c_str() : "null comm"; }
+int noc_comm_group_begin(void) { return (nccl_api() && nccl_api()->GroupStart() == ncclSuccess) ? NOC_OK : NOC_ERR_NCCL; }
+int noc_comm_group_end(void) { return (nccl_api() && nccl_api()->GroupEnd() == ncclSuccess) ? NOC_OK : NOC_ERR_NCCL; }
+
+int noc_comm_allgather(noc_comm* comm, const void* src_dev, void* dst_dev, int64_t count, int64_t elem_bytes) {
+  if (!comm) return NOC_ERR_BAD_ARG;
+  noc_ctx* ctx = comm->ctx;
+  if (!src_dev || !dst_dev || count < 0 || elem_bytes < 1) return fail(ctx, NOC_ERR_BAD_ARG, "noc_comm_allgather: src, dst, count >= 0, elem_bytes >= 1");
+  if (count == 0) return NOC_OK;
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  NOC_NCCL(comm, nccl_api()->AllGather(src_dev, dst_dev, (size_t)(count * elem_bytes), ncclUint8, comm->comm, ctx->stream));
+  ctx->launches++;
+  return NOC_OK;
+}
+
+// pairs of all ranks -> final pick, on the context's stream
+static int best_from_local(noc_comm* comm, const CostIndex* local_dev, noc_cost_index_t* best_dev, noc_cost_index_t* best_host) {
+  noc_ctx* ctx = comm->ctx;
+  void* pairs;
+  int rc;
+  if ((rc = scratch(ctx, SCR_COMM_PAIRS, sizeof(CostIndex) * (size_t)(comm->nranks + 1), &pairs))) return rc;
+  NOC_NCCL(comm, nccl_api()->AllGather(local_dev, pairs, sizeof(CostIndex), ncclUint8, comm->comm, ctx->stream));
+  ctx->launches++;
   {
     LaunchScope ls(ctx, NOC_KERNEL_ARGMIN);
-    k_argmin_cost<<<1, 1024, 0, ctx->stream>>>((const double*)dc, batch, (long long*)s, (double*)s + 1);
+    k_argmin_pairs<<<1, 32, 0, ctx->stream>>>((const CostIndex*)pairs, comm->nranks, (CostIndex*)best_dev);
   }
   NOC_CUDA(ctx, cudaGetLastError());
-  long long hi;
-  double hv;
-  NOC_CUDA(ctx, cudaMemcpyAsync(&hi, s, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NOC_CUDA(ctx, cudaMemcpyAsync(&hv, (double*)s + 1, 8, cudaMemcpyDeviceToHost, ctx->stream));
-  NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  *best_index = hi;
-  *best_cost = hv;
+  if (best_host) {
+    NOC_CUDA(ctx, cudaMemcpyAsync(best_host, best_dev, sizeof(CostIndex), cudaMemcpyDeviceToHost, ctx->stream));
+    NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return NOC_OK;
+}
+
+int noc_comm_best_rollout(noc_comm* comm, const double* cost_dev, int64_t count, int64_t index_offset,
+                          noc_cost_index_t* best_dev, noc_cost_index_t* best_host) {
+  if (!comm) return NOC_ERR_BAD_ARG;
+  noc_ctx* ctx = comm->ctx;
+  if (!cost_dev || !best_dev || count < 1) return fail(ctx, NOC_ERR_BAD_ARG, "noc_comm_best_rollout: cost, best_dev, count >= 1");
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* pairs;
+  int rc;
+  if ((rc = scratch(ctx, SCR_COMM_PAIRS, sizeof(CostIndex) * (size_t)(comm->nranks + 1), &pairs))) return rc;
+  CostIndex* local = (CostIndex*)pairs + comm->nranks;   // own pair, after the gathered ones
+  if ((rc = argmin_device(ctx, cost_dev, count, index_offset, local))) return rc;
+  return best_from_local(comm, local, best_dev, best_host);
+}
+
+int noc_comm_lqr_solve_from_x0(noc_comm* comm, const noc_problem_t* p, int64_t count, const double* x0_dev,
+                               const double* QRQf_dev, double* cost_all_dev, double* K0_all_dev, int32_t* status_dev,
+                               noc_cost_index_t* best_dev, noc_cost_index_t* best_host) {
+  if (!comm) return NOC_ERR_BAD_ARG;
+  noc_ctx* ctx = comm->ctx;
+  int rc = check_prob(ctx, p, count);
+  if (rc) return rc;
+  if (p->model == NOC_MODEL_LTV_USER) return fail(ctx, NOC_ERR_BAD_ARG, "noc_comm_lqr_solve_from_x0 needs a built-in model");
+  if (!x0_dev || !QRQf_dev || !best_dev || count < 1) return fail(ctx, NOC_ERR_BAD_ARG, "x0, QRQf, best_dev and count >= 1 are required");
+  for (const void* q : {(const void*)x0_dev, (const void*)QRQf_dev, (const void*)best_dev})
+    if (!is_device_ptr(q)) return fail(ctx, NOC_ERR_BAD_ARG, "noc_comm_lqr_solve_from_x0: device pointers only");
+  PendingGuard pending_guard(ctx);
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t n = p->n, m = p->m;
+  const int G = comm->nranks, me = comm->rank;
+  double* cost_local;
+  if (cost_all_dev) cost_local = cost_all_dev + (size_t)me * count;
+  else { void* q; if ((rc = scratch(ctx, SCR_COMM_COST, sizeof(double) * (size_t)count, &q))) return rc; cost_local = (double*)q; }
+  double* K0_local = K0_all_dev ? K0_all_dev + (size_t)me * count * m * n : nullptr;
+  const bool gather = G > 1 && (cost_all_dev || K0_all_dev);
+  SideStreamDrain drain{ctx, gather};
+  cudaStream_t const gstream = ctx->aux_stream;
+  // after every swept chunk: its cost / K0 slices go to every rank (a broadcast per root, grouped: an all-gather with a
+  // strided destination) on the gather stream, under the sweep of the next chunk
+  auto after_chunk = [&](size_t off, size_t cb, int chunk_no) -> int {
+    if (!gather) return NOC_OK;
+    cudaEvent_t ev = ctx->chunk_ev[chunk_no & 3];
+    NOC_CUDA(ctx, cudaEventRecord(ev, ctx->stream));
+    NOC_CUDA(ctx, cudaStreamWaitEvent(gstream, ev, 0));
+    NcclApi* api = nccl_api();
+    NOC_NCCL(comm, api->GroupStart());
+    for (int r = 0; r < G; ++r) {
+      if (cost_all_dev) {
+        double* q = cost_all_dev + (size_t)r * count + off;
+        NOC_NCCL(comm, api->Broadcast(q, q, cb, ncclFloat64, r, comm->comm, gstream));
+      }
+      if (K0_all_dev) {
+        double* q = K0_all_dev + ((size_t)r * count + off) * m * n;
+        NOC_NCCL(comm, api->Broadcast(q, q, cb * m * n, ncclFloat64, r, comm->comm, gstream));
+      }
+    }
+    NOC_NCCL(comm, api->GroupEnd());
+    ctx->launches++;
+    return NOC_OK;
+  };
+  rc = p->model == NOC_MODEL_QUAD12
+           ? from_x0_device_chunks<0>(ctx, p, count, x0_dev, QRQf_dev, K0_local, cost_local, status_dev, gather, after_chunk)
+           : from_x0_device_chunks<1>(ctx, p, count, x0_dev, QRQf_dev, K0_local, cost_local, status_dev, gather, after_chunk);
+  if (rc) return rc;
+  if (gather) {
+    NOC_CUDA(ctx, cudaEventRecord(ctx->join_ev, gstream));
+    NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
+  }
+  void* pairs;
+  if ((rc = scratch(ctx, SCR_COMM_PAIRS, sizeof(CostIndex) * (size_t)(G + 1), &pairs))) return rc;
+  CostIndex* local = (CostIndex*)pairs + G;
+  if ((rc = argmin_device(ctx, cost_local, count, (int64_t)me * count, local))) return rc;
+  if ((rc = best_from_local(comm, local, best_dev, best_host))) return rc;
+  if (!(p->flags & NOC_FLAG_ASYNC) && !best_host) NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NOC_OK;
 }
 

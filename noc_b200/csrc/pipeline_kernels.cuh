@@ -115,34 +115,89 @@ __global__ void __launch_bounds__(128) k_linearize(const double* __restrict__ xb
   }
 }
 
-// Single-CTA argmin over finite costs (NaN = failed instance, skipped).  Ties -> smallest index.
-__global__ void __launch_bounds__(1024) k_argmin_cost(const double* __restrict__ cost, long long batch,
-                                                      long long* __restrict__ best_index,
-                                                      double* __restrict__ best_cost) {
-  __shared__ double sv[32];
-  __shared__ long long si[32];
-  double v = __longlong_as_double(0x7ff0000000000000LL);  // +inf
-  long long idx = -1;
-  for (long long i = threadIdx.x; i < batch; i += blockDim.x) {
-    const double c = cost[i];
-    if (c < v) { v = c; idx = i; }   // false for NaN
-  }
+// "Pick the best rollout": argmin over finite costs (NaN = failed instance, skipped), ties -> smallest index.
+// Multi-CTA: every CTA reduces a grid-strided share to one (cost, index) pair; the last CTA to finish (atomic
+// ticket) reduces the pairs and leaves the result ON THE DEVICE as {cost, index + index_offset}: no host round trip
+// unless the caller asks for one.  (Round 1 ran a single 1024-thread CTA over up to 8 x 65,536 gathered costs.)
+struct CostIndex {
+  double cost;       // NaN when no finite cost exists
+  long long index;   // -1 when no finite cost exists
+};
+
+__device__ __forceinline__ void argmin_merge(double& v, long long& idx, double ov, long long oi) {
+  if (oi >= 0 && (idx < 0 || ov < v || (ov == v && oi < idx))) { v = ov; idx = oi; }
+}
+
+__device__ __forceinline__ void argmin_block_reduce(double& v, long long& idx, double* sv, long long* si) {
   for (int o = 16; o > 0; o >>= 1) {
     const double ov = __shfl_down_sync(0xffffffffu, v, o);
     const long long oi = __shfl_down_sync(0xffffffffu, idx, o);
-    if (oi >= 0 && (ov < v || (ov == v && (idx < 0 || oi < idx)))) { v = ov; idx = oi; }
+    argmin_merge(v, idx, ov, oi);
   }
   if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = v; si[threadIdx.x >> 5] = idx; }
   __syncthreads();
   if (threadIdx.x < 32) {
-    v = (threadIdx.x < (blockDim.x >> 5)) ? sv[threadIdx.x] : __longlong_as_double(0x7ff0000000000000LL);
-    idx = (threadIdx.x < (blockDim.x >> 5)) ? si[threadIdx.x] : -1;
+    const bool on = threadIdx.x < ((blockDim.x + 31) >> 5);
+    v = on ? sv[threadIdx.x] : 0.0;
+    idx = on ? si[threadIdx.x] : -1;
     for (int o = 16; o > 0; o >>= 1) {
       const double ov = __shfl_down_sync(0xffffffffu, v, o);
       const long long oi = __shfl_down_sync(0xffffffffu, idx, o);
-      if (oi >= 0 && (ov < v || (ov == v && (idx < 0 || oi < idx)))) { v = ov; idx = oi; }
+      argmin_merge(v, idx, ov, oi);
     }
-    if (threadIdx.x == 0) { *best_index = idx; *best_cost = idx >= 0 ? v : qnan(); }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_argmin_cost(const double* __restrict__ cost, long long batch,
+                                                      long long index_offset, CostIndex* __restrict__ partial,
+                                                      unsigned* __restrict__ ticket, CostIndex* __restrict__ best) {
+  __shared__ double sv[32];
+  __shared__ long long si[32];
+  __shared__ bool last;
+  double v = 0.0;
+  long long idx = -1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < batch; i += (long long)gridDim.x * blockDim.x) {
+    const double c = cost[i];
+    if (c < __longlong_as_double(0x7ff0000000000000LL) && (idx < 0 || c < v)) { v = c; idx = i; }   // finite only (false for NaN, +inf); ascending i: the first minimum wins
+  }
+  argmin_block_reduce(v, idx, sv, si);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x].cost = v;
+    partial[blockIdx.x].index = idx;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  v = 0.0; idx = -1;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) {
+    const volatile CostIndex* p = partial + i;   // written by other CTAs of this launch: read past the cache
+    argmin_merge(v, idx, p->cost, p->index);
+  }
+  argmin_block_reduce(v, idx, sv, si);
+  if (threadIdx.x == 0) {
+    best->cost = idx >= 0 ? v : qnan();
+    best->index = idx >= 0 ? idx + index_offset : -1;
+    *ticket = 0;   // ready for the next launch
+  }
+}
+
+// final step of the cross-GPU pick: the smallest of the G gathered (cost, global index) pairs
+__global__ void __launch_bounds__(32) k_argmin_pairs(const CostIndex* __restrict__ pairs, int count,
+                                                     CostIndex* __restrict__ best) {
+  double v = 0.0;
+  long long idx = -1;
+  for (int i = threadIdx.x; i < count; i += 32) argmin_merge(v, idx, pairs[i].cost, pairs[i].index);
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ov = __shfl_down_sync(0xffffffffu, v, o);
+    const long long oi = __shfl_down_sync(0xffffffffu, idx, o);
+    argmin_merge(v, idx, ov, oi);
+  }
+  if (threadIdx.x == 0) {
+    best->cost = idx >= 0 ? v : qnan();
+    best->index = idx;
   }
 }
 

@@ -69,16 +69,48 @@ int main() {
     auto sbest = sh.solveFromInitialStates(B, x0.data(), sK0.data(), sP0.data(), scost.data(), sst.data());
     CHECK(same(sK0, rK0) && same(sP0, rP0) && same(scost, rcost) && sst == rst);
     CHECK(sbest.first == rb && sbest.second == rcost[rb]);
-    {  // a second GPU, when the box has one: two shards on two devices (one host thread each)
+    {  // the in-library multi-GPU plane on ONE device (an NCCL communicator of size 1): device-resident gather + pick
+      ShardedBatchedLqr one({0}, N);
+      CHECK(one.deviceGather());
+      std::vector<double> tK0(B * 48), tcost(B), dcost(B), dK0(B * 48);
+      std::vector<int32_t> tst(B, -1);
+      auto tbest = one.solveFromInitialStates(B, x0.data(), tK0.data(), nullptr, tcost.data(), tst.data());
+      CHECK(same(tK0, rK0) && same(tcost, rcost) && tst == rst && tbest.first == rb && tbest.second == rcost[rb]);
+      // the gathered arrays stay on the device: read them back through the C-ABI copy
+      CHECK(noc_memcpy(ctx->handle(), dcost.data(), one.deviceCosts(0), sizeof(double) * B) == NOC_OK);
+      CHECK(noc_memcpy(ctx->handle(), dK0.data(), one.deviceK0(0), sizeof(double) * B * 48) == NOC_OK);
+      ctx->synchronize();
+      CHECK(same(dcost, rcost) && same(dK0, rK0));
+      std::printf("comm plane (1 rank) OK\n");
+    }
+    {  // a second GPU, when the box has one: two NCCL ranks in this process, one host thread each; costs and first-step
+       // gains of BOTH slices end up on BOTH devices without passing through host arrays
       bool two = false;
       try { Context probe(1); two = true; } catch (const NocError&) {}
       if (two) {
         ShardedBatchedLqr sh2({0, 1}, N);
-        std::vector<double> tK0(B * 48), tP0(B * 144), tcost(B);
-        std::vector<int32_t> tst(B, -1);
-        auto tbest = sh2.solveFromInitialStates(B, x0.data(), tK0.data(), tP0.data(), tcost.data(), tst.data());
-        CHECK(same(tK0, rK0) && same(tP0, rP0) && same(tcost, rcost) && tst == rst && tbest.first == rb);
-        std::printf("two-GPU shards OK\n");
+        CHECK(sh2.deviceGather());
+        for (int64_t Bt : {B, B - 1}) {   // B - 1: the second slice is padded with a copy of the last instance
+          std::vector<double> tK0(Bt * 48), tcost(Bt);
+          std::vector<int32_t> tst(Bt, -1);
+          auto tbest = sh2.solveFromInitialStates(Bt, x0.data(), tK0.data(), nullptr, tcost.data(), tst.data());
+          int64_t rbt = 0;
+          for (int64_t i = 1; i < Bt; ++i) if (rcost[i] < rcost[rbt]) rbt = i;
+          CHECK(std::memcmp(tK0.data(), rK0.data(), sizeof(double) * Bt * 48) == 0);
+          CHECK(std::memcmp(tcost.data(), rcost.data(), sizeof(double) * Bt) == 0);
+          CHECK(std::memcmp(tst.data(), rst.data(), sizeof(int32_t) * Bt) == 0);
+          CHECK(tbest.first == rbt && tbest.second == rcost[rbt]);
+          // device 1 holds device 0's slice as well (and vice versa): read the gathered arrays back from GPU 1
+          const int64_t cnt = sh2.sliceLength();
+          std::vector<double> g1(2 * cnt), k1(2 * cnt * 48);
+          Context c1(1);
+          CHECK(noc_memcpy(c1.handle(), g1.data(), sh2.deviceCosts(1), sizeof(double) * 2 * cnt) == NOC_OK);
+          CHECK(noc_memcpy(c1.handle(), k1.data(), sh2.deviceK0(1), sizeof(double) * 2 * cnt * 48) == NOC_OK);
+          c1.synchronize();
+          CHECK(std::memcmp(g1.data(), rcost.data(), sizeof(double) * Bt) == 0);
+          CHECK(std::memcmp(k1.data(), rK0.data(), sizeof(double) * Bt * 48) == 0);
+        }
+        std::printf("two-GPU comm plane OK\n");
       }
     }
     auto s0 = shardSlice(10, 0, 3), s1 = shardSlice(10, 1, 3), s2 = shardSlice(10, 2, 3);

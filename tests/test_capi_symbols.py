@@ -79,3 +79,37 @@ def test_product_never_touches_the_oracle():
     if os.path.exists(capi.LIB_PATH):
         deps = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
         assert "oracle" not in deps
+
+
+def test_binding_checks_dtype_and_size_before_the_pointer_crosses():
+    """the C-ABI takes raw pointers, so the ctypes mirror must refuse a float32 / int64 / too-small array
+    instead of letting the library write fp64 / int32 data of its own size behind it."""
+    import numpy as np
+    from noc_b200 import capi
+    assert capi._f(None, 10, "x") is None
+    ok = np.zeros(12)
+    assert capi._f(ok, 12, "x") == ok.ctypes.data
+    with pytest.raises(TypeError):
+        capi._f(np.zeros(12, dtype=np.float32), 12, "K0")
+    with pytest.raises(TypeError):
+        capi._i(np.zeros(4, dtype=np.int64), 4, "status")
+    with pytest.raises(ValueError):
+        capi._f(np.zeros(11), 12, "cost")
+    with pytest.raises(ValueError):
+        capi._f(np.zeros((4, 6))[:, ::2], 12, "x0")            # not contiguous
+    import torch
+    t = torch.zeros(12, dtype=torch.float64)
+    assert capi._f(t, 12, "x") == t.data_ptr()
+    with pytest.raises(TypeError):
+        capi._f(torch.zeros(12, dtype=torch.float32), 12, "x")
+    with pytest.raises(ValueError):
+        capi._i(torch.zeros(3, dtype=torch.int32), 4, "iters")
+
+
+def test_no_link_time_nccl_dependency():
+    """The multi-GPU plane loads NCCL with dlopen at run time (inside a PyTorch process it shares torch's copy); the
+    product library itself must stay loadable on a box without libnccl."""
+    import subprocess
+    from noc_b200 import capi
+    deps = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in deps.lower(), deps
