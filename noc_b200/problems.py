@@ -53,6 +53,55 @@ def sample_x0(batch: int, seed: int = 0x4E4F43, model: int = MODEL_QUAD12):
     return x
 
 
+# ---- SURVEY.md §8d's generator, literally: std::mt19937_64 seeded 0x4E4F43 + instance_id, twelve draws of
+# std::uniform_real_distribution<double> per instance in state order, body rates U(-0.5, 0.5).
+_MT_F = np.uint64(6364136223846793005)
+_MT_A = np.uint64(0xB5026F5AA96619E9)
+_MT_UP, _MT_LO = np.uint64(0xFFFFFFFF80000000), np.uint64(0x7FFFFFFF)
+
+
+def mt19937_64_first_draws(seeds, count: int = 12):
+    """First `count` (<= 156) outputs of std::mt19937_64 for every seed in `seeds` (vectorised over the seeds).
+    Only state words 0 .. count+156 are ever touched by the first `count` outputs, so the 312-word state is not
+    built in full."""
+    assert 1 <= count <= 156
+    seeds = np.asarray(seeds, dtype=np.uint64)
+    L = count + 157
+    st = np.empty((seeds.size, L), dtype=np.uint64)
+    st[:, 0] = seeds
+    with np.errstate(over="ignore"):
+        for i in range(1, L):
+            prev = st[:, i - 1]
+            st[:, i] = _MT_F * (prev ^ (prev >> np.uint64(62))) + np.uint64(i)
+        y = (st[:, :count] & _MT_UP) | (st[:, 1:count + 1] & _MT_LO)      # the twist reads the OLD word i+1
+        x = st[:, 156:156 + count] ^ (y >> np.uint64(1)) ^ np.where(y & np.uint64(1), _MT_A, np.uint64(0))
+    x = x ^ ((x >> np.uint64(29)) & np.uint64(0x5555555555555555))
+    x = x ^ ((x << np.uint64(17)) & np.uint64(0x71D67FFFEDA60000))
+    x = x ^ ((x << np.uint64(37)) & np.uint64(0xFFF7EEE000000000))
+    return x ^ (x >> np.uint64(43))
+
+
+def uniform_real_from_u64(x, lo, hi):
+    """libstdc++'s uniform_real_distribution<double>(lo, hi) on a 64-bit engine: canonical = double(x) / 2^64
+    (one draw; a result of 1.0 is replaced by the largest double below 1), value = canonical * (hi - lo) + lo."""
+    c = x.astype(np.float64) * (1.0 / 18446744073709551616.0)
+    c = np.where(c >= 1.0, np.nextafter(1.0, 0.0), c)
+    return c * (hi - lo) + lo
+
+
+def sample_x0_survey(batch: int, first_instance: int = 0, seed0: int = 0x4E4F43):
+    """SURVEY.md §8d config 2 / 4 initial states: instance b draws x0 from std::mt19937_64(seed0 + b) in state
+    order: pos U(-2,2), vel U(-1,1), roll/pitch U(-0.3,0.3), yaw U(-pi,pi), body rates U(-0.5,0.5).
+    (tests/test_problems.py cross-checks the generator against a g++ program using <random>.)"""
+    lo = np.array([-2.0] * 3 + [-1.0] * 3 + [-0.3, -0.3, -np.pi] + [-0.5] * 3)
+    out = np.empty((batch, 12))
+    for b0 in range(0, batch, 16384):
+        b1 = min(batch, b0 + 16384)
+        seeds = np.arange(first_instance + b0, first_instance + b1, dtype=np.uint64) + np.uint64(seed0)
+        out[b0:b1] = uniform_real_from_u64(mt19937_64_first_draws(seeds, 12), lo, -lo)
+    return out
+
+
 def sample_goals(batch: int, seed: int = 0x534C51, model: int = MODEL_QUAD12):
     """Config 3 / 5 waypoint goals: pos U(-3,3)^3, yaw U(-pi/2,pi/2), everything else zero."""
     rng = np.random.default_rng(seed)
