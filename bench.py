@@ -6,10 +6,15 @@
 One "step" = one pass of the hot path over one batch: the finite-horizon LTV Riccati sweep of
 BASELINE.json configs[1] (batch 65,536 per GPU, distinct A_k,B_k per instance and step), every gain
 K_k written.  `value` is timed with the A_k,B_k stream resident in HBM (12.6 GB >> 126 MB L2, so no
-L2 flush is needed between steps); `e2e` goes through the C-ABI with HOST buffers (pinned x0 in; K0,
-P0, cost, status out) — nominal rollout, linearisation and sweep all inside the timed region.
+L2 flush is needed between steps).  `e2e` goes through the C-ABI with HOST buffers (pinned x0 in; K0,
+cost, status out) — nominal rollout, linearisation and sweep all inside the timed region — as mean
+and median of >= 50 steps; `e2e_same_contract` / `e2e_all_gains_to_host` are the `value` contract
+(all K_k, and A_k,B_k from host memory) through host buffers.  `extra` holds one block per other
+BASELINE.json config (1, 3, 4, 5, control-limited 3b / 5b; tools/bench_configs.py), each with its own
+roofline and CPU sample.
 N > 1 (torchrun, one rank per GPU): every rank sweeps its own 65,536 instances (weak scaling, no
-data-path collective), then costs are all-gathered over NCCL and the best rollout picked.
+data-path collective), then the library's own NCCL plane (noc_comm) picks the best rollout across the
+GPUs without a host round trip; `extra.config4_sharded_1M` is configs[3]'s strong-scaling batch.
 
 `--impl reference`: the reference publishes no solver source, so this arm times the
 in-repo CPU oracle (kind "port") on all host cores.  bench.py is one of the three places allowed to
@@ -160,6 +165,13 @@ def run_reference(args):
         oracle.lqr_batch(N_X, N_U, HORIZON, AB, qr, x0dev=x0, threads=threads)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
+    # the GPU arm's e2e contract on the CPU: x0 -> nominal rollout -> linearise -> sweep -> K0, cost (no A_k,B_k given)
+    oracle.lqr_from_x0_batch(0, HORIZON, pb.DT, x0[:256], qr, threads=threads, want_P0=False)
+    t0 = time.perf_counter()
+    fx_steps = max(1, min(args.steps, 3))
+    for _ in range(fx_steps):
+        oracle.lqr_from_x0_batch(0, HORIZON, pb.DT, x0, qr, threads=threads, want_P0=False)
+    fx = sample * fx_steps / (time.perf_counter() - t0)
     sample_txt = (f"{sample} of the {BATCH_PER_GPU} config-2 instances per step (LTV sweep n=12 m=4 N=100, all K_k "
                   f"written), OpenMP over instances")
     line = {
@@ -169,6 +181,11 @@ def run_reference(args):
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "contracts": {
+            "value": "A_k,B_k given in host memory -> all N gains K_k, K0, cost (the GPU arm's `value` and "
+                     "`e2e_same_contract`)",
+            "from_x0": {"value": fx, "unit": UNIT,
+                        "what": "x0 given -> nominal rollout -> linearisation -> sweep -> K0, cost (the GPU arm's `e2e`)"}},
         "gpu_launches": 0,
         "note": "KahnShi/NOC ships no solver source (SURVEY.md §0): this is the in-repo CPU oracle, not the reference",
     }
@@ -181,9 +198,62 @@ def workload_config(gpus, batch=BATCH_PER_GPU):
         "workload": "configs[1]: finite-horizon LTV LQR Riccati sweep, quadrotor n=12 m=4 N=100, "
                     f"batch {batch} random initial states per GPU, distinct A_k,B_k per instance and step",
         "n": N_X, "m": N_U, "N": HORIZON, "batch_per_gpu": batch, "global_batch": batch * gpus,
-        "sharding": f"dp{gpus} (independent instances; NCCL all-gather of costs + argmin only)",
+        "sharding": f"dp{gpus} (independent instances; in-library NCCL plane: all-gather of the ranks' 16-byte "
+                    "(cost, index) pairs + final pick, results left on the device)",
         "l2": "inputs larger than L2 (A_k,B_k stream 12.6 GB per step vs 126 MB L2); no flush needed",
     }
+
+
+def bind_to_gpu_numa(torch, local):
+    """Pin this process to the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) BEFORE the pinned
+    host buffers are allocated: first touch then places them on the GPU's NUMA node, and the e2e copies of the eight
+    ranks do not all cross one socket's memory controller.  Returns a description for the JSON line."""
+    try:
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/local_cpulist"
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"cpus": txt, "bound": True}
+        return {"cpus": txt, "bound": False}
+    except Exception as ex:
+        return {"bound": False, "why": str(ex)[:80]}
+
+
+def current_kernel_traffic():
+    """dram bytes per launch of the headline kernel from the committed ncu capture — only if that capture was taken on
+    the kernel source this library was built from (sha256 of riccati12.cuh); otherwise None, never a stale number."""
+    import hashlib
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        rec = json.load(open(tp))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "noc_b200", "csrc", "riccati12.cuh"), "rb").read()).hexdigest()
+        if rec.get("riccati12_cuh_sha256") == sha:
+            return rec.get("k_ric12_dram_bytes_per_launch_65536"), rec.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
+def host_timed(fn, steps, sync):
+    """Wall-clock per-step times of a synchronous host-buffer call (results are in host memory on return)."""
+    ts = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t1 = time.perf_counter()
+        fn()
+        ts.append(time.perf_counter() - t1)
+    sync()
+    return time.perf_counter() - t0, ts
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -206,6 +276,7 @@ def _run_noc(args):
         raise SystemExit("bench.py: no CUDA device — libnoc_b200 has no CPU fallback (use --impl reference "
                          "for the CPU oracle)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(torch, local)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -220,6 +291,9 @@ def _run_noc(args):
     solver = capi.Solver(local)
     stream = torch.cuda.Stream(device=dev)
     solver.set_stream(stream.cuda_stream)
+    # the multi-GPU plane lives in the library (noc_comm: NCCL loaded by libnoc_b200 itself); torch.distributed only
+    # carries the 128-byte id, the barriers and the max-over-ranks of the timings
+    comm = capi.Comm.from_torch_distributed(solver, dist, dev) if world > 1 else None
     f64 = dict(dtype=torch.float64, device=dev)
 
     # ---- inputs resident in HBM: x0 -> hover-thrust nominal -> A_k,B_k stream (our own kernels, untimed)
@@ -231,7 +305,7 @@ def _run_noc(args):
     d_K0 = torch.empty(B, N_U, N_X, **f64)
     d_cost = torch.empty(B, **f64)
     d_status = torch.full((B,), -1, dtype=torch.int32, device=dev)
-    d_all_cost = torch.empty(world * B, **f64) if world > 1 else None
+    d_best = torch.zeros(2, **f64)                 # {double cost; int64 index}, written by the library on the device
     torch.cuda.synchronize()
     p_model = capi.problem(capi.MODEL_QUAD12, N, flags=capi.FLAG_ASYNC)
     p_ltv = capi.problem(capi.MODEL_LTV_USER, N, flags=capi.FLAG_ASYNC)
@@ -241,19 +315,22 @@ def _run_noc(args):
     stream.synchronize()
     del d_xbar
 
-    best = {}
-
     def step():
         solver.lqr_solve_batch(p_ltv, B, d_AB, d_qr, x0dev=d_x0, K=d_K, K0=d_K0, cost=d_cost, status=d_status)
-        if world > 1:
-            with torch.cuda.stream(stream):
-                dist.all_gather_into_tensor(d_all_cost, d_cost)
-            best["idx"], best["cost"] = solver.argmin_cost(d_all_cost, world * B)
+        if comm is not None:   # pick the best rollout over all GPUs: local multi-CTA argmin, 16-byte pairs over NVLink, final pick
+            comm.best_rollout(d_cost, B, rank * B, d_best)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], **f64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     for _ in range(args.warmup):
         step()
@@ -276,63 +353,86 @@ def _run_noc(args):
     solver.profile_enable(False)
     ric_ms, ric_n = solver.profile_read(capi.KERNEL_RICCATI)
     launches = solver.launch_count - launches0
-    if world > 1:
-        t = torch.tensor([ms], **f64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    ms = max_over_ranks(ms)
     n_bad = int((d_status != 0).sum().item())
     value = world * B * args.steps / (ms * 1e-3)
+    best_pair = None
+    if comm is not None:
+        bp = d_best.cpu()
+        best_pair = {"cost": float(bp[0].item()), "index": int(bp.view(torch.int64)[1].item())}
 
-    # ---- e2e: the same solves through the C-ABI with HOST buffers (pinned), copies inside the timed region
+    # ---- e2e: the same solves through the C-ABI with HOST buffers (pinned, pre-faulted by the warm-up calls), copies
+    # inside the timed region.  Contract: x0 in -> K0 (the MPC gain), cost, status out.
+    e2e_steps = max(args.steps, 50)
     h_x0 = torch.from_numpy(x0).pin_memory()
-    h_K0 = torch.empty(B, N_U, N_X, dtype=torch.float64).pin_memory()
-    h_P0 = torch.empty(B, N_X, N_X, dtype=torch.float64).pin_memory()
-    h_cost = torch.empty(B, dtype=torch.float64).pin_memory()
-    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+    h_K0 = torch.zeros(B, N_U, N_X, dtype=torch.float64).pin_memory()
+    h_P0 = torch.zeros(B, N_X, N_X, dtype=torch.float64).pin_memory()
+    h_cost = torch.zeros(B, dtype=torch.float64).pin_memory()
+    h_status = torch.zeros(B, dtype=torch.int32).pin_memory()
     p_sync = capi.problem(capi.MODEL_QUAD12, N)
     h2d = h_x0.numel() * 8 + qr.size * 8
-    d2h = (h_K0.numel() + h_P0.numel() + h_cost.numel()) * 8 + h_status.numel() * 4
+    d2h = (h_K0.numel() + h_cost.numel()) * 8 + h_status.numel() * 4
 
     def e2e_step():
-        solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
+        solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K0=h_K0, cost=h_cost, status=h_status)
 
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 5)):
         e2e_step()
     barrier()
-    step_s = []
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        t1 = time.perf_counter()
-        e2e_step()                     # synchronous: results are in the host buffers on return
-        step_s.append(time.perf_counter() - t1)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    e2e_s, step_s = host_timed(e2e_step, e2e_steps, torch.cuda.synchronize)
+    e2e_s = max_over_ranks(e2e_s)
+    e2e_value = world * B * e2e_steps / e2e_s
+    e2e_bad = int((h_status != 0).sum().item())
+    e2e_median = max_over_ranks(float(np.median(step_s)))
 
-    # ---- extra: every gain K_k back to the host as well (2.5 GB per step over PCIe: the copy dominates)
-    allk = None
+    # round 1's e2e contract (P0, 1152 B per instance, as well) for continuity
+    def e2e_p0_step():
+        solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
+
+    for _ in range(3):
+        e2e_p0_step()
+    barrier()
+    p0_s, p0_steps = host_timed(e2e_p0_step, 20, torch.cuda.synchronize)
+    p0_s = max_over_ranks(p0_s)
+
+    # ---- same-contract extras (N = 1): what `value` computes, through host buffers
+    allk = same = None
     if world == 1 and not args.no_allk:
-        try:
-            h_K = torch.empty(B, N, N_U, N_X, dtype=torch.float64).pin_memory()
-            for _ in range(1):
-                solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K=h_K, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
-            t1 = time.perf_counter()
+        try:   # x0 in, ALL gains out (2.5 GB per step over PCIe: the copy dominates)
+            h_K = torch.zeros(B, N, N_U, N_X, dtype=torch.float64).pin_memory()
+            solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K=h_K, K0=h_K0, cost=h_cost, status=h_status)
             reps = 3
-            for _ in range(reps):
-                solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K=h_K, K0=h_K0, P0=h_P0, cost=h_cost, status=h_status)
-            dt_allk = (time.perf_counter() - t1) / reps
-            allk = {"value": B / dt_allk, "unit": UNIT, "ms_per_step": 1e3 * dt_allk,
-                    "d2h_bytes_per_step": d2h + h_K.numel() * 8,
-                    "what": "as e2e, plus all N gains K_k copied to pinned host memory"}
-            del h_K
+            dt_allk, _ = host_timed(lambda: solver.lqr_solve_from_x0(p_sync, B, h_x0, qr, K=h_K, K0=h_K0, cost=h_cost,
+                                                                     status=h_status), reps, torch.cuda.synchronize)
+            allk = {"value": B * reps / dt_allk, "unit": UNIT, "ms_per_step": 1e3 * dt_allk / reps,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h + h_K.numel() * 8,
+                    "what": "noc_lqr_solve_from_x0: pinned host x0 in; ALL N gains K_k, K0, cost, status to pinned host memory"}
+            # A_k,B_k in HOST memory in, all gains out: literally the reference arm's contract.  Bounded batch (the
+            # 12.6 GB stream of the full batch would need as much pinned memory); two-buffer pipeline in the library.
+            Bs = min(B, 8192)
+            h_AB = torch.empty(Bs, N, N_X * N_X + N_X * N_U, dtype=torch.float64).pin_memory()
+            h_AB.copy_(d_AB[:Bs])
+            p_ltv_sync = capi.problem(capi.MODEL_LTV_USER, N)
+            fn = lambda: solver.lqr_solve_batch(p_ltv_sync, Bs, h_AB, qr, x0dev=h_x0[:Bs], K=h_K[:Bs], K0=h_K0[:Bs],
+                                                cost=h_cost[:Bs], status=h_status[:Bs])
+            fn()
+            dt_same, _ = host_timed(fn, reps, torch.cuda.synchronize)
+            same = {"value": Bs * reps / dt_same, "unit": UNIT, "ms_per_step": 1e3 * dt_same / reps, "batch": Bs,
+                    "h2d_bytes_per_step": h_AB.numel() * 8 + Bs * N_X * 8 + qr.size * 8,
+                    "d2h_bytes_per_step": Bs * (N * 48 + 48 + 1) * 8 + Bs * 4,
+                    "what": "noc_lqr_solve_batch with A_k,B_k in pinned HOST memory (1536 B per instance-step over PCIe) and "
+                            "all N gains K_k, K0, cost, status back to the host: the contract of `value` and of the "
+                            "reference arm, PCIe-bound"}
+            del h_K, h_AB
         except Exception as ex:   # pinned allocation refused: report, do not fail the bench
-            allk = {"unavailable": str(ex)[:120]}
+            allk = allk or {"unavailable": str(ex)[:120]}
+            same = same or {"unavailable": str(ex)[:120]}
 
-    # ---- extra: the same pipeline with x0 and the outputs resident in HBM (no PCIe), device-timed
-    d_P0 = torch.empty(B, N_X, N_X, **f64)
+    # ---- extra: the from-x0 pipeline with x0 and the outputs resident in HBM (no PCIe), device-timed
     p_dev = capi.problem(capi.MODEL_QUAD12, N, flags=capi.FLAG_ASYNC)
 
     def pipe_step():
-        solver.lqr_solve_from_x0(p_dev, B, d_x0, d_qr, K0=d_K0, P0=d_P0, cost=d_cost, status=d_status)
+        solver.lqr_solve_from_x0(p_dev, B, d_x0, d_qr, K0=d_K0, cost=d_cost, status=d_status)
 
     for _ in range(args.warmup):
         pipe_step()
@@ -343,26 +443,64 @@ def _run_noc(args):
         pipe_step()
     p1.record(stream)
     barrier()
-    pipe_ms = p0.elapsed_time(p1) / args.steps
-    if world > 1:
-        t = torch.tensor([e2e_s], **f64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * B * args.steps / e2e_s
-    e2e_bad = int((h_status != 0).sum().item())
+    pipe_ms = max_over_ranks(p0.elapsed_time(p1) / args.steps)
+
+    # ---- SURVEY 8d's literal input generator (mt19937_64 per instance, body rates U(-0.5,0.5)) on the headline sweep
+    survey = None
+    if world == 1 and not args.no_extra:
+        xs = pb.sample_x0_survey(B)
+        d_xs = torch.from_numpy(xs).to(dev)
+        d_xb2 = torch.empty(B, N + 1, N_X, **f64)
+        with torch.cuda.stream(stream):
+            solver.rollout_open_loop(p_model, B, d_xs, None, d_xb2)
+            solver.linearize_batch(p_model, B, d_xb2, None, d_AB)
+        del d_xb2
+        fn = lambda: solver.lqr_solve_batch(p_ltv, B, d_AB, d_qr, x0dev=d_xs, K=d_K, K0=d_K0, cost=d_cost, status=d_status)
+        fn()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(5):
+            fn()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        sms = s0.elapsed_time(s1) / 5
+        survey = {"value": B / sms * 1e3, "unit": UNIT, "ms_per_step": sms, "status_not_ok": int((d_status != 0).sum().item()),
+                  "what": "the headline sweep on SURVEY.md 8d's literal inputs: std::mt19937_64(0x4E4F43 + instance), body rates "
+                          "U(-0.5,0.5) (the default sampler uses U(-0.2,0.2))"}
+    del d_AB, d_K
+    torch.cuda.empty_cache()
+
+    # ---- the other BASELINE.json configs (tools/bench_configs.py): device-timed, each with its roofline and CPU sample
+    extra = {}
+    from tools import bench_configs as bc
+    bb = bc.Bench(torch, solver, stream, dev, quick=args.quick_extra, cpu=not args.no_cpu)
+    if not args.no_extra:
+        r4 = bb.config4_sharded(comm, world, rank)          # every rank: configs[3] is the sharded 1M-solve batch
+        r4["ms"] = max_over_ranks(r4["ms"])
+        r4.update({"config": 4, "n_gpus": world, "scaling": "strong", "solves_per_s": r4["total"] / r4["ms"] * 1e3,
+                   "what": "configs[3]: 1,048,576 MPC warm-start LQR solves (N=50, K0 / cost) sharded over the GPUs through "
+                           "noc_comm_lqr_solve_from_x0 (cost all-gather under the sweep + cross-GPU pick); max over ranks",
+                   "roofline": bc.fp64_roofline(float(r4["total"]) / world * r4["N"] * bc.FLOPS_STEP[12], r4["ms"],
+                                                "whole step (rollout + k_ric12<RIC_LQR,FUSED> + gather + pick)",
+                                                "per-GPU solves x N x 9,045 over the whole step time (dense symmetric count)")})
+        extra["config4_sharded_1M"] = r4
+        if world == 1:
+            for key, fn in (("config1", bb.config1), ("config4_share", bb.config4_share), ("config3", lambda: bb.slq(3)),
+                            ("config5", lambda: bb.slq(5)), ("config3b_box", lambda: bb.slq(3, box=(0.0, 4.0))),
+                            ("config5b_box", lambda: bb.slq(5, box=(0.0, 4.0))), ("generic_kernel", bb.generic)):
+                try:
+                    extra[key] = fn()
+                except Exception as ex:
+                    extra[key] = {"failed": f"{type(ex).__name__}: {str(ex)[:200]}"}
+                log(f"extra {key}: done")
 
     line = None
     if rank == 0:
         peaks, peaks_kind = measured_peaks()
         ric_avg_ms = ric_ms / max(ric_n, 1)
         achieved = B * N * BYTES_PER_STEP / (ric_avg_ms * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("k_ric12_dram_bytes_per_launch_65536")
-            except Exception:
-                traffic = None
+        traffic, traffic_src = current_kernel_traffic()
         fp64_peak = fp64_peak_tflops()
         fp64_ach = B * N * FLOPS_PER_STEP_SYM / (ric_avg_ms * 1e-3) / 1e12
         line = {
@@ -371,16 +509,25 @@ def _run_noc(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world, B),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "noc_lqr_solve_from_x0: pinned host x0 -> nominal rollout -> fused linearise+Riccati sweep -> "
-                           "pinned host K0,P0,cost,status (device->host copies of finished chunks overlap the next chunk)",
-                    "ms_per_step": 1e3 * e2e_s / args.steps, "median_ms_per_step": 1e3 * float(np.median(step_s)),
-                    "max_ms_per_step": 1e3 * float(np.max(step_s))},
+                           "pinned host K0, cost, status (device->host copies of finished chunks overlap the next chunk)",
+                    "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps, "median_ms_per_step": 1e3 * e2e_median,
+                    "max_ms_per_step": 1e3 * float(np.max(step_s)),
+                    "value_at_median": world * B / e2e_median, "host_numa_binding": numa,
+                    "contract_note": "outputs are the first-step gain K0 (what an MPC loop applies), cost and status; the "
+                                     "reference arm's `contracts.from_x0` times the same contract on the CPU; the same-"
+                                     "contract figures for `value` are e2e_same_contract / e2e_all_gains_to_host"},
+            "e2e_with_P0": {"value": world * B * 20 / p0_s, "unit": UNIT, "ms_per_step": 1e3 * p0_s / 20,
+                            "median_ms_per_step": 1e3 * float(np.median(p0_steps)),
+                            "d2h_bytes_per_step": d2h + h_P0.numel() * 8, "what": "round 1's e2e contract: K0, P0, cost, status"},
+            "e2e_same_contract": same,
             "e2e_all_gains_to_host": allk,
-            "pipeline_device_resident": {"value": world * B / (pipe_ms * 1e-3) if world == 1 else None, "unit": UNIT,
-                                         "ms_per_step": pipe_ms,
-                                         "what": "x0 -> rollout -> fused linearise+sweep -> K0,P0,cost,status, all in HBM (rank 0)"},
+            "pipeline_device_resident": {"value": world * B / (pipe_ms * 1e-3), "unit": UNIT, "ms_per_step": pipe_ms,
+                                         "what": "x0 -> rollout -> fused linearise+sweep -> K0,cost,status, all in HBM (max over ranks)"},
+            "config2_survey_inputs": survey,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks_kind,
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peaks_kind,
                          "kernel": "k_ric12<LAYOUT_A_THEN_B,RIC_LQR>", "kernel_ms": ric_avg_ms, "kernel_launches": ric_n,
                          "algorithmic_bytes_per_launch": B * N * BYTES_PER_STEP,
                          "kernel_share_of_step": ric_ms / ms if world == 1 else None,
@@ -388,15 +535,18 @@ def _run_noc(args):
                                   "frac": (fp64_ach / fp64_peak) if fp64_peak else None}},
             "clocks": clocks,
             "status_not_ok": n_bad + e2e_bad,
+            "extra": extra,
         }
-        if world > 1:
-            line["best_rollout"] = {"index": best.get("idx"), "cost": best.get("cost")}
+        if best_pair is not None:
+            line["best_rollout"] = best_pair
         if world == 1 and not args.no_cpu:
             v, cores, secs = cpu_leg(args.cpu_sample)
             line["cpu_baseline"] = {
                 "value": v, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{args.cpu_sample} of the {B} instances, one pass, {secs:.2f} s wall on {cores} threads "
                           "(in-repo C oracle, OpenMP over instances; the reference has no solver source)"}
+    if comm is not None:
+        comm.close()
     solver.close()
     if world > 1:
         dist.barrier()
@@ -430,7 +580,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=32768)
     ap.add_argument("--ref-sample", type=int, default=8192)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-allk", action="store_true", help="skip the all-gains-to-host extra")
+    ap.add_argument("--no-allk", action="store_true", help="skip the all-gains-to-host / same-contract extras")
+    ap.add_argument("--no-extra", action="store_true", help="skip the blocks of the other BASELINE.json configs")
+    ap.add_argument("--quick-extra", action="store_true", help="small batches in the extra blocks (smoke runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "noc":
         log("note: fewer than 3 warm-up steps requested")
