@@ -71,10 +71,9 @@ def _box_qp_bvls(H, g, lo, hi):
     from scipy.optimize import lsq_linear
     L = np.linalg.cholesky(H)
     r = lsq_linear(L.T, -np.linalg.solve(L, g), bounds=(lo, hi), method="bvls", tol=1e-15, max_iter=200)
-    k = r.x
-    grad = H @ k + g
-    clamped = ((k <= lo) & (grad > 0)) | ((k >= hi) & (grad < 0))
-    return k, clamped
+    # BVLS reports its active set; it may leave an active component one ulp inside the bound, so snap those
+    k = np.where(r.active_mask < 0, lo, np.where(r.active_mask > 0, hi, r.x))
+    return k, r.active_mask != 0
 
 
 def _numpy_ilqr(f, x0, xg, uh, Q, R, Qf, N, box=None, tol=1e-8, max_iter=50, n_alpha=11, armijo=1e-4):
