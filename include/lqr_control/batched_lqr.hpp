@@ -185,6 +185,9 @@ class BatchedSlq {
   void setWeights(const Weights& w) { checkWeightDims(w, prob_); weights_ = w; }
   // box on every input component (rotor thrust limits): control-limited backward pass + clamped rollouts
   void setInputBox(double u_min, double u_max) { prob_.u_min = u_min; prob_.u_max = u_max; }
+  // Levenberg-Marquardt schedule: NOC_REG_X10 (default) or NOC_REG_ADAPTIVE (mu raised on failed factorisations and
+  // failed line searches, lowered after accepted steps)
+  void setRegularisation(int schedule, double mu0 = 0.0) { prob_.reg_schedule = schedule; prob_.reg0 = mu0; }
   void solve(int64_t batch, const double* x0, const double* xgoal, double* x, double* u, double* K, double* cost,
              int32_t* iters, int32_t* alpha_idx, int32_t* status) {
     ctx_->check(noc_slq_solve_batch(ctx_->handle(), &prob_, batch, x0, xgoal, weights_.qrqf.data(), x, u, K, cost,

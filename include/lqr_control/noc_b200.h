@@ -86,7 +86,19 @@ typedef struct {
   double u_min, u_max;     /* SLQ: box on every input component (control-limited DDP: box QP for the feed-forward,
                               zero feedback on clamped inputs, clamped rollouts).  -INFINITY / +INFINITY
                               (the defaults) = unconstrained.  Both built-in models. */
+  int32_t reg_schedule;    /* SLQ: noc_reg_schedule */
+  int32_t reserved_;       /* keep 0 */
 } noc_problem_t;
+
+/* SLQ regularisation schedules (the Levenberg-Marquardt mu added to the diagonal of Quu) */
+typedef enum {
+  NOC_REG_X10 = 0,       /* default: mu <- max(10 mu, 1e-6) when a factorisation fails, never decreased; a failed line
+                            search ends the instance with NOC_STATUS_LS_FAIL */
+  NOC_REG_ADAPTIVE = 1   /* Tassa-style: mu <- max(1e-6, mu*delta), delta <- max(2, 2 delta) on a failed factorisation AND
+                            on a failed line search (the iteration is repeated from the same nominal and recorded as
+                            alpha_idx = -2); delta <- min(1/2, delta/2), mu <- mu*delta (0 below 1e-6) after every
+                            accepted step.  mu > 1e6 ends the instance (REG_FAIL / LS_FAIL) */
+} noc_reg_schedule;
 
 /* ---- context ------------------------------------------------------------------------------ */
 int noc_create(noc_ctx** out, int device_id);
@@ -128,7 +140,7 @@ int noc_profile_enable(noc_ctx* ctx, int on);
 /* total device milliseconds and launch count of one kernel id since the last reset (synchronises) */
 int noc_profile_read(noc_ctx* ctx, int kernel_id, double* total_ms, int64_t* launches);
 int noc_profile_reset(noc_ctx* ctx);
-/* fill defaults: tol 1e-8, max_iter 50, n_alpha 11, armijo 1e-4, dt 0.02, layout A_THEN_B, no input box */
+/* fill defaults: tol 1e-8, max_iter 50, n_alpha 11, armijo 1e-4, dt 0.02, layout A_THEN_B, no input box, NOC_REG_X10 */
 void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N);
 
 /* ---- SURVEY §8(a) a2+a3: backward Riccati recursion, Cholesky, gains -------------------------
@@ -190,7 +202,8 @@ int noc_dare_solve_at(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, co
 /* ---- SLQ / iLQR with the built-in nonlinear models ---------------------------
  *   x0, xgoal [batch][n]; QRQf shared.
  *   x [batch][N+1][n], u [batch][N][m], K [batch][N][m*n] (NULL ok), cost [batch],
- *   iters [batch], alpha_idx [batch][max_iter] (accepted j per iteration, -1 beyond), status [batch]  */
+ *   iters [batch], alpha_idx [batch][max_iter] (accepted j per iteration, -1 beyond; -2 = iteration rejected and
+ *   regularisation raised, NOC_REG_ADAPTIVE only), status [batch]                                     */
 int noc_slq_solve_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* x0,
                         const double* xgoal, const double* QRQf, double* x, double* u, double* K,
                         double* cost, int32_t* iters, int32_t* alpha_idx, int32_t* status);

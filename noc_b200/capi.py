@@ -25,6 +25,7 @@ MODEL_QUAD12, MODEL_DUAL24, MODEL_LTV_USER = 0, 1, 2
 LAYOUT_A_THEN_B, LAYOUT_ROWS_AB = 0, 1
 FLAG_NONE, FLAG_ASYNC = 0, 1
 OPT_SCRATCH_LIMIT_BYTES, OPT_CHUNK_WAVES, OPT_SINGLE_STREAM = 0, 1, 2
+REG_X10, REG_ADAPTIVE = 0, 1
 
 EXPORTS = [
     "noc_create", "noc_destroy", "noc_last_error", "noc_version", "noc_set_stream", "noc_synchronize", "noc_set_option",
@@ -42,7 +43,7 @@ class Problem(C.Structure):
     _fields_ = [("n", C.c_int32), ("m", C.c_int32), ("N", C.c_int32), ("model", C.c_int32),
                 ("layout", C.c_int32), ("max_iter", C.c_int32), ("n_alpha", C.c_int32), ("flags", C.c_int32),
                 ("dt", C.c_double), ("tol", C.c_double), ("reg0", C.c_double), ("armijo", C.c_double),
-                ("u_min", C.c_double), ("u_max", C.c_double)]
+                ("u_min", C.c_double), ("u_max", C.c_double), ("reg_schedule", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class CostIndex(C.Structure):

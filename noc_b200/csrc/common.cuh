@@ -31,4 +31,19 @@ __device__ __forceinline__ void stg128_cs(double* p, double a, double b) {
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// Adaptive Levenberg-Marquardt schedule of SLQ (oracle: reg_increase / reg_decrease): delta0 = 2,
+// mu_min = 1e-6.  Multiplications and comparisons only, so both sides agree bit for bit.
+__device__ __forceinline__ void reg_increase(double& mu, double& delta) {
+  const double d = delta * 2.0;
+  delta = (d > 2.0) ? d : 2.0;
+  const double v = mu * delta;
+  mu = (v > 1e-6) ? v : 1e-6;
+}
+__device__ __forceinline__ void reg_decrease(double& mu, double& delta) {
+  const double d = delta * 0.5;
+  delta = (d < 0.5) ? d : 0.5;
+  const double v = mu * delta;
+  mu = (v >= 1e-6) ? v : 0.0;
+}
+
 }  // namespace noc

@@ -219,7 +219,7 @@ int scratch_budget(noc_ctx* ctx, int entry, int n, int N, int extra, int64_t bat
 enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
        SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC, SCR_FLAGS, SCR_XC, SCR_UC, SCR_LCC,
        SCR_PIPE_AB0, SCR_PIPE_AB1, SCR_PIPE_X0, SCR_PIPE_X1, SCR_PIPE_QR0, SCR_PIPE_QR1, SCR_PIPE_OUT0,
-       SCR_PIPE_OUT_LAST = SCR_PIPE_OUT0 + 9, SCR_ARGMIN_PART, SCR_COMM_PAIRS, SCR_COMM_COST, SCR_END };
+       SCR_PIPE_OUT_LAST = SCR_PIPE_OUT0 + 9, SCR_ARGMIN_PART, SCR_COMM_PAIRS, SCR_COMM_COST, SCR_DELTA, SCR_END };
 
 // W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
 // Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
@@ -635,6 +635,8 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
   if ((rc = scratch(ctx, SCR_KFF, sizeof(double) * B * N * m, &dkff))) return rc;
   if ((rc = scratch(ctx, SCR_DV, sizeof(double) * B * 2, &ddV))) return rc;
   if ((rc = scratch(ctx, SCR_MU, sizeof(double) * B, &dmu))) return rc;
+  void* ddelta;
+  if ((rc = scratch(ctx, SCR_DELTA, sizeof(double) * B, &ddelta))) return rc;
   if ((rc = scratch(ctx, SCR_BSTATUS, sizeof(int32_t) * B, &dbst))) return rc;
   if ((rc = scratch(ctx, SCR_IDX0, sizeof(int32_t) * B, &didx0))) return rc;
   if ((rc = scratch(ctx, SCR_IDX1, sizeof(int32_t) * B, &didx1))) return rc;
@@ -656,7 +658,7 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
     LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
     k_slq_init<MODEL><<<(unsigned)((batch + 127) / 128), 128, wbytes, ctx->stream>>>(
         (const double*)dx0, (const double*)dxg, (const double*)dQ, (const double*)dui, (double*)dx, (double*)du, (double*)dJ, (double*)dmu,
-        (int32_t*)dst, (int32_t*)dit, (int32_t*)dai, (int32_t*)didx0, batch, p->N, p->dt, p->reg0, p->max_iter);
+        (double*)ddelta, (int32_t*)dst, (int32_t*)dit, (int32_t*)dai, (int32_t*)didx0, batch, p->N, p->dt, p->reg0, p->max_iter);
   }
   NOC_CUDA(ctx, cudaGetLastError());
   typename std::conditional<MODEL == 0, Ric12Args, Ric24Args>::type ra{};
@@ -672,7 +674,8 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
     // a2+a3: affine backward pass (regularisation retries in-kernel)
     ra.AB = (const double*)dAB; ra.idx = cur; ra.xbar = (const double*)dx; ra.ubar = (const double*)du;
     ra.xgoal = (const double*)dxg; ra.K = (double*)dK; ra.kff = (double*)dkff; ra.dV = (double*)ddV;
-    ra.mu = (double*)dmu; ra.status = (int32_t*)dbst; ra.batch = count; ra.N = p->N;
+    ra.mu = (double*)dmu; ra.delta = (double*)ddelta; ra.reg_schedule = p->reg_schedule;
+    ra.status = (int32_t*)dbst; ra.batch = count; ra.N = p->N;
     ra.dt = p->dt;
     if constexpr (MODEL == 0) {
       ra.u_min = p->u_min; ra.u_max = p->u_max;
@@ -695,6 +698,7 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
     fa.status = (int32_t*)dst; fa.iters = (int32_t*)dit; fa.alpha_idx = (int32_t*)dai; fa.N = p->N;
     fa.iter = it; fa.max_iter = p->max_iter; fa.n_alpha = p->n_alpha; fa.dt = p->dt; fa.tol = p->tol;
     fa.armijo = p->armijo; fa.u_min = p->u_min; fa.u_max = p->u_max;
+    fa.mu = (double*)dmu; fa.delta = (double*)ddelta; fa.reg_schedule = p->reg_schedule;
     int32_t hc[2] = {0, 0};
     const int32_t* list = cur;
     int list_count = count;
@@ -887,6 +891,7 @@ void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N) {
   p->armijo = 1e-4;
   p->u_min = -INFINITY;
   p->u_max = INFINITY;
+  p->reg_schedule = NOC_REG_X10;
 }
 
 int noc_create(noc_ctx** out, int device_id) {
@@ -1240,6 +1245,7 @@ int noc_slq_solve_warm(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, cons
   if (p->max_iter < 1 || p->n_alpha < 1 || p->n_alpha > 32)
     return fail(ctx, NOC_ERR_BAD_ARG, "need max_iter >= 1 and 1 <= n_alpha <= 32");
   if (!(p->u_min < p->u_max)) return fail(ctx, NOC_ERR_BAD_ARG, "need u_min < u_max (-INFINITY / INFINITY = no input box)");
+  if (p->reg_schedule != NOC_REG_X10 && p->reg_schedule != NOC_REG_ADAPTIVE) return fail(ctx, NOC_ERR_BAD_ARG, "unknown reg_schedule");
   if (batch > 0x7fffffffLL) return fail(ctx, NOC_ERR_BAD_ARG, "batch too large for 32-bit work lists");
   if (batch == 0) return NOC_OK;
   return p->model == NOC_MODEL_QUAD12

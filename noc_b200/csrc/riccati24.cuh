@@ -57,6 +57,8 @@ struct Ric24Args {
   double* kff;           // [batch][N][8]
   double* dV;            // [batch][2]
   double* mu;            // [batch]
+  double* delta;         // [batch] in/out: adaptive schedule's scaling factor (reg_schedule == 1)
+  int reg_schedule;      // noc_reg_schedule
   long long batch;
   int N;
 };
@@ -602,8 +604,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
       }
     }
     if (MODE != RIC_AFFINE) break;
+    // (the adaptive schedule's factor lives in global memory: it is touched once per sweep, not worth a register pair)
+    double dl = (a.reg_schedule == 1) ? a.delta[b] : 1.0;
+    __syncwarp();
     if (failed && !reg_fail) {
-      mu = (mu * 10.0 > 1e-6) ? mu * 10.0 : 1e-6;
+      if (a.reg_schedule == 1) {
+        reg_increase(mu, dl);
+        if (t == 0 && valid) a.delta[b] = dl;
+      } else {
+        mu = (mu * 10.0 > 1e-6) ? mu * 10.0 : 1e-6;
+      }
       if (mu > 1e6) reg_fail = true;
     }
     if (!__any_sync(0xffffffffu, failed && !reg_fail)) break;

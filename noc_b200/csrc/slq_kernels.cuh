@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(128) k_slq_init(const double* __restrict__ x0,
                                                   const double* __restrict__ u_init,   // [batch][N][m] or nullptr (hover)
                                                   double* __restrict__ x,
                                                   double* __restrict__ u, double* __restrict__ J,
-                                                  double* __restrict__ mu, int32_t* __restrict__ status,
+                                                  double* __restrict__ mu, double* __restrict__ delta,
+                                                  int32_t* __restrict__ status,
                                                   int32_t* __restrict__ iters, int32_t* __restrict__ alpha_idx,
                                                   int32_t* __restrict__ idx, long long batch, int N, double dt,
                                                   double reg0, int max_iter) {
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(128) k_slq_init(const double* __restrict__ x0,
   cost = cost + w.terminal(xk, xg);
   J[b] = cost;
   mu[b] = reg0;
+  delta[b] = 1.0;
   status[b] = 2;  // NOC_STATUS_MAX_ITER until something else happens
   iters[b] = 0;
   idx[b] = (int32_t)b;
@@ -154,6 +156,9 @@ struct SlqFwdArgs {
   int n_alpha;              // <= 32
   double dt, tol, armijo;
   double u_min, u_max;      // input box of the closed-loop rollouts (+-inf = none)
+  double* mu;               // [batch] Levenberg-Marquardt mu (adaptive schedule: updated after every line search)
+  double* delta;            // [batch] its scaling factor
+  int reg_schedule;         // noc_reg_schedule
 };
 
 // The forward pass is three kernels per step length: (1) k_slq_rollout, the sequential closed-loop rollout, only
@@ -347,6 +352,11 @@ __global__ void __launch_bounds__(128) k_slq_stage_cost(const SlqFwdArgs a) {
 // bookkeeping of an accepted step (trial index `accepted`, cost Jacc): records, convergence test, next work list
 __device__ __forceinline__ void slq_record_step(const SlqFwdArgs& a, long long b, double Jold, double Jacc, int accepted) {
   if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + a.iter] = accepted;
+  if (a.reg_schedule == 1) {   // accepted step: relax the regularisation
+    double mu = a.mu[b], dl = a.delta[b];
+    reg_decrease(mu, dl);
+    a.mu[b] = mu; a.delta[b] = dl;
+  }
   const double denom = (Jold > 1e-12) ? Jold : 1e-12;
   const double rel = (Jold - Jacc) / denom;
   a.J[b] = Jacc;
@@ -356,6 +366,24 @@ __device__ __forceinline__ void slq_record_step(const SlqFwdArgs& a, long long b
     return;
   }
   if (a.iter + 1 < a.max_iter) a.flags[b] |= 1;
+}
+
+// no step length passed (the nominal has been put back).  Default schedule: the instance stops with LS_FAIL.  Adaptive
+// schedule: mu is raised and the iteration is repeated from the same nominal (recorded as alpha_idx = -2) unless mu
+// leaves its range.  Called by one lane.
+__device__ __forceinline__ void slq_line_search_failed(const SlqFwdArgs& a, long long b) {
+  a.iters[b] = a.iter + 1;
+  if (a.reg_schedule == 1) {
+    double mu = a.mu[b], dl = a.delta[b];
+    reg_increase(mu, dl);
+    a.mu[b] = mu; a.delta[b] = dl;
+    if (!(mu > 1e6)) {
+      if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + a.iter] = -2;
+      if (a.iter + 1 < a.max_iter) a.flags[b] |= 1;
+      return;
+    }
+  }
+  a.status[b] = 3;  // NOC_STATUS_LS_FAIL
 }
 
 // ordinary round (one step length per launch): one WARP per instance.  The stage costs are read with coalesced
@@ -401,10 +429,7 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
     double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
     for (int i = lane; i < (N + 1) * n / 2; i += 32) dxp[i] = sx[i];
     for (int i = lane; i < N * m / 2; i += 32) dup[i] = su[i];
-    if (lane == 0) {
-      a.status[b] = 3;  // NOC_STATUS_LS_FAIL
-      a.iters[b] = a.iter + 1;
-    }
+    if (lane == 0) slq_line_search_failed(a, b);
     return;
   }
   if (lane == 0) slq_record_step(a, b, Jold, Jacc, a.trial);
@@ -451,9 +476,8 @@ __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
   for (int i = lane; i < (N + 1) * n / 2; i += 32) dxp[i] = sx[i];
   for (int i = lane; i < N * m / 2; i += 32) dup[i] = su[i];
   if (lane != 0) return;
-  if (c < 0) {
-    a.status[b] = 3;  // NOC_STATUS_LS_FAIL (the nominal has been put back)
-    a.iters[b] = a.iter + 1;
+  if (c < 0) {   // the nominal has been put back
+    slq_line_search_failed(a, b);
     return;
   }
   slq_record_step(a, b, Jold, Jacc, a.cand_first + c);

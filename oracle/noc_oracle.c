@@ -810,6 +810,22 @@ double noc_oracle_forward_box(int model, int N, double dt, const double* xbar, c
   return J;
 }
 
+/* Adaptive Levenberg-Marquardt schedule (Tassa, Erez, Todorov 2012): delta0 = 2, mu_min = 1e-6.
+ * increase: delta <- max(delta0, delta * delta0), mu <- max(mu_min, mu * delta)
+ * decrease: delta <- min(1 / delta0, delta / delta0), mu <- mu * delta if that is >= mu_min, else 0 */
+static void reg_increase(double* mu, double* delta) {
+  const double d = *delta * 2.0;
+  *delta = (d > 2.0) ? d : 2.0;
+  const double v = *mu * *delta;
+  *mu = (v > 1e-6) ? v : 1e-6;
+}
+static void reg_decrease(double* mu, double* delta) {
+  const double d = *delta * 0.5;
+  *delta = (d < 0.5) ? d : 0.5;
+  const double v = *mu * *delta;
+  *mu = (v >= 1e-6) ? v : 0.0;
+}
+
 int noc_oracle_slq(const noc_oracle_slq_opts* o, const double* x0, const double* xgoal,
                    const double* QRQf, double* x, double* u, double* K, double* kff, double* cost,
                    int32_t* iters, int32_t* alpha_idx, double* reg) {
@@ -834,6 +850,8 @@ int noc_oracle_slq_warm(const noc_oracle_slq_opts* o, const double* x0, const do
   noc_oracle_rollout_open_loop(o->model, N, o->dt, x0, u, x);
   double J = noc_oracle_traj_cost(o->model, N, x, u, xgoal, QRQf);
   double mu = o->reg0;
+  double delta = 1.0;   /* adaptive schedule: the factor mu was last scaled by */
+  const int adaptive = o->reg_schedule == 1;
   int status = NOC_O_MAX_ITER;
   int it = 0;
   for (int i = 0; i < o->max_iter; ++i) alpha_idx[i] = -1;
@@ -841,7 +859,8 @@ int noc_oracle_slq_warm(const noc_oracle_slq_opts* o, const double* x0, const do
     double dV[2];
     int bad = 0;
     while (noc_oracle_backward_affine_box(o->model, N, o->dt, x, u, xgoal, QRQf, mu, o->u_min, o->u_max, Kw, kw, dV) != NOC_O_OK) {
-      mu = (mu * 10.0 > 1e-6) ? mu * 10.0 : 1e-6;
+      if (adaptive) reg_increase(&mu, &delta);
+      else mu = (mu * 10.0 > 1e-6) ? mu * 10.0 : 1e-6;
       if (mu > 1e6) { bad = 1; break; }
     }
     if (bad) { status = NOC_O_REG_FAIL; ++it; break; }
@@ -854,8 +873,16 @@ int noc_oracle_slq_warm(const noc_oracle_slq_opts* o, const double* x0, const do
       if (J - Ja >= o->armijo * expected) { accepted = j; Jn = Ja; break; }
       alpha = alpha * 0.5;
     }
-    if (accepted < 0) { status = NOC_O_LS_FAIL; ++it; break; }
+    if (accepted < 0) {
+      if (!adaptive) { status = NOC_O_LS_FAIL; ++it; break; }
+      /* adaptive: no step length passed -> raise mu and repeat the iteration from the same nominal (it counts) */
+      reg_increase(&mu, &delta);
+      if (mu > 1e6) { status = NOC_O_LS_FAIL; ++it; break; }
+      alpha_idx[it] = -2;
+      continue;
+    }
     alpha_idx[it] = accepted;
+    if (adaptive) reg_decrease(&mu, &delta);
     memcpy(x, xn, (size_t)(N + 1) * n * sizeof(double));
     memcpy(u, un, (size_t)N * m * sizeof(double));
     const double denom = (J > 1e-12) ? J : 1e-12;

@@ -76,6 +76,7 @@ typedef struct {
   int model, N, max_iter, n_alpha;
   double dt, tol, reg0, armijo;
   double u_min, u_max;   /* box on every input component; -INFINITY / INFINITY = unconstrained */
+  int reg_schedule;      /* 0: mu x10 on a failed factorisation, never decreased; 1: adaptive (2.4c) */
 } noc_oracle_slq_opts;
 /* x[(N+1)*n], u[N*m], K[N*m*n] (may be NULL), kff[N*m] (may be NULL), alpha_idx[max_iter] (filled with -1
  * beyond iters), returns status; *iters, *cost, *reg (final mu) */

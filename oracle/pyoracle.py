@@ -37,7 +37,7 @@ def build(force: bool = False) -> str:
 class SlqOpts(C.Structure):
     _fields_ = [("model", C.c_int), ("N", C.c_int), ("max_iter", C.c_int), ("n_alpha", C.c_int),
                 ("dt", C.c_double), ("tol", C.c_double), ("reg0", C.c_double), ("armijo", C.c_double),
-                ("u_min", C.c_double), ("u_max", C.c_double)]
+                ("u_min", C.c_double), ("u_max", C.c_double), ("reg_schedule", C.c_int)]
 
 
 _lib = None
@@ -185,8 +185,9 @@ def dare(A, B, Q, R, tol=1e-12, max_iter=10000):
     return P, K, it
 
 
-def slq_opts(model, N, dt=0.02, tol=1e-8, max_iter=50, n_alpha=11, reg0=0.0, armijo=1e-4, u_min=-np.inf, u_max=np.inf):
-    return SlqOpts(model, N, max_iter, n_alpha, dt, tol, reg0, armijo, u_min, u_max)
+def slq_opts(model, N, dt=0.02, tol=1e-8, max_iter=50, n_alpha=11, reg0=0.0, armijo=1e-4, u_min=-np.inf, u_max=np.inf,
+             reg_schedule=0):
+    return SlqOpts(model, N, max_iter, n_alpha, dt, tol, reg0, armijo, u_min, u_max, reg_schedule)
 
 
 def slq(opts, x0, xgoal, QRQf, want_K=True):

@@ -46,7 +46,8 @@ def test_problem_struct_layout(lib):
     p = capi.problem(capi.MODEL_DUAL24, 7)
     assert (p.n, p.m, p.N) == (24, 8, 7)
     assert p.u_min == -float("inf") and p.u_max == float("inf")        # no input box by default
-    assert ctypes.sizeof(capi.Problem) == 8 * 4 + 6 * 8
+    assert p.reg_schedule == capi.REG_X10 and p.reserved_ == 0
+    assert ctypes.sizeof(capi.Problem) == 8 * 4 + 6 * 8 + 2 * 4
 
 
 def test_version_and_no_gpu_fails_loudly(lib):

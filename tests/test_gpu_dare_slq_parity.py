@@ -150,7 +150,8 @@ def _slq_compare(oracle, solver, batch, N, x0, xg, qr, **kw):
     aidx = np.full((batch, prob.max_iter), -7, dtype=np.int32)
     solver.slq_solve_batch(prob, batch, x0, xg, qr, x=x, u=u, K=K, cost=cost, iters=iters, alpha_idx=aidx, status=status)
     opts = oracle.slq_opts(0, N, dt=prob.dt, tol=prob.tol, max_iter=prob.max_iter, n_alpha=prob.n_alpha,
-                           reg0=prob.reg0, armijo=prob.armijo, u_min=prob.u_min, u_max=prob.u_max)
+                           reg0=prob.reg0, armijo=prob.armijo, u_min=prob.u_min, u_max=prob.u_max,
+                           reg_schedule=prob.reg_schedule)
     ref = oracle.slq_batch(opts, x0, xg, qr, want_traj=True, want_K=True)
     assert np.array_equal(status, ref["status"])
     assert np.array_equal(iters, ref["iters"])          # iteration counts identical (north_star)
@@ -237,6 +238,30 @@ def test_slq_regularisation_retry(oracle, solver):
     x0 = pb.sample_x0(batch, seed=31); xg = pb.sample_goals(batch, seed=7)
     _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=5)
     _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=5, u_min=1.0, u_max=3.5)   # mu retries under the input box
+
+
+def test_slq_adaptive_regularisation_bitexact(oracle, solver):
+    """NOC_REG_ADAPTIVE: mu lowered after accepted steps, raised on failed factorisations AND failed
+    line searches (iteration repeated from the same nominal, alpha_idx = -2).  Bit-identical to the oracle."""
+    from noc_b200 import capi
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    # (a) started from mu0 = 1: the schedule walks mu down, fewer iterations than the fixed rule
+    batch, N = 24, 60
+    x0 = pb.hover_state(batch); xg = pb.sample_goals(batch, seed=5150)
+    ada = _slq_compare(oracle, solver, batch, N, x0, xg, qr, reg_schedule=capi.REG_ADAPTIVE, reg0=1.0)
+    fix = _slq_compare(oracle, solver, batch, N, x0, xg, qr, reg0=1.0)
+    assert ada["iters"].sum() < fix["iters"].sum()
+    # (b) tight input box: line searches fail and are repeated with a larger mu; several warps, ragged tail
+    pick = [284, 217, 252, 60, 89, 101, 214, 226, 293, 490] + list(range(30))
+    xg = pb.sample_goals(512, seed=33)[pick]; x0 = pb.hover_state(len(pick))
+    out = _slq_compare(oracle, solver, len(pick), N, x0, xg, qr, reg_schedule=capi.REG_ADAPTIVE, u_min=0.0, u_max=4.0)
+    assert (out["aidx"] == -2).any(axis=1).sum() >= 8
+    # (c) an indefinite R: factorisation retries inside the sweep follow the adaptive rule too
+    Rb = R.copy(); Rb[1, 1] = -0.5
+    x0 = pb.sample_x0(10, seed=31); xg = pb.sample_goals(10, seed=7)
+    _slq_compare(oracle, solver, 10, 20, x0, xg, pb.pack_qrqf(Q, Rb, Qf), max_iter=6, reg_schedule=capi.REG_ADAPTIVE)
+    _slq_compare(oracle, solver, 10, 20, x0, xg, pb.pack_qrqf(Q, Rb, Qf), max_iter=6, reg_schedule=capi.REG_ADAPTIVE,
+                 u_min=1.0, u_max=3.5)
 
 
 def test_slq_optional_outputs(oracle, solver):

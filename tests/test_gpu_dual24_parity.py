@@ -77,7 +77,8 @@ def test_from_x0_dual24_bitexact(oracle, solver):
     assert np.array_equal(K0, ref["K0"]) and np.array_equal(P0, ref["P0"]) and np.array_equal(cost, ref["cost"])
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(max_iter=4), dict(u_min=0.5, u_max=4.0), dict(u_min=1.5, u_max=3.2, max_iter=20)])
+@pytest.mark.parametrize("kw", [dict(), dict(max_iter=4), dict(u_min=0.5, u_max=4.0), dict(u_min=1.5, u_max=3.2, max_iter=20),
+                                dict(reg_schedule=1, reg0=0.5, max_iter=25), dict(reg_schedule=1, u_min=1.5, u_max=3.2, max_iter=20)])
 def test_slq_dual24_bitexact(oracle, solver, kw):
     from noc_b200 import capi
     batch, N = 9, 30
@@ -90,7 +91,8 @@ def test_slq_dual24_bitexact(oracle, solver, kw):
     cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
     aidx = np.full((batch, prob.max_iter), -7, dtype=np.int32)
     solver.slq_solve_batch(prob, batch, x0, xg, qr, x=x, u=u, K=K, cost=cost, iters=iters, alpha_idx=aidx, status=status)
-    opts = oracle.slq_opts(M, N, max_iter=prob.max_iter, u_min=prob.u_min, u_max=prob.u_max)
+    opts = oracle.slq_opts(M, N, max_iter=prob.max_iter, u_min=prob.u_min, u_max=prob.u_max, reg0=prob.reg0,
+                           reg_schedule=prob.reg_schedule)
     ref = oracle.slq_batch(opts, x0, xg, qr, want_traj=True, want_K=True)
     assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
     assert np.array_equal(aidx, ref["alpha_idx"]) and np.array_equal(cost, ref["cost"])

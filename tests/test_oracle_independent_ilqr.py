@@ -76,8 +76,23 @@ def _box_qp_bvls(H, g, lo, hi):
     return k, r.active_mask != 0
 
 
-def _numpy_ilqr(f, x0, xg, uh, Q, R, Qf, N, box=None, tol=1e-8, max_iter=50, n_alpha=11, armijo=1e-4):
+def _numpy_ilqr(f, x0, xg, uh, Q, R, Qf, N, box=None, tol=1e-8, max_iter=50, n_alpha=11, armijo=1e-4, adaptive=False,
+                mu0=0.0):
+    """adaptive = the Tassa-style schedule of DESIGN.md §2.4c (mu raised on failed factorisations / line searches,
+    lowered after accepted steps); rejected iterations are recorded as -2."""
     n, m = x0.size, uh.size
+    mu, delta = mu0, 1.0
+
+    def increase():
+        nonlocal mu, delta
+        delta = max(2.0, delta * 2.0)
+        mu = max(1e-6, mu * delta)
+
+    def decrease():
+        nonlocal mu, delta
+        delta = min(0.5, delta / 2.0)
+        mu = mu * delta if mu * delta >= 1e-6 else 0.0
+
     step = lambda x, u: x + DT * f(x, u)
     clamp = (lambda u: np.minimum(np.maximum(u, box[0]), box[1])) if box else (lambda u: u)
 
@@ -105,8 +120,8 @@ def _numpy_ilqr(f, x0, xg, uh, Q, R, Qf, N, box=None, tol=1e-8, max_iter=50, n_a
             Qu = R @ (us[k] - uh) + B.T @ Vx
             Qxx = Q + A.T @ Vxx @ A
             Qux = B.T @ Vxx @ A
-            Quu = R + B.T @ Vxx @ B
-            np.linalg.cholesky(Quu)                       # positive definite: no regularisation on these problems
+            Quu = R + B.T @ Vxx @ B + mu * np.eye(m)
+            np.linalg.cholesky(Quu)                       # positive definite: no factorisation retries on these problems
             kk = -np.linalg.solve(Quu, Qu)
             KK = -np.linalg.solve(Quu, Qux)
             if box is not None:
@@ -135,8 +150,16 @@ def _numpy_ilqr(f, x0, xg, uh, Q, R, Qf, N, box=None, tol=1e-8, max_iter=50, n_a
                 accepted = j
                 break
         if accepted is None:
-            return J, it + 1, taken, 3
+            if not adaptive:
+                return J, it + 1, taken, 3
+            increase()
+            if mu > 1e6:
+                return J, it + 1, taken, 3
+            taken.append(-2)
+            continue
         taken.append(accepted)
+        if adaptive:
+            decrease()
         rel = (J - Jn) / max(J, 1e-12)
         xs, us, J = xn, un, Jn
         if rel < tol:
@@ -144,18 +167,22 @@ def _numpy_ilqr(f, x0, xg, uh, Q, R, Qf, N, box=None, tol=1e-8, max_iter=50, n_a
     return J, max_iter, taken, 2
 
 
-def _compare(oracle, model, N, count, seed, box=None, max_iter=50):
+def _compare(oracle, model, N, count, seed, box=None, max_iter=50, adaptive=False, mu0=0.0, pick=None):
     n, m = pb.dims(model)
     Q, R, Qf = pb.default_weights(model)
     qr = pb.pack_qrqf(Q, R, Qf)
     f = _quad_f if model == pb.MODEL_QUAD12 else _dual_f
     xs = pb.hover_state(count, model=model)
     xg = pb.sample_goals(count, seed=seed, model=model)
+    if pick is not None:      # a few named instances of a larger sample
+        xs, xg, count = xs[pick], xg[pick], len(pick)
     kw = dict(u_min=box[0], u_max=box[1]) if box else {}
-    ref = oracle.slq_batch(oracle.slq_opts(model, N, max_iter=max_iter, **kw), xs, xg, qr, want_traj=False)
+    ref = oracle.slq_batch(oracle.slq_opts(model, N, max_iter=max_iter, reg_schedule=int(adaptive), reg0=mu0, **kw), xs, xg, qr,
+                           want_traj=False)
     worst = 0.0
     for b in range(count):
-        J, iters, alphas, status = _numpy_ilqr(f, xs[b], xg[b], pb.hover_input(model), Q, R, Qf, N, box=box, max_iter=max_iter)
+        J, iters, alphas, status = _numpy_ilqr(f, xs[b], xg[b], pb.hover_input(model), Q, R, Qf, N, box=box, max_iter=max_iter,
+                                               adaptive=adaptive, mu0=mu0)
         assert status == ref["status"][b], (b, status, ref["status"][b])
         assert iters == ref["iters"][b], (b, iters, ref["iters"][b])
         assert alphas == [int(a) for a in ref["alpha_idx"][b][:iters]], b
@@ -209,3 +236,17 @@ def test_survey_sampler_states_slq_vs_independent_numpy_ilqr(oracle):
         assert (status, iters) == (ref["status"][b], ref["iters"][b]), b
         assert alphas == [int(a) for a in ref["alpha_idx"][b][:iters]], b
         assert abs(J - ref["cost"][b]) <= 1e-9 * abs(ref["cost"][b]), b
+
+
+def test_adaptive_regularisation_vs_independent_numpy_ilqr(oracle):
+    """DESIGN.md §2.4c (NOC_REG_ADAPTIVE) restated in numpy: started from mu0 = 1 the schedule has to walk mu down
+    (1 -> 0.5 -> 0.125 -> ... -> 0) over the accepted steps; under the tight input box some line searches fail and are
+    repeated with a larger mu (-2 entries).  Same counts / step indices / status, cost to 1e-9."""
+    worst, ref = _compare(oracle, pb.MODEL_QUAD12, N=60, count=6, seed=5150, adaptive=True, mu0=1.0, max_iter=40)
+    fixed = oracle.slq_batch(oracle.slq_opts(0, 60, max_iter=40, reg0=1.0), pb.hover_state(6), pb.sample_goals(6, seed=5150),
+                             pb.pack_qrqf(*pb.default_weights()), want_traj=False)
+    assert ref["iters"].sum() < fixed["iters"].sum()      # a mu that never comes down needs more iterations
+    # instances of a boxed waypoint sample in which a line search fails and is repeated with a larger mu
+    _, ref = _compare(oracle, pb.MODEL_QUAD12, N=60, count=512, seed=33, box=(0.0, 4.0), adaptive=True, max_iter=50,
+                      pick=[284, 217, 252])
+    assert (ref["alpha_idx"] == -2).any(axis=1).all() and np.all(ref["status"] == 0)
