@@ -69,7 +69,12 @@ typedef enum {
 
 enum {
   NOC_FLAG_NONE = 0,
-  NOC_FLAG_ASYNC = 1       /* do not synchronise before returning (all pointers must be device pointers) */
+  NOC_FLAG_ASYNC = 1,      /* do not synchronise before returning (all pointers must be device pointers) */
+  NOC_FLAG_TIME_PARALLEL = 2 /* noc_lqr_solve_batch / noc_lqr_solve_from_x0 / noc_lqr_solve_along, n=12, m=4, A_THEN_B records:
+                              time-parallel Riccati sweep — the horizon is cut into chunks that are swept
+                              concurrently and glued by an associative scan: the latency path for SMALL batches (a call is
+                              ~N/6 dependent steps deep instead of N; one CTA per instance).  Different association of the
+                              arithmetic: results agree with the sequential sweep to ~1e-12 relative, not bitwise. */
 };
 
 typedef struct {

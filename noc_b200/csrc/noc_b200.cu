@@ -21,6 +21,7 @@
 #include "riccati12.cuh"
 #include "riccati24.cuh"
 #include "riccati_generic.cuh"
+#include "riccati_scan.cuh"
 #include "slq_kernels.cuh"
 
 namespace {
@@ -379,6 +380,42 @@ int build_w12(noc_ctx* ctx, const double* dQRQf, bool dare, const double** W, co
   return NOC_OK;
 }
 
+// Time-parallel sweep (NOC_FLAG_TIME_PARALLEL, riccati_scan.cuh): one CTA per instance, its warps own chunks of the
+// horizon.  The chunk plan minimises the depth of the dependent chain under a three-constant cost model (microseconds
+// per phase-A step, phase-C step and boundary solve of a lone warp, measured on B200: tools/latency_probe.py): chunks
+// 0..C-2 take `len` steps, the last one — which only runs plain steps while the others also fold their interval
+// elements — takes the rest.
+void plan_time_parallel(int N, int* chunks, int* len) {
+  const double tA = 1.0, tC = 0.65, tB = 2.5;
+  double best = 1e300;
+  *chunks = 1; *len = N;
+  for (int C = 1; C <= TP_MAX_CHUNKS; ++C) {
+    if (C == 1) { const double c1 = N * tC; if (c1 < best) { best = c1; *chunks = 1; *len = N; } continue; }
+    for (int L = 1; (C - 1) * L < N; ++L) {
+      const int last = N - (C - 1) * L;
+      const double cost = std::max(L * tA, last * tC) + (C - 1) * tB + L * tC;
+      if (cost < best) { best = cost; *chunks = C; *len = L; }
+    }
+  }
+}
+
+int launch_ric12_tp(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* dAB, const double* W, const double* Qf,
+                    const double* dx0, double* dK, double* dK0, double* dP0, double* dcost, int32_t* dstatus) {
+  RicTpArgs a{};
+  a.AB = dAB; a.W = W; a.Qf = Qf; a.x0 = dx0; a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
+  a.batch = batch; a.N = p->N;
+  plan_time_parallel(p->N, &a.chunks, &a.len);
+  const size_t smem = ric_tp_smem_bytes(a.chunks);
+  int rc = configure_kernel(ctx, (const void*)k_ric12_tp, ric_tp_smem_bytes(TP_MAX_CHUNKS), false);
+  if (rc) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+    k_ric12_tp<<<(unsigned)batch, a.chunks * 32, smem, ctx->stream>>>(a);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  return NOC_OK;
+}
+
 // device-pointer core of the n=12 sweep
 int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* dAB, const double* dQRQf,
                  const double* dx0, double* dK, double* dK0, double* dP0, double* dcost, int32_t* dstatus) {
@@ -388,6 +425,10 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   a.AB = dAB; a.x0 = dx0;
   a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
   a.batch = batch; a.N = p->N;
+  if (p->flags & NOC_FLAG_TIME_PARALLEL) {
+    if (p->layout != NOC_LAYOUT_A_THEN_B) return fail(ctx, NOC_ERR_UNSUPPORTED, "NOC_FLAG_TIME_PARALLEL: A_THEN_B records only");
+    return launch_ric12_tp(ctx, p, batch, dAB, a.W, a.Qf, dx0, dK, dK0, dP0, dcost, dstatus);
+  }
   return launch_ric12_layout<RIC_LQR>(ctx, p->layout, a);
 }
 
@@ -396,6 +437,8 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
 int lqr_batch_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, bool generic, const double* dAB,
                      const double* dQ, int qr_per_instance, const double* dx0, double* dK, double* dK0, double* dP0,
                      double* dcost, int32_t* dstatus) {
+  if ((p->flags & NOC_FLAG_TIME_PARALLEL) && (generic || p->n != 12))
+    return fail(ctx, NOC_ERR_UNSUPPORTED, "NOC_FLAG_TIME_PARALLEL: n=12, m=4 with shared weights only");
   if (generic) {
     RicGenArgs g{};
     g.AB = dAB; g.QRQf = dQ; g.x0 = dx0; g.K = dK; g.K0 = dK0; g.P0 = dP0; g.cost = dcost; g.status = dstatus;
@@ -486,11 +529,60 @@ int lqr_batch_host_pipeline(noc_ctx* ctx, const noc_problem_t* p, int64_t batch,
   return NOC_OK;
 }
 
+// NOC_FLAG_TIME_PARALLEL on the from-x0 / along entry points (small batches): nominal rollout, time-parallel
+// linearisation into a record scratch, time-parallel sweep — three launches, each a short dependent chain.
+int from_x0_time_parallel(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* ubar,
+                          const double* QRQf, double* xbar_out, double* K, double* K0, double* P0, double* cost,
+                          int32_t* status) {
+  int rc;
+  NOC_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t B = (size_t)batch, n = 12, m = 4, N = p->N;
+  if (sizeof(double) * B * N * R12_REC > ((size_t)8 << 30))
+    return fail(ctx, NOC_ERR_UNSUPPORTED, "NOC_FLAG_TIME_PARALLEL is the small-batch latency path (record scratch would exceed 8 GB)");
+  const void *dx0, *dQ, *dub;
+  void *dK, *dK0, *dP0, *dcost, *dstatus, *dxout, *dxbar, *dAB;
+  if ((rc = stage_in(ctx, 0, x0, sizeof(double) * B * n, &dx0))) return rc;
+  if ((rc = stage_in(ctx, 1, QRQf, sizeof(double) * (2 * n * n + m * m), &dQ))) return rc;
+  if ((rc = stage_in(ctx, 2, ubar, sizeof(double) * B * N * m, &dub))) return rc;
+  if ((rc = stage_out(ctx, 5, xbar_out, sizeof(double) * B * (N + 1) * n, &dxout))) return rc;
+  if ((rc = stage_out(ctx, 0, K, sizeof(double) * B * N * m * n, &dK))) return rc;
+  if ((rc = stage_out(ctx, 1, K0, sizeof(double) * B * m * n, &dK0))) return rc;
+  if ((rc = stage_out(ctx, 2, P0, sizeof(double) * B * n * n, &dP0))) return rc;
+  if ((rc = stage_out(ctx, 3, cost, sizeof(double) * B, &dcost))) return rc;
+  if ((rc = stage_out(ctx, 4, status, sizeof(int32_t) * B, &dstatus))) return rc;
+  dxbar = dxout;
+  if (!dxbar && (rc = scratch(ctx, SCR_XBAR, sizeof(double) * B * (N + 1) * n, &dxbar))) return rc;
+  if ((rc = scratch(ctx, SCR_AB, sizeof(double) * B * N * R12_REC, &dAB))) return rc;
+  const double *W, *Qf;
+  if ((rc = build_w12(ctx, (const double*)dQ, false, &W, &Qf))) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_ROLLOUT);
+    k_rollout_open_loop<0><<<(unsigned)((B + 31) / 32), 32, 0, ctx->stream>>>((const double*)dx0, (const double*)dub, (double*)dxbar, (long long)B, p->N,
+                                                                             p->dt, (long long)((N + 1) * n), (long long)n);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  {
+    const long long total = (long long)B * p->N;
+    LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+    k_linearize<0><<<(unsigned)((total + 127) / 128), 128, 0, ctx->stream>>>((const double*)dxbar, (const double*)dub, (double*)dAB, (long long)B, p->N,
+                                                                           p->dt, NOC_LAYOUT_A_THEN_B, nullptr);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  if ((rc = launch_ric12_tp(ctx, p, batch, (const double*)dAB, W, Qf, (const double*)dx0, (double*)dK, (double*)dK0, (double*)dP0,
+                            (double*)dcost, (int32_t*)dstatus)))
+    return rc;
+  return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
+}
+
 template <int MODEL>
 int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* ubar,
                  const double* QRQf, double* xbar_out, double* K, double* K0, double* P0, double* cost,
                  int32_t* status) {
   int rc;
+  if (p->flags & NOC_FLAG_TIME_PARALLEL) {
+    if (MODEL != 0) return fail(ctx, NOC_ERR_UNSUPPORTED, "NOC_FLAG_TIME_PARALLEL: n=12, m=4 only");
+    return from_x0_time_parallel(ctx, p, batch, x0, ubar, QRQf, xbar_out, K, K0, P0, cost, status);
+  }
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t B = (size_t)batch, n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, N = p->N, rec = n * n + n * m;
   const void *dx0, *dQ, *dub;
