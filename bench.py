@@ -468,6 +468,33 @@ def _run_noc(args):
         survey = {"value": B / sms * 1e3, "unit": UNIT, "ms_per_step": sms, "status_not_ok": int((d_status != 0).sum().item()),
                   "what": "the headline sweep on SURVEY.md 8d's literal inputs: std::mt19937_64(0x4E4F43 + instance), body rates "
                           "U(-0.5,0.5) (the default sampler uses U(-0.2,0.2))"}
+    # ---- the sweep with its 12x12x16 products on the FP64 tensor cores (DMMA), timed on the headline workload: the
+    # warp-per-instance recursion of riccati_scan.cuh, one chunk (no scan), A_k,B_k and K_k in HBM as for `value`
+    dmma = None
+    if world == 1 and not args.no_extra:
+        dmma = {}
+        p_tp = capi.problem(capi.MODEL_LTV_USER, N, flags=capi.FLAG_ASYNC | capi.FLAG_TIME_PARALLEL)
+        solver.set_option(capi.OPT_TIME_PARALLEL_CHUNKS, 1)
+        for name, flag in (("dmma", 0), ("dfma", 1)):
+            solver.set_option(capi.OPT_TIME_PARALLEL_DFMA, flag)
+            fn = lambda: solver.lqr_solve_batch(p_tp, B, d_AB, d_qr, x0dev=d_x0, K=d_K, K0=d_K0, cost=d_cost, status=d_status)
+            fn()
+            torch.cuda.synchronize()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record(stream)
+            for _ in range(3):
+                fn()
+            s1.record(stream)
+            torch.cuda.synchronize()
+            tms = s0.elapsed_time(s1) / 3
+            dmma[name] = {"ms_per_step": tms, "value": B / tms * 1e3, "unit": UNIT,
+                          "hbm_frac": B * N * BYTES_PER_STEP / (tms * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"]}
+        solver.set_option(capi.OPT_TIME_PARALLEL_DFMA, 0)
+        solver.set_option(capi.OPT_TIME_PARALLEL_CHUNKS, 0)
+        dmma["what"] = ("k_ric12_tp<DMMA> vs <DFMA>, chunks = 1: one warp per instance, G = P F and H = W + F'G as "
+                        "mma.sync.m8n8k4.f64 tiles (24 per step) vs DFMA chains; same records and outputs as `value` "
+                        "(tolerance parity, tests/test_gpu_time_parallel.py); the headline k_ric12 (4 lanes per instance, "
+                        "DFMA, bitwise parity) is `value`")
     del d_AB, d_K
     torch.cuda.empty_cache()
 
@@ -524,6 +551,7 @@ def _run_noc(args):
             "pipeline_device_resident": {"value": world * B / (pipe_ms * 1e-3), "unit": UNIT, "ms_per_step": pipe_ms,
                                          "what": "x0 -> rollout -> fused linearise+sweep -> K0,cost,status, all in HBM (max over ranks)"},
             "config2_survey_inputs": survey,
+            "dmma_sweep": dmma,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,

@@ -119,7 +119,10 @@ typedef enum {
                                       batches that need more are processed in several outer chunks */
   NOC_OPT_CHUNK_WAVES = 1,         /* from-x0 pipeline with host outputs: inner chunk = this many waves of the sweep kernel */
   NOC_OPT_SINGLE_STREAM = 2,       /* 1: inner chunks on one stream (default: two alternating streams) */
-  NOC_OPT_COUNT = 3
+  NOC_OPT_TIME_PARALLEL_DFMA = 3,  /* 1: NOC_FLAG_TIME_PARALLEL sweeps form their 12x12x16 products with DFMA chains instead of
+                                      FP64 tensor-core tiles (DMMA) — the A/B measurement of DESIGN.md 3.1d */
+  NOC_OPT_TIME_PARALLEL_CHUNKS = 4,/* > 0: force that many horizon chunks (1 = plain warp-per-instance recursion); 0 = planned */
+  NOC_OPT_COUNT = 5
 } noc_option;
 int noc_set_option(noc_ctx* ctx, int option, int64_t value);
 /* Device memory for callers that do not link the CUDA runtime themselves (the C++ facade, cgo / ctypes bindings):

@@ -386,7 +386,7 @@ int build_w12(noc_ctx* ctx, const double* dQRQf, bool dare, const double** W, co
 // 0..C-2 take `len` steps, the last one — which only runs plain steps while the others also fold their interval
 // elements — takes the rest.
 void plan_time_parallel(int N, int* chunks, int* len) {
-  const double tA = 1.0, tC = 0.65, tB = 2.5;
+  const double tA = 3.5, tC = 1.15, tB = 4.8;   // measured with clock64 in the kernel (eight warps of a CTA on one SM), microseconds
   double best = 1e300;
   *chunks = 1; *len = N;
   for (int C = 1; C <= TP_MAX_CHUNKS; ++C) {
@@ -405,12 +405,19 @@ int launch_ric12_tp(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const d
   a.AB = dAB; a.W = W; a.Qf = Qf; a.x0 = dx0; a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
   a.batch = batch; a.N = p->N;
   plan_time_parallel(p->N, &a.chunks, &a.len);
-  const size_t smem = ric_tp_smem_bytes(a.chunks);
-  int rc = configure_kernel(ctx, (const void*)k_ric12_tp, ric_tp_smem_bytes(TP_MAX_CHUNKS), false);
+  const bool dfma = ctx->opt[NOC_OPT_TIME_PARALLEL_DFMA] != 0;   // comparison build of the same kernel without tensor cores
+  if (ctx->opt[NOC_OPT_TIME_PARALLEL_CHUNKS] > 0) {               // forced plan (measurements): C chunks of equal length
+    a.chunks = (int)std::min<int64_t>(ctx->opt[NOC_OPT_TIME_PARALLEL_CHUNKS], std::min<int64_t>(TP_MAX_CHUNKS, p->N));
+    a.len = a.chunks > 1 ? std::max(1, p->N / a.chunks) : p->N;
+  }
+  const size_t smem_c = ric_tp_smem_bytes(a.chunks);
+  int rc = dfma ? configure_kernel(ctx, (const void*)k_ric12_tp<false>, ric_tp_smem_bytes(TP_MAX_CHUNKS), false)
+                : configure_kernel(ctx, (const void*)k_ric12_tp<true>, ric_tp_smem_bytes(TP_MAX_CHUNKS), false);
   if (rc) return rc;
   {
     LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
-    k_ric12_tp<<<(unsigned)batch, a.chunks * 32, smem, ctx->stream>>>(a);
+    if (dfma) k_ric12_tp<false><<<(unsigned)batch, a.chunks * 32, smem_c, ctx->stream>>>(a);
+    else k_ric12_tp<true><<<(unsigned)batch, a.chunks * 32, smem_c, ctx->stream>>>(a);
   }
   NOC_CUDA(ctx, cudaGetLastError());
   return NOC_OK;

@@ -74,6 +74,19 @@ __device__ __forceinline__ void tp_tri(int e, int& i, int& j) {
   j = r + (e - start);
 }
 
+// FP64 tensor-core tile: D(8x8) += A(8x4) B(4x8), mma.sync.m8n8k4 (SASS: DMMA).  Fragments of lane (g = lane>>2,
+// t = lane&3): a = A[g][t], b = B[t][g], {d0, d1} = D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// DMMA = true: the 12x12x16 products of the step (G = J F, H = W + F'G, the fold's A_agg [A+BK | B]) run on the FP64
+// tensor cores (24 + 12 DMMAs per step instead of ~240 DFMAs and their shared-memory operand loads).  This path is
+// tolerance-parity by construction (the scan re-associates anyway), so the fragment accumulation order is no obstacle
+// here — unlike in the bitwise sweeps of riccati12.cuh.
+template <bool DMMA>
 struct TpWarp {
   double* w;          // this warp's shared memory
   const double* Ws;   // W 16x16
@@ -104,6 +117,36 @@ struct TpWarp {
   // 6 half .. 6 half + 5; if `transposed_out` the 12x12 part of the result is ALSO stored transposed at outT
   // (outT[c*12 + r] = out[r][c]) — how A_agg is kept.
   __device__ __forceinline__ void mul12x16(const double* LT, const double* X, double* out, double* outT) {
+    if (DMMA) {
+      const int g = lane >> 2, t = lane & 3;
+      double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll
+      for (int ki = 0; ki < 3; ++ki) {
+        const double a0 = LT[(4 * ki + t) * 12 + g];                               // L[g][4ki+t]
+        const double a1 = (g < 4) ? LT[(4 * ki + t) * 12 + 8 + g] : 0.0;           // L[8+g][4ki+t], rows 12..15 are padding
+        const double b0 = X[foff(4 * ki + t, g)], b1 = X[foff(4 * ki + t, 8 + g)];
+        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+      }
+#pragma unroll
+      for (int ni = 0; ni < 2; ++ni) {
+        sts128(out + g * 16 + 8 * ni + 2 * t, acc[0][ni][0], acc[0][ni][1]);
+        if (g < 4) sts128(out + (8 + g) * 16 + 8 * ni + 2 * t, acc[1][ni][0], acc[1][ni][1]);
+      }
+      if (outT) {   // out[r][c] -> outT[c*12 + r], c < 12
+        outT[(2 * t) * 12 + g] = acc[0][0][0];
+        outT[(2 * t + 1) * 12 + g] = acc[0][0][1];
+        if (t < 2) { outT[(8 + 2 * t) * 12 + g] = acc[0][1][0]; outT[(9 + 2 * t) * 12 + g] = acc[0][1][1]; }
+        if (g < 4) {
+          outT[(2 * t) * 12 + 8 + g] = acc[1][0][0];
+          outT[(2 * t + 1) * 12 + 8 + g] = acc[1][0][1];
+          if (t < 2) { outT[(8 + 2 * t) * 12 + 8 + g] = acc[1][1][0]; outT[(9 + 2 * t) * 12 + 8 + g] = acc[1][1][1]; }
+        }
+      }
+      return;
+    }
     const int c = lane & 15, r0 = 6 * (lane >> 4);
     double acc[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -133,7 +176,30 @@ struct TpWarp {
     const int c = lane & 15, half = lane >> 4;
     mul12x16(w + TP_JS, Fs, Gs, nullptr);   // J symmetric: row l of J = column l
     __syncwarp();
-    {   // H = W + F'G: column c, rows 8*half .. +7
+    if (DMMA) {   // H = W + F'G, 16x16x12: A fragments F'[8mi+g][4ki+t] = F[4ki+t][8mi+g], B fragments G[4ki+t][8ni+g]
+      const int g = lane >> 2, t = lane & 3;
+      double acc[2][2][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) {
+          const double2 v = lds128(Ws + (8 * mi + g) * 16 + 8 * ni + 2 * t);
+          acc[mi][ni][0] = v.x; acc[mi][ni][1] = v.y;
+        }
+#pragma unroll
+      for (int ki = 0; ki < 3; ++ki) {
+        const double a0 = Fs[foff(4 * ki + t, g)], a1 = Fs[foff(4 * ki + t, 8 + g)];
+        const double b0 = Gs[(4 * ki + t) * 16 + g], b1 = Gs[(4 * ki + t) * 16 + 8 + g];
+        dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+        dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+        dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+        dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 2; ++ni) sts128(Hs + (8 * mi + g) * 16 + 8 * ni + 2 * t, acc[mi][ni][0], acc[mi][ni][1]);
+    } else {   // H = W + F'G: column c, rows 8*half .. +7
       double acc[8];
       const int i0 = 8 * half;
 #pragma unroll
@@ -333,6 +399,7 @@ struct TpWarp {
   }
 };
 
+template <bool DMMA>
 __global__ void __launch_bounds__(TP_MAX_CHUNKS * 32, 1) k_ric12_tp(const RicTpArgs a) {
   extern __shared__ __align__(128) double smem[];
   double* Ws = smem;
@@ -342,7 +409,7 @@ __global__ void __launch_bounds__(TP_MAX_CHUNKS * 32, 1) k_ric12_tp(const RicTpA
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int C = a.chunks, N = a.N;
   const long long b = blockIdx.x;
-  TpWarp t{smem + TP_CTA_DOUBLES + warp * TP_WARP_DOUBLES, Ws, lane};
+  TpWarp<DMMA> t{smem + TP_CTA_DOUBLES + warp * TP_WARP_DOUBLES, Ws, lane};
   t.init_maps();
   for (int i = threadIdx.x; i < 256; i += blockDim.x) Ws[i] = a.W[i];
   for (int i = threadIdx.x; i < 144; i += blockDim.x) Qfs[i] = a.Qf[i];

@@ -28,9 +28,14 @@ def _traj_AB(oracle, x0, N):
     return np.stack([oracle.linearize_traj(0, N, 0.02, oracle.rollout_open_loop(0, N, 0.02, x, ubar), ubar, 0) for x in x0])
 
 
+@pytest.mark.parametrize("dfma,chunks", [(0, 0), (1, 0), (0, 1), (0, 5)])
 @pytest.mark.parametrize("batch,N", [(1, 1), (2, 2), (3, 7), (5, 23), (64, 100), (9, 200), (2, 517)])
-def test_time_parallel_sweep_matches_the_sequential_oracle(oracle, solver, batch, N):
+def test_time_parallel_sweep_matches_the_sequential_oracle(oracle, solver, batch, N, dfma, chunks):
+    """dfma = 1: the same kernel with DFMA chains instead of FP64 tensor-core tiles; chunks: forced plan (1 = the plain
+    warp-per-instance recursion, no scan)."""
     from noc_b200 import capi
+    solver.set_option(capi.OPT_TIME_PARALLEL_DFMA, dfma)
+    solver.set_option(capi.OPT_TIME_PARALLEL_CHUNKS, chunks)
     qr = pb.pack_qrqf(*pb.default_weights())
     x0 = pb.sample_x0(batch, seed=4000 + N)
     AB = _traj_AB(oracle, x0, N)
@@ -47,6 +52,8 @@ def test_time_parallel_sweep_matches_the_sequential_oracle(oracle, solver, batch
     assert np.max(np.abs(cost - ref["cost"]) / np.abs(ref["cost"])) < RTOL
     assert np.array_equal(P0, P0.transpose(0, 2, 1))
     assert np.array_equal(K[:, 0], K0)
+    solver.set_option(capi.OPT_TIME_PARALLEL_DFMA, 0)
+    solver.set_option(capi.OPT_TIME_PARALLEL_CHUNKS, 0)
 
 
 def test_time_parallel_dense_weights_and_random_ltv(oracle, solver):

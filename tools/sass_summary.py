@@ -24,9 +24,10 @@ def main():
         if m:
             cur = m.group(1)
             continue
-        m = re.search(r"REG:(\d+).*?SHARED:(\d+).*?LOCAL:(\d+)", line)
+        m = re.search(r"REG:(\d+)", line)
         if m and cur:
-            regs[cur] = (int(m.group(1)), int(m.group(2)), int(m.group(3)))
+            g = lambda key: int((re.search(key + r":(\d+)", line) or [0, 0])[1])
+            regs[cur] = (int(m.group(1)), g("SHARED"), g("STACK") + g("LOCAL"))
     counts, order, cur = {}, [], None
     for line in sass.splitlines():
         m = re.match(r"\s*Function : (\S+)", line)
@@ -42,7 +43,7 @@ def main():
                     counts[cur][w] += 1
     dm = demangle(order)
     print(f"# cuobjdump -sass {os.path.relpath(SO, ROOT)}  (sm_100a only; counts are static instructions per kernel)")
-    print("# kernel | regs | static smem | local bytes/thread | total | " + " | ".join(WATCH))
+    print("# kernel | regs | static smem | stack+local bytes/thread | total | " + " | ".join(WATCH))
     for k in sorted(order, key=lambda k: dm[k]):
         r = regs.get(k, ("?", "?", "?"))
         name = re.sub(r"^void ", "", dm[k]); name = re.sub(r"\(.*$", "", name)
