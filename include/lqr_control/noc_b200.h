@@ -122,7 +122,9 @@ typedef enum {
   NOC_OPT_TIME_PARALLEL_DFMA = 3,  /* 1: NOC_FLAG_TIME_PARALLEL sweeps form their 12x12x16 products with DFMA chains instead of
                                       FP64 tensor-core tiles (DMMA) — the A/B measurement of DESIGN.md 3.1d */
   NOC_OPT_TIME_PARALLEL_CHUNKS = 4,/* > 0: force that many horizon chunks (1 = plain warp-per-instance recursion); 0 = planned */
-  NOC_OPT_COUNT = 5
+  NOC_OPT_NO_SMALL_BATCH_KERNEL = 5, /* 1: noc_lqr_solve_batch keeps the 8-instances-per-warp sweep also for batches of at most two
+                                      instances per SM (default: those run one instance per warp, bit-identical, ~1.6x sooner) */
+  NOC_OPT_COUNT = 6
 } noc_option;
 int noc_set_option(noc_ctx* ctx, int option, int64_t value);
 /* Device memory for callers that do not link the CUDA runtime themselves (the C++ facade, cgo / ctypes bindings):

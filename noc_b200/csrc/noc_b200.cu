@@ -399,14 +399,17 @@ void plan_time_parallel(int N, int* chunks, int* len) {
   }
 }
 
+// `bitwise`: the plain warp-per-instance recursion (one chunk, DFMA chains) — every chain in the spec's order, so the
+// results are bit-identical to k_ric12 and the oracle; used for small batches without the caller asking (lqr12_device).
 int launch_ric12_tp(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* dAB, const double* W, const double* Qf,
-                    const double* dx0, double* dK, double* dK0, double* dP0, double* dcost, int32_t* dstatus) {
+                    const double* dx0, double* dK, double* dK0, double* dP0, double* dcost, int32_t* dstatus, bool bitwise = false) {
   RicTpArgs a{};
   a.AB = dAB; a.W = W; a.Qf = Qf; a.x0 = dx0; a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
   a.batch = batch; a.N = p->N;
   plan_time_parallel(p->N, &a.chunks, &a.len);
-  const bool dfma = ctx->opt[NOC_OPT_TIME_PARALLEL_DFMA] != 0;   // comparison build of the same kernel without tensor cores
-  if (ctx->opt[NOC_OPT_TIME_PARALLEL_CHUNKS] > 0) {               // forced plan (measurements): C chunks of equal length
+  bool dfma = ctx->opt[NOC_OPT_TIME_PARALLEL_DFMA] != 0;   // comparison build of the same kernel without tensor cores
+  if (bitwise) { a.chunks = 1; a.len = p->N; dfma = true; }
+  else if (ctx->opt[NOC_OPT_TIME_PARALLEL_CHUNKS] > 0) {          // forced plan (measurements): C chunks of equal length
     a.chunks = (int)std::min<int64_t>(ctx->opt[NOC_OPT_TIME_PARALLEL_CHUNKS], std::min<int64_t>(TP_MAX_CHUNKS, p->N));
     a.len = a.chunks > 1 ? std::max(1, p->N / a.chunks) : p->N;
   }
@@ -436,6 +439,10 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
     if (p->layout != NOC_LAYOUT_A_THEN_B) return fail(ctx, NOC_ERR_UNSUPPORTED, "NOC_FLAG_TIME_PARALLEL: A_THEN_B records only");
     return launch_ric12_tp(ctx, p, batch, dAB, a.W, a.Qf, dx0, dK, dK0, dP0, dcost, dstatus);
   }
+  // Small batches: the sweep is a latency chain whatever the mapping, and a warp that owns ONE instance steps in about
+  // half the time of a warp that owns eight (1,700 vs 3,600 clk).  Same chains, same order, same bits.
+  if (p->layout == NOC_LAYOUT_A_THEN_B && batch <= 2LL * ctx->sm_count && !ctx->opt[NOC_OPT_NO_SMALL_BATCH_KERNEL])
+    return launch_ric12_tp(ctx, p, batch, dAB, a.W, a.Qf, dx0, dK, dK0, dP0, dcost, dstatus, true);
   return launch_ric12_layout<RIC_LQR>(ctx, p->layout, a);
 }
 
@@ -540,7 +547,7 @@ int lqr_batch_host_pipeline(noc_ctx* ctx, const noc_problem_t* p, int64_t batch,
 // linearisation into a record scratch, time-parallel sweep — three launches, each a short dependent chain.
 int from_x0_time_parallel(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* x0, const double* ubar,
                           const double* QRQf, double* xbar_out, double* K, double* K0, double* P0, double* cost,
-                          int32_t* status) {
+                          int32_t* status, bool bitwise) {
   int rc;
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t B = (size_t)batch, n = 12, m = 4, N = p->N;
@@ -576,7 +583,7 @@ int from_x0_time_parallel(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
   }
   NOC_CUDA(ctx, cudaGetLastError());
   if ((rc = launch_ric12_tp(ctx, p, batch, (const double*)dAB, W, Qf, (const double*)dx0, (double*)dK, (double*)dK0, (double*)dP0,
-                            (double*)dcost, (int32_t*)dstatus)))
+                            (double*)dcost, (int32_t*)dstatus, bitwise)))
     return rc;
   return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
 }
@@ -588,8 +595,12 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   int rc;
   if (p->flags & NOC_FLAG_TIME_PARALLEL) {
     if (MODEL != 0) return fail(ctx, NOC_ERR_UNSUPPORTED, "NOC_FLAG_TIME_PARALLEL: n=12, m=4 only");
-    return from_x0_time_parallel(ctx, p, batch, x0, ubar, QRQf, xbar_out, K, K0, P0, cost, status);
+    return from_x0_time_parallel(ctx, p, batch, x0, ubar, QRQf, xbar_out, K, K0, P0, cost, status, false);
   }
+  // small batches of the quadrotor: rollout -> time-parallel linearisation -> one instance per warp (bit-identical to the
+  // fused 8-per-warp sweep: the records are the same bits and the pruned products are exact zeros)
+  if (MODEL == 0 && batch <= 2LL * ctx->sm_count && !ctx->opt[NOC_OPT_NO_SMALL_BATCH_KERNEL])
+    return from_x0_time_parallel(ctx, p, batch, x0, ubar, QRQf, xbar_out, K, K0, P0, cost, status, true);
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t B = (size_t)batch, n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, N = p->N, rec = n * n + n * m;
   const void *dx0, *dQ, *dub;

@@ -431,6 +431,7 @@ __global__ void __launch_bounds__(TP_MAX_CHUNKS * 32, 1) k_ric12_tp(const RicTpA
   };
   double* Js = t.w + TP_JS;
   bool failed = false;
+  int kfail = -1;   // one chunk: the step at which the factorisation first failed (the sequential sweep's NaN rule)
   Ldl4 ch;
 
   // ---------------- phase A
@@ -448,6 +449,7 @@ __global__ void __launch_bounds__(TP_MAX_CHUNKS * 32, 1) k_ric12_tp(const RicTpA
     // the last chunk runs the true recursion: its gains are final
     double* kout = (last && Kg) ? Kg + (size_t)k * 48 : nullptr;
     failed |= t.step(buf, kout, ch);
+    if (failed && kfail < 0) kfail = k;
     if (last && k == 0 && a.K0 && lane < 12) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) a.K0[(size_t)b * 48 + q * 12 + lane] = t.w[TP_KS + q * 12 + lane];
@@ -494,16 +496,22 @@ __global__ void __launch_bounds__(TP_MAX_CHUNKS * 32, 1) k_ric12_tp(const RicTpA
     if (a.P0)
       for (int e = lane; e < 144; e += 32) a.P0[(size_t)b * 144 + e] = Js[e];
     if (a.cost && a.x0) {
+      // the spec's order: row chains r_i = P0[i][:] x0, then the chain over i, then the half
       const double* x = a.x0 + (size_t)b * 12;
-      double r = 0.0;
+      double* rs = t.w + TP_KS;
       if (lane < 12) {
+        double r = 0.0;
 #pragma unroll
         for (int j = 0; j < 12; ++j) r = fmad(Js[lane * 12 + j], x[j], r);
-        r = r * x[lane];
+        rs[lane] = r;
       }
+      __syncwarp();
+      if (lane == 0) {
+        double cc = 0.0;
 #pragma unroll
-      for (int off = 8; off > 0; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-      if (lane == 0) a.cost[b] = 0.5 * r;
+        for (int i = 0; i < 12; ++i) cc = fmad(x[i], rs[i], cc);
+        a.cost[b] = 0.5 * cc;
+      }
     }
   }
   if (lane == 0) ready[TP_MAX_CHUNKS + c] = failed ? 1 : 0;
@@ -512,8 +520,10 @@ __global__ void __launch_bounds__(TP_MAX_CHUNKS * 32, 1) k_ric12_tp(const RicTpA
   for (int q = 0; q < C; ++q) any_failed |= ready[TP_MAX_CHUNKS + q] != 0;
   if (any_failed) {   // NOT_PD anywhere (or a singular boundary system): every output of the instance is NaN
     const double nanv = qnan();
+    // one chunk = the plain recursion: the gains of the steps after the failing one (k > kfail) are valid, as in k_ric12
+    const int nan_steps = (C == 1) ? kfail + 1 : N;
     if (Kg)
-      for (int e = threadIdx.x; e < N * 48; e += blockDim.x) Kg[e] = nanv;
+      for (int e = threadIdx.x; e < nan_steps * 48; e += blockDim.x) Kg[e] = nanv;
     if (a.K0)
       for (int e = threadIdx.x; e < 48; e += blockDim.x) a.K0[(size_t)b * 48 + e] = nanv;
     if (a.P0)

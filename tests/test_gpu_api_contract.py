@@ -121,14 +121,20 @@ def test_mixed_host_and_device_pointers_and_async(oracle, solver):
 
 def test_per_kernel_profile_counters(solver):
     from noc_b200 import capi
-    x0 = pb.sample_x0(64, seed=5)
+    x0 = pb.sample_x0(640, seed=5)
     solver.profile_reset(); solver.profile_enable(True)
     n0 = solver.launch_count
-    solver.lqr_solve_from_x0(capi.problem(0, 10), 64, x0, _qr(), cost=np.empty(64))
+    solver.lqr_solve_from_x0(capi.problem(0, 10), 640, x0, _qr(), cost=np.empty(640))
     solver.profile_enable(False)
     ms, cnt = solver.profile_read(capi.KERNEL_RICCATI)
     assert cnt == 1 and ms > 0 and solver.launch_count - n0 == 3      # rollout, weight packing, fused sweep
     assert solver.profile_read(capi.KERNEL_LINEARIZE)[1] == 0          # linearisation is fused into the sweep
+    # at most two instances per SM: the small-batch path (time-parallel linearisation + one instance per warp)
+    solver.profile_reset(); solver.profile_enable(True)
+    n0 = solver.launch_count
+    solver.lqr_solve_from_x0(capi.problem(0, 10), 64, x0[:64], _qr(), cost=np.empty(64))
+    solver.profile_enable(False)
+    assert solver.launch_count - n0 == 4 and solver.profile_read(capi.KERNEL_LINEARIZE)[1] == 1
 
 
 def test_outer_chunking_of_the_nominal_scratch(oracle):

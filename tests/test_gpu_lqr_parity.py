@@ -12,10 +12,14 @@ from noc_b200 import problems as pb
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def solver():
+@pytest.fixture(scope="module", params=[0, 1], ids=["small-batch-kernel", "eight-per-warp-kernel"])
+def solver(request):
+    """Every test of this module runs twice: batches of at most two instances per SM go to the warp-per-instance
+    recursion (k_ric12_tp<DFMA>, one chunk) by default, and to the 8-instances-per-warp sweep (k_ric12) with
+    NOC_OPT_NO_SMALL_BATCH_KERNEL — both must reproduce the oracle bit for bit."""
     from noc_b200 import capi
     s = capi.Solver(0)
+    s.set_option(capi.OPT_NO_SMALL_BATCH_KERNEL, request.param)
     yield s
     s.close()
 
