@@ -93,6 +93,9 @@ class BatchedLqr {
   noc_problem_t& problem() { return prob_; }
   // the weights' dimensions must be the problem's (the library reads Q | R | Qf with the problem's n, m)
   void setWeights(const Weights& w) { checkWeightDims(w, prob_); weights_ = w; }
+  // time-parallel sweep for small batches (NOC_FLAG_TIME_PARALLEL; n=12, m=4): ~2x shorter calls, results agree with
+  // the default sweep to ~1e-12 relative instead of bitwise
+  void setTimeParallel(bool on) { prob_.flags = on ? (prob_.flags | NOC_FLAG_TIME_PARALLEL) : (prob_.flags & ~NOC_FLAG_TIME_PARALLEL); }
   void setTimeStep(double dt) { prob_.dt = dt; }
   int stateDim() const { return prob_.n; }
   int inputDim() const { return prob_.m; }

@@ -271,6 +271,10 @@ int noc_comm_lqr_solve_from_x0(noc_comm* comm, const noc_problem_t* prob, int64_
                                const double* QRQf_dev, double* cost_all_dev, double* K0_all_dev,
                                int32_t* status_dev, noc_cost_index_t* best_dev, noc_cost_index_t* best_host);
 
+/* The chunk plan a NOC_FLAG_TIME_PARALLEL sweep of horizon N uses: `chunks` warps per instance, chunks 0 .. chunks-2 take
+ * `len` steps each, the last one the remaining N - (chunks-1)*len >= 1 (host-side function, needs no GPU).             */
+int noc_plan_time_parallel(int32_t N, int32_t* chunks, int32_t* len);
+
 /* ---- diagnostics -----------------------------------------------------------------------------------
  * The pivots' reciprocals inside the sweep use a branch-free correctly-rounded sequence valid on
  * (1e-280, 1e280); this runs it next to the IEEE division on n values so tests can compare the bits. */

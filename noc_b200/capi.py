@@ -35,7 +35,7 @@ EXPORTS = [
     "noc_argmin_cost", "noc_argmin_cost_async", "noc_comm_unique_id", "noc_comm_create_rank", "noc_comm_create_all",
     "noc_comm_destroy", "noc_comm_rank", "noc_comm_size", "noc_comm_last_error", "noc_comm_group_begin",
     "noc_comm_group_end", "noc_comm_allgather", "noc_comm_best_rollout", "noc_comm_lqr_solve_from_x0",
-    "noc_profile_enable", "noc_profile_read", "noc_profile_reset", "noc_selftest_rcp",
+    "noc_profile_enable", "noc_profile_read", "noc_profile_reset", "noc_selftest_rcp", "noc_plan_time_parallel",
 ]
 KERNEL_SETUP, KERNEL_ROLLOUT, KERNEL_LINEARIZE, KERNEL_RICCATI, KERNEL_FORWARD, KERNEL_ARGMIN = range(6)
 
@@ -292,6 +292,15 @@ class Solver:
         idx, val = C.c_int64(), C.c_double()
         self._check(self._lib.noc_argmin_cost(self._h, _f(cost, batch, "cost"), batch, C.byref(idx), C.byref(val)))
         return idx.value, val.value
+
+
+def plan_time_parallel(N: int):
+    """(chunks, len) of the time-parallel sweep's chunk plan for horizon N (host-side, no GPU needed)."""
+    c, l = C.c_int32(), C.c_int32()
+    rc = load_library().noc_plan_time_parallel(N, C.byref(c), C.byref(l))
+    if rc != OK:
+        raise NocError(rc, "noc_plan_time_parallel: N >= 1 required")
+    return c.value, l.value
 
 
 def comm_unique_id() -> bytes:

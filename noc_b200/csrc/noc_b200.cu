@@ -1363,6 +1363,14 @@ int noc_slq_solve_warm(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, cons
              : slq_impl<1>(ctx, p, batch, x0, xgoal, QRQf, u_init, x, u, K, cost, iters, alpha_idx, status);
 }
 
+int noc_plan_time_parallel(int32_t N, int32_t* chunks, int32_t* len) {
+  if (N < 1 || !chunks || !len) return NOC_ERR_BAD_ARG;
+  int c = 1, l = N;
+  plan_time_parallel(N, &c, &l);
+  *chunks = c; *len = l;
+  return NOC_OK;
+}
+
 int noc_selftest_rcp(noc_ctx* ctx, const double* x, double* y_fast, double* y_ieee, int64_t n) {
   if (!ctx) return NOC_ERR_BAD_ARG;
   if (!x || !y_fast || !y_ieee || n < 1) return fail(ctx, NOC_ERR_BAD_ARG, "x, outputs and n>=1 required");

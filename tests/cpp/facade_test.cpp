@@ -63,6 +63,18 @@ int main() {
     for (int64_t i = 1; i < B; ++i) if (rcost[i] < rcost[rb]) rb = i;
     CHECK(best.first == rb && best.second == rcost[rb]);
 
+    {  // the time-parallel sweep (NOC_FLAG_TIME_PARALLEL): same gains to north_star's 1e-9, not bitwise
+      BatchedLqr tp(ctx, N);
+      tp.setTimeParallel(true);
+      std::vector<double> tK0(B * 48), tP0(B * 144), tcost(B);
+      std::vector<int32_t> tst(B, -1);
+      tp.solveFromInitialStates(B, x0.data(), nullptr, tK0.data(), tP0.data(), tcost.data(), tst.data());
+      double worst = 0.0, scale = 0.0;
+      for (size_t i = 0; i < tK0.size(); ++i) { worst = std::max(worst, std::fabs(tK0[i] - rK0[i])); scale = std::max(scale, std::fabs(rK0[i])); }
+      CHECK(worst <= 1e-9 * scale && tst == rst);
+      for (int64_t i = 0; i < B; ++i) CHECK(std::fabs(tcost[i] - rcost[i]) <= 1e-9 * std::fabs(rcost[i]));
+    }
+
     ShardedBatchedLqr sh({0, 0, 0}, N);   // three shards (contexts) on one GPU: exercises the slicing
     std::vector<double> sK0(B * 48), sP0(B * 144), scost(B);
     std::vector<int32_t> sst(B, -1);

@@ -114,3 +114,25 @@ def test_no_link_time_nccl_dependency():
     from noc_b200 import capi
     deps = subprocess.run(["ldd", capi.LIB_PATH], capture_output=True, text=True).stdout
     assert "nccl" not in deps.lower(), deps
+
+
+def test_time_parallel_chunk_plan_invariants(lib):
+    """Host-side logic of NOC_FLAG_TIME_PARALLEL (no GPU needed): for every horizon the plan uses 1..8 chunks, every
+    chunk has at least one step, the chunks tile the horizon, short horizons are not cut at all, and the last chunk —
+    which only runs plain steps while the others also fold their interval elements — is the longest."""
+    from noc_b200 import capi
+    prev_chunks = 1
+    for N in list(range(1, 130)) + [200, 333, 517, 1000, 4096]:
+        chunks, ln = capi.plan_time_parallel(N)
+        assert 1 <= chunks <= 8 and ln >= 1
+        last = N - (chunks - 1) * ln
+        assert last >= 1
+        if chunks == 1:
+            assert ln == N
+        else:
+            assert last >= ln                       # the cheap chunk is the long one
+        if N <= 16:
+            assert chunks == 1                      # a scan cannot beat sixteen plain steps
+    assert capi.plan_time_parallel(100)[0] > 1 and capi.plan_time_parallel(200)[0] > 1
+    with pytest.raises(capi.NocError):
+        capi.plan_time_parallel(0)
