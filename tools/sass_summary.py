@@ -46,7 +46,7 @@ def main():
     print("# kernel | regs | static smem | stack+local bytes/thread | total | " + " | ".join(WATCH))
     for k in sorted(order, key=lambda k: dm[k]):
         r = regs.get(k, ("?", "?", "?"))
-        name = re.sub(r"^void ", "", dm[k]); name = re.sub(r"\(.*$", "", name)
+        name = re.sub(r"^void ", "", dm[k]).replace("(anonymous namespace)::", ""); name = re.sub(r"\(.*$", "", name)
         c = counts[k]
         print(f"{name} | {r[0]} | {r[1]} | {r[2]} | {c['total']} | " + " | ".join(str(c[w]) for w in WATCH))
 
