@@ -319,7 +319,7 @@ template <> struct Ric24Cfg<RIC_AFFINE> { static constexpr int warps = 7; };
 template <int LAYOUT, int MODE, bool FUSED, int W, bool BOX = false>
 int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a) {
   auto kern = k_ric24<LAYOUT, MODE, FUSED, W, BOX>;
-  const size_t smem = ric24_smem_bytes<MODE, FUSED>(W);
+  const size_t smem = ric24_smem_bytes<MODE, FUSED, BOX>(W);
   int rc = configure_kernel(ctx, (const void*)kern, smem, true);
   if (rc) return rc;
   const long long per_cta = 2LL * W;

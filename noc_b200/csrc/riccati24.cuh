@@ -31,7 +31,8 @@ constexpr int R24_ES = 1632;    // affine: [xbar_k - xgoal ; ubar_k - u_h]
 constexpr int R24_VS = 1664;    // affine: Vx[24]
 constexpr int R24_HU = 1688;    // affine: h_u[8]
 constexpr int R24_XG = 1696;    // affine: xgoal[24]
-constexpr int R24_STRIDE_LQR = 1602, R24_STRIDE_LQR_FUSED = 1634, R24_STRIDE_AFF = 1722;   // 16 B modulo 128 B: the two instances of a warp differ in bank quad
+constexpr int R24_QP = 1720;     // BOX: workspace of the 8x8 box QP (QP_WS_DOUBLES(8) = 112)
+constexpr int R24_STRIDE_LQR = 1602, R24_STRIDE_LQR_FUSED = 1634, R24_STRIDE_AFF = 1722, R24_STRIDE_AFF_BOX = 1834;   // 16 B modulo 32 B: the two instances of a warp differ in bank quad
 constexpr int R24_WLD = 34;                                   // padded row stride of W
 constexpr int R24_WS_DOUBLES = 32 * R24_WLD;
 constexpr int R24_QF_DOUBLES = 576;
@@ -63,14 +64,14 @@ struct Ric24Args {
   int N;
 };
 
-template <int MODE, bool FUSED>
+template <int MODE, bool FUSED, bool BOX = false>
 __host__ __device__ constexpr int r24_stride() {
-  return MODE == RIC_AFFINE ? R24_STRIDE_AFF : (FUSED ? R24_STRIDE_LQR_FUSED : R24_STRIDE_LQR);
+  return MODE == RIC_AFFINE ? (BOX ? R24_STRIDE_AFF_BOX : R24_STRIDE_AFF) : (FUSED ? R24_STRIDE_LQR_FUSED : R24_STRIDE_LQR);
 }
-template <int MODE, bool FUSED>
+template <int MODE, bool FUSED, bool BOX = false>
 inline size_t ric24_smem_bytes(int warps) {
   return sizeof(double) *
-         (size_t)(R24_WS_DOUBLES + R24_QF_DOUBLES + R24_BAR_DOUBLES + warps * 2 * r24_stride<MODE, FUSED>());
+         (size_t)(R24_WS_DOUBLES + R24_QF_DOUBLES + R24_BAR_DOUBLES + warps * 2 * r24_stride<MODE, FUSED, BOX>());
 }
 
 // M x M square-root-free Cholesky in registers (oracle: chol_lower / chol_solve_neg), fully unrolled
@@ -122,16 +123,23 @@ struct LdlReg {
   }
 };
 
-// ---- input box: the oracle's box_qp for any M, operands in local memory.  A rare, divergent path
-// (only the instances whose feed-forward leaves the box run it), kept out of line so that it does not weigh on the
-// register allocation of the sweep.  U: Quu, row-major M x M, lower triangle valid (shared memory).
+// ---- input box: the oracle's box_qp for any M.  A rare, divergent path (only the instances whose
+// feed-forward leaves the box run it), with dynamic loops, so its operands cannot live in registers.  They live in
+// SHARED memory — `ws`, a per-instance scratch of QP_WS_DOUBLES(M) doubles (R24_QP, only in the BOX instantiation's
+// slice) — not in local memory: all lanes of an instance run the QP redundantly on identical values, so every access is
+// a broadcast (one wavefront), every lane reads back what it (and, identically, its neighbours) wrote, and no
+// synchronisation is needed.  (Round 1 kept them in thread-local arrays: 16 lanes x 1 KB of L1-backed local memory
+// per instance made the boxed n=24 sweep 3.9x slower than the unconstrained one, profiles/ncu_r01_k_ric12_affine_box.txt.)
+// U: Quu, row-major M x M, lower triangle valid (shared memory).
+template <int M>
+__host__ __device__ constexpr int QP_WS_DOUBLES() { return M * M + 6 * M; }
 template <int M>
 __device__ __forceinline__ void ldl_mask(const double* U, const bool (&cl)[M], double* Um) {
   for (int a = 0; a < M; ++a)
     for (int b = 0; b <= a; ++b) Um[a * M + b] = (cl[a] || cl[b]) ? (a == b ? 1.0 : 0.0) : U[a * M + b];
 }
 template <int M>
-__device__ __forceinline__ double qp_eval_gen(const double* U, const double (&g)[M], const double (&x)[M], double (&r)[M]) {
+__device__ __forceinline__ double qp_eval_gen(const double* U, const double (&g)[M], const double* x, double* r) {
   for (int a = 0; a < M; ++a) {
     double s = 0.0;
     for (int b = 0; b < M; ++b) s = fmad(b <= a ? U[a * M + b] : U[b * M + a], x[b], s);
@@ -143,31 +151,46 @@ __device__ __forceinline__ double qp_eval_gen(const double* U, const double (&g)
 }
 template <int M>
 __device__ __forceinline__ void box_qp_gen(const double* U, const double (&g)[M], const double (&lo)[M], const double (&hi)[M],
-                                        double (&x)[M], bool (&cl)[M]) {
-  double r[M], grad[M], rhs[M], dx[M], xc[M], rc[M], Um[M * M];
+                                        double (&xio)[M], bool (&cl)[M], double* ws) {
+  double* Um = ws;                 // M x M masked matrix
+  double* r = ws + M * M;          // U x
+  double* grad = r + M;
+  double* dx = grad + M;
+  double* xc = dx + M;
+  double* rc = xc + M;
+  double* x = rc + M;              // the iterate
   double gmax = 0.0;
   for (int a = 0; a < M; ++a) {
-    x[a] = r12_clamp(x[a], lo[a], hi[a]);
+    x[a] = r12_clamp(xio[a], lo[a], hi[a]);
     if (fabs(g[a]) > gmax) gmax = fabs(g[a]);
   }
   double f = qp_eval_gen<M>(U, g, x, r);
+  auto finish = [&]() {
+#pragma unroll
+    for (int a = 0; a < M; ++a) xio[a] = x[a];
+  };
   for (int it = 0; it < R12_QP_MAXIT; ++it) {
     int nfree = 0;
     double gn = 0.0;
+#pragma unroll
     for (int a = 0; a < M; ++a) {
-      grad[a] = r[a] + g[a];
-      cl[a] = (x[a] <= lo[a] && grad[a] > 0.0) || (x[a] >= hi[a] && grad[a] < 0.0);
-      if (!cl[a]) { ++nfree; if (fabs(grad[a]) > gn) gn = fabs(grad[a]); }
+      const double ga = r[a] + g[a];
+      grad[a] = ga;
+      cl[a] = (x[a] <= lo[a] && ga > 0.0) || (x[a] >= hi[a] && ga < 0.0);
+      if (!cl[a]) { ++nfree; if (fabs(ga) > gn) gn = fabs(ga); }
     }
-    if (nfree == 0 || gn < R12_QP_GTOL * (1.0 + gmax)) return;
+    if (nfree == 0 || gn < R12_QP_GTOL * (1.0 + gmax)) { finish(); return; }
     ldl_mask<M>(U, cl, Um);
     LdlReg<M> chm;
-    if (chm.factor(Um)) return;
+    if (chm.factor(Um)) { finish(); return; }
+    double rhs[M], dxr[M];
+#pragma unroll
     for (int a = 0; a < M; ++a) rhs[a] = cl[a] ? 0.0 : grad[a];
-    chm.solve_neg(rhs, dx);
+    chm.solve_neg(rhs, dxr);
     double sdotg = 0.0;
-    for (int a = 0; a < M; ++a) sdotg = fmad(grad[a], dx[a], sdotg);
-    if (!(sdotg < 0.0)) return;
+#pragma unroll
+    for (int a = 0; a < M; ++a) { dx[a] = dxr[a]; sdotg = fmad(grad[a], dxr[a], sdotg); }
+    if (!(sdotg < 0.0)) { finish(); return; }
     double step = 1.0;
     bool ok = false;
     for (int ls = 0; ls < R12_QP_MAXLS; ++ls) {
@@ -181,12 +204,14 @@ __device__ __forceinline__ void box_qp_gen(const double* U, const double (&g)[M]
       }
       step = step * 0.5;
     }
-    if (!ok) return;
+    if (!ok) { finish(); return; }
   }
+#pragma unroll
   for (int a = 0; a < M; ++a) {   // iteration cap: the clamped set of the last accepted point
     const double ga = r[a] + g[a];
     cl[a] = (x[a] <= lo[a] && ga > 0.0) || (x[a] >= hi[a] && ga < 0.0);
   }
+  finish();
 }
 
 template <int LAYOUT>
@@ -216,7 +241,7 @@ template <int LAYOUT, int MODE, bool FUSED, int WARPS, bool BOX = false>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
   extern __shared__ __align__(128) double smem[];
   static_assert(!FUSED || LAYOUT == 0, "fused linearisation: A_THEN_B records");
-  constexpr int STRIDE = r24_stride<MODE, FUSED>();
+  constexpr int STRIDE = r24_stride<MODE, FUSED, BOX>();
   double* Ws = smem;
   double* Qfs = smem + R24_WS_DOUBLES;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -449,6 +474,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
       }
 
       // ---------------- phase 2b: Hxx rows of the own x-columns
+      {
       double hA[12], hB[24];
       {
         const double* wa = Ws + cA * R24_WLD;
@@ -478,7 +504,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
           if (n1) hB[i + 1] = fmad(v.y, gb, hB[i + 1]);
         }
       }
-      __syncwarp();  // every lane is done with Fs (and Xs, Es, Vs); the exchanged Hux / Huu are visible
+      __syncwarp();  // every lane is done with Fs (and Xs, Es, Vs) and with P; the exchanged Hux / Huu are visible
+      // The 36 Hxx accumulators wait for phase 4 in shared memory, in the slot of P (dead between phase 1 and phase 4;
+      // 36 x 16 lanes = its 576 doubles exactly), lane-contiguous: with them in registers next to the factorisation
+      // (88), the solves and the affine / box operands phase 3 spilled ~200-550 B per thread to local memory, and with
+      // the shared-memory carve-out at its maximum the seven warps' spill frames do not fit what is left of L1
+      // (profiles/ncu_r01_k_ric24_affine_fused_sparse.txt: 9.5 M local loads, long-scoreboard stalls).
+#pragma unroll
+      for (int i = 0; i < 12; i += 2) sts128(Ps + (i >> 1) * 32 + 2 * t, hA[i], hA[i + 1]);
+#pragma unroll
+      for (int i = 0; i < 24; i += 2) sts128(Ps + (6 + (i >> 1)) * 32 + 2 * t, hB[i], hB[i + 1]);
+      }
       if (!FUSED && it + 1 < N) fetch(k - 1);
 
       // ---------------- phase 3: redundant 8x8 L D L^T, gains of the own x-columns.  The right-hand sides are read
@@ -511,10 +547,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
             if (!(kf[c] > lo[c] && kf[c] < hi[c])) inside = false;
           }
           if (!inside) {
-            box_qp_gen<8>(Us, hur, lo, hi, kf, cl);
-            double Um[64];
-            ldl_mask<8>(Us, cl, Um);
-            failed |= ch.factor(Um);
+            static_assert(QP_WS_DOUBLES<8>() <= R24_STRIDE_AFF_BOX - R24_QP, "QP workspace");
+            double* ws = base + R24_QP;
+            box_qp_gen<8>(Us, hur, lo, hi, kf, cl, ws);
+            ldl_mask<8>(Us, cl, ws);
+            failed |= ch.factor(ws);
             boxed_step = true;
           }
         }
@@ -569,6 +606,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_ric24(const Ric24Args a) {
       }
 
       // ---------------- phase 4: P'[i][j] = Hxx[i][j] + sum_a Hux[a][i] K[a][j], i <= j, own x-columns
+      double hA[12], hB[24];
+#pragma unroll
+      for (int i = 0; i < 12; i += 2) { const double2 v = lds128(Ps + (i >> 1) * 32 + 2 * t); hA[i] = v.x; hA[i + 1] = v.y; }
+#pragma unroll
+      for (int i = 0; i < 24; i += 2) { const double2 v = lds128(Ps + (6 + (i >> 1)) * 32 + 2 * t); hB[i] = v.x; hB[i + 1] = v.y; }
+      __syncwarp();  // every lane has its accumulators back before P' overwrites the slot
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const double ka = kA[c], kb = kB[c];
