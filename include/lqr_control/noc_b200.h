@@ -124,7 +124,10 @@ typedef enum {
   NOC_OPT_TIME_PARALLEL_CHUNKS = 4,/* > 0: force that many horizon chunks (1 = plain warp-per-instance recursion); 0 = planned */
   NOC_OPT_NO_SMALL_BATCH_KERNEL = 5, /* 1: noc_lqr_solve_batch keeps the 8-instances-per-warp sweep also for batches of at most two
                                       instances per SM (default: those run one instance per warp, bit-identical, ~1.6x sooner) */
-  NOC_OPT_COUNT = 6
+  NOC_OPT_NO_TENSOR_SWEEP = 6,     /* 1: the n=12 LTV sweep over A_THEN_B records forms its products with DFMA chains (k_ric12) instead
+                                      of FP64 tensor-core tiles (k_ric12_mma); both are bit-identical to the oracle — DMMA evaluates
+                                      the same ascending fma chain (tools/ubench/dmma_order.cu) — this is the A/B switch */
+  NOC_OPT_COUNT = 7
 } noc_option;
 int noc_set_option(noc_ctx* ctx, int option, int64_t value);
 /* Device memory for callers that do not link the CUDA runtime themselves (the C++ facade, cgo / ctypes bindings):

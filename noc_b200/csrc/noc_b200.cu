@@ -22,6 +22,7 @@
 #include "riccati24.cuh"
 #include "riccati_generic.cuh"
 #include "riccati_scan.cuh"
+#include "riccati12_mma.cuh"
 #include "slq_kernels.cuh"
 
 namespace {
@@ -308,6 +309,22 @@ int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
   return launch_ric12_cfg<LAYOUT, MODE, FUSED, RicCfg<MODE>::warps, RicCfg<MODE>::min_ctas, BOX>(ctx, a);
 }
 
+// The LTV sweep with its products on the FP64 tensor cores (riccati12_mma.cuh): A_THEN_B records, bit-identical to k_ric12
+int launch_ric12_mma(noc_ctx* ctx, const Ric12Args& a) {
+  constexpr int W = 4, CTAS = 2;
+  auto kern = k_ric12_mma<W, CTAS>;
+  const size_t smem = ric12_mma_smem_bytes(W);
+  int rc = configure_kernel(ctx, (const void*)kern, smem, true);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)((a.batch + 8LL * W - 1) / (8LL * W));
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+    kern<<<grid, W * 32, smem, ctx->stream>>>(a);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  return NOC_OK;
+}
+
 template <int MODE>
 int launch_ric12_layout(noc_ctx* ctx, int layout, const Ric12Args& a) {
   return layout == NOC_LAYOUT_A_THEN_B ? launch_ric12<0, MODE>(ctx, a) : launch_ric12<1, MODE>(ctx, a);
@@ -443,6 +460,7 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   // half the time of a warp that owns eight (1,700 vs 3,600 clk).  Same chains, same order, same bits.
   if (p->layout == NOC_LAYOUT_A_THEN_B && batch <= 2LL * ctx->sm_count && !ctx->opt[NOC_OPT_NO_SMALL_BATCH_KERNEL])
     return launch_ric12_tp(ctx, p, batch, dAB, a.W, a.Qf, dx0, dK, dK0, dP0, dcost, dstatus, true);
+  if (p->layout == NOC_LAYOUT_A_THEN_B && !ctx->opt[NOC_OPT_NO_TENSOR_SWEEP]) return launch_ric12_mma(ctx, a);
   return launch_ric12_layout<RIC_LQR>(ctx, p->layout, a);
 }
 

@@ -12,14 +12,17 @@ from noc_b200 import problems as pb
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[0, 1], ids=["small-batch-kernel", "eight-per-warp-kernel"])
+@pytest.fixture(scope="module", params=[(0, 0), (1, 0), (1, 1)],
+                ids=["small-batch-kernel", "tensor-core-sweep", "dfma-sweep"])
 def solver(request):
-    """Every test of this module runs twice: batches of at most two instances per SM go to the warp-per-instance
-    recursion (k_ric12_tp<DFMA>, one chunk) by default, and to the 8-instances-per-warp sweep (k_ric12) with
-    NOC_OPT_NO_SMALL_BATCH_KERNEL — both must reproduce the oracle bit for bit."""
+    """Every test of this module runs three times: batches of at most two instances per SM go to the warp-per-instance
+    recursion (k_ric12_tp<DFMA>, one chunk) by default; with NOC_OPT_NO_SMALL_BATCH_KERNEL they go to the
+    8-instances-per-warp sweeps — k_ric12_mma (products on the FP64 tensor cores, A_THEN_B records) and, with
+    NOC_OPT_NO_TENSOR_SWEEP, k_ric12 (DFMA chains).  All three must reproduce the oracle bit for bit."""
     from noc_b200 import capi
     s = capi.Solver(0)
-    s.set_option(capi.OPT_NO_SMALL_BATCH_KERNEL, request.param)
+    s.set_option(capi.OPT_NO_SMALL_BATCH_KERNEL, request.param[0])
+    s.set_option(capi.OPT_NO_TENSOR_SWEEP, request.param[1])
     yield s
     s.close()
 
