@@ -311,7 +311,7 @@ int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
 
 // The LTV sweep with its products on the FP64 tensor cores (riccati12_mma.cuh): A_THEN_B records, bit-identical to k_ric12
 int launch_ric12_mma(noc_ctx* ctx, const Ric12Args& a) {
-  constexpr int W = 4, CTAS = 2;
+  constexpr int W = 8, CTAS = 1;   // one CTA of eight warps per SM: the phase interlock pairs warps w and w+4
   auto kern = k_ric12_mma<W, CTAS>;
   const size_t smem = ric12_mma_smem_bytes(W);
   int rc = configure_kernel(ctx, (const void*)kern, smem, true);

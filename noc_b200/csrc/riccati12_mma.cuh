@@ -43,7 +43,8 @@ constexpr int RM_FS = 0;            // record A[12][12] | B[12][4]
 constexpr int RM_PH = 192;          // P[12][12] (row stride 12) between steps; the three 8x8 tiles of H' inside a step
 constexpr int RM_STRIDE = 388;      // per instance: 3104 B = 32 B modulo 128 B (the scalar phase touches all eight instances at once)
 constexpr int RM_GBUF = 192;        // G' (12 x 16, swizzled), two buffers per warp
-constexpr int RM_WARP_DOUBLES = 8 * RM_STRIDE + 2 * RM_GBUF;
+constexpr int RM_ZPAD = 16;         // zeros: the padding rows 12..15 of P in the second M tile
+constexpr int RM_WARP_DOUBLES = 8 * RM_STRIDE + 2 * RM_GBUF + RM_ZPAD;
 constexpr int RM_BAR_DOUBLES = 8;
 
 inline size_t ric12_mma_smem_bytes(int warps) { return sizeof(double) * (size_t)(RM_BAR_DOUBLES + warps * RM_WARP_DOUBLES); }
@@ -55,6 +56,13 @@ __device__ __forceinline__ void rm_dmma(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
+// one elected lane of the (converged) warp
+__device__ __forceinline__ bool rm_elect_one() {
+  unsigned pred;
+  asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+  return pred != 0;
+}
+
 // position p of the permuted order [u3 u2 u1 u0 | x0 .. x11] -> index in the W = blockdiag(Q, R) order [x0 .. x11 | u0 .. u3]
 __host__ __device__ constexpr int rm_perm(int p) { return p < 4 ? 15 - p : p - 4; }
 
@@ -64,10 +72,15 @@ __device__ __forceinline__ int rm_hoff(int r, int c) { return ((r >> 3) + (c >> 
 template <int WARPS, int MIN_CTAS>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12Args a) {
   extern __shared__ __align__(128) double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr bool PAIRED = (WARPS == 8);
+  // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the TMA operands (shared-memory
+  // destination, mbarrier, global source) in uniform registers — computed from threadIdx alone every bulk copy became an
+  // ELECT / R2UR waterfall loop of 17 instructions (155 per warp-step, profiles/ncu_r02_k_ric12_mma_v1.txt)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;   // tensor phase: fragment coordinates; scalar phase: instance slot g, lane t of it
   double* wbase = smem + RM_BAR_DOUBLES + warp * RM_WARP_DOUBLES;
   double* Gb = wbase + 8 * RM_STRIDE;
+  double* zpad = Gb + 2 * RM_GBUF + (lane & 3);
   double* base = wbase + g * RM_STRIDE;    // own instance in the scalar phase
   double* Ps = base + RM_PH;
   const unsigned bar = smem_u32(smem) + 8u * warp;
@@ -87,7 +100,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
   const unsigned fs0_u32 = smem_u32(wbase + RM_FS);
   unsigned phase = 0;
   auto fetch = [&](int k) {
-    if (lane == 0) {
+    if (rm_elect_one()) {
       mbar_expect_tx(bar, 8u * 1536u);
       const double* src = rec0 + (size_t)k * R12_REC;
 #pragma unroll
@@ -126,6 +139,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
       for (int e = 0; e < 2; ++e) wc[T][e] = a.W[rm_perm(tr[T] + g) * 16 + rm_perm(tc[T] + 2 * t + e)];
   }
 
+  if (lane < RM_ZPAD) Gb[2 * RM_GBUF + lane] = 0.0;
   // P <- Qf
   for (int e = t; e < 144; e += 4) Ps[e] = a.Qf[e];
   for (int e = 144 + t; e < 192; e += 4) Ps[e] = 0.0;
@@ -136,57 +150,132 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
   double *Kp0 = Kp + j0, *Kp1 = Kp + j1, *Kp2 = Kp + j2;
   __syncwarp();
 
+  // Phase interlock (one CTA of eight warps per SM): warps w and w+4 share a scheduler, and left alone they drift into
+  // the same phase — both in the tensor phase (each DMMA stream at half speed), then both in the latency-bound scalar
+  // phase with the FP64 pipe idle; that state is stable (measured: 8,900 cycles per pair of warp-steps, 70 % pipe).  A
+  // named barrier per pair at every phase boundary, the upper warp starting half a period late, keeps one warp's
+  // tensor phase under the other's scalar phase.
+  const unsigned pair_bar = 1u + (unsigned)(warp & 3);
+  auto pair_sync = [&]() {
+    if (PAIRED) asm volatile("bar.sync %0, 64;\n" ::"r"(pair_bar) : "memory");
+  };
+  if (PAIRED && warp >= 4) pair_sync();
+
+#ifdef RM_TIMING
+  long long tm_wait = 0, tm_tensor = 0, tm_scalar = 0, tm_sync = 0;
+#define RM_TICK(acc) { const long long now_ = clock64(); acc += now_ - tm_last; tm_last = now_; }
+  long long tm_last = clock64();
+#else
+#define RM_TICK(acc)
+#endif
   for (int it = 0; it < N; ++it) {
     const int k = N - 1 - it;
     mbar_wait(bar, phase);
     phase ^= 1u;
     __syncwarp();
+    RM_TICK(tm_wait)
 
-    // ---------------- tensor phase: H' of the eight instances, one after the other
-#pragma unroll 2
-    for (int q = 0; q < 8; ++q) {
+    // ---------------- tensor phase: H' of the eight instances, software-pipelined over the instances.  A warp issues in
+    // order, and a DMMA holds the FP64 pipe for 16 cycles (26 to its result: tools/ubench/dmma_issue.cu), so everything
+    // that is not a DMMA is placed BETWEEN DMMAs whose operands are long ready — slot q of the loop issues
+    //     G'(q)   [12 DMMAs]   with, in their shadow: the store of H'(q-2), the fragment loads of instance q+1 and the TMA
+    //                          request for instance q's next record (its fragments are in registers by then), and
+    //     H'(q-1) [ 9 DMMAs]   with, in their shadow: the store of G'(q), the warp barrier and the reload of G'(q) in the
+    //                          B-fragment layout (consumed one slot later).
+    // The first version issued block after block (loads, 12 DMMAs, stores, barrier, loads, 9 DMMAs, stores): 4,700 cycles
+    // per warp-step for 2,688 cycles of DMMA issue.
+    double fb[3][3][2];      // F' fragments, ring over instances q-1, q, q+1
+    double pa[2][3][2];      // P fragments, instances q, q+1
+    double gb[2][3][2];      // G' fragments (B layout), instances q-1, q
+    double hacc[3][2];
+    auto load_frags = [&](int q) {
       const double* Fq = wbase + q * RM_STRIDE + RM_FS;
-      double* PHq = wbase + q * RM_STRIDE + RM_PH;
-      double* Gq = Gb + (q & 1) * RM_GBUF;
-      double fb[3][2], pa[3][2];
+      const double* PHq = wbase + q * RM_STRIDE + RM_PH;
+      const double* P1 = p1on ? PHq + po1 : zpad;      // padding rows of the second M tile read zeros
 #pragma unroll
       for (int ki = 0; ki < 3; ++ki) {
-        fb[ki][0] = Fq[fo0 + ki * fs0];
-        fb[ki][1] = Fq[fo1 + ki * 48];
-        pa[ki][0] = PHq[po0 + 4 * ki];
-        const double p1 = PHq[po1 + 4 * ki];
-        pa[ki][1] = p1on ? p1 : 0.0;
+        fb[q % 3][ki][0] = Fq[fo0 + ki * fs0];
+        fb[q % 3][ki][1] = Fq[fo1 + ki * 48];
+        pa[q & 1][ki][0] = PHq[po0 + 4 * ki];
+        pa[q & 1][ki][1] = P1[4 * ki];
       }
+    };
+    const bool more = it + 1 < N;
+    if (more && rm_elect_one()) mbar_expect_tx(bar, 8u * 1536u);
+    const double* src_next = rec0 + (size_t)(k - 1) * R12_REC;
+    load_frags(0);
+#pragma unroll
+    for (int q = 0; q <= 8; ++q) {
       double gacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};   // [mi][ni][e]
+      if (q < 8) {
 #pragma unroll
-      for (int ki = 0; ki < 3; ++ki) {
-        rm_dmma(gacc[0][0][0], gacc[0][0][1], pa[ki][0], fb[ki][0]);
-        rm_dmma(gacc[0][1][0], gacc[0][1][1], pa[ki][0], fb[ki][1]);
-        rm_dmma(gacc[1][0][0], gacc[1][0][1], pa[ki][1], fb[ki][0]);
-        rm_dmma(gacc[1][1][0], gacc[1][1][1], pa[ki][1], fb[ki][1]);
+        for (int ki = 0; ki < 3; ++ki) {
+          rm_dmma(gacc[0][0][0], gacc[0][0][1], pa[q & 1][ki][0], fb[q % 3][ki][0]);
+          rm_dmma(gacc[0][1][0], gacc[0][1][1], pa[q & 1][ki][0], fb[q % 3][ki][1]);
+          rm_dmma(gacc[1][0][0], gacc[1][0][1], pa[q & 1][ki][1], fb[q % 3][ki][0]);
+          rm_dmma(gacc[1][1][0], gacc[1][1][1], pa[q & 1][ki][1], fb[q % 3][ki][1]);
+          if (ki == 0 && q >= 2) {   // H'(q-2), issued a slot ago, has long landed
+            double* PHp = wbase + (q - 2) * RM_STRIDE + RM_PH;
+#pragma unroll
+            for (int T = 0; T < 3; ++T) sts128(PHp + 64 * T + hs, hacc[T][0], hacc[T][1]);
+          }
+          if (ki == 1 && q + 1 < 8) load_frags(q + 1);
+        }
+        // every lane's fragments of instance q are in registers (the DMMAs above consumed them): its record slot is free
+        if (more && rm_elect_one())
+          bulk_g2s(fs0_u32 + (unsigned)(q * RM_STRIDE * 8), src_next + (size_t)(q < nvalid ? q : nvalid - 1) * rstride, 1536u, bar);
       }
-      sts128(Gq + gs0, gacc[0][0][0], gacc[0][0][1]);
-      sts128(Gq + gs1, gacc[0][1][0], gacc[0][1][1]);
-      if (p1on) {
-        sts128(Gq + 128 + gs0, gacc[1][0][0], gacc[1][0][1]);
-        sts128(Gq + 128 + gs1, gacc[1][1][0], gacc[1][1][1]);
+      if (q >= 1) {   // H'(q-1) = W' + F'^T G'
+        if (q == 8) {   // (no G' slot to hide the store of H'(6) in)
+          double* PHp = wbase + 6 * RM_STRIDE + RM_PH;
+#pragma unroll
+          for (int T = 0; T < 3; ++T) sts128(PHp + 64 * T + hs, hacc[T][0], hacc[T][1]);
+        }
+#pragma unroll
+        for (int T = 0; T < 3; ++T) { hacc[T][0] = wc[T][0]; hacc[T][1] = wc[T][1]; }
+#pragma unroll
+        for (int ki = 0; ki < 3; ++ki) {
+          rm_dmma(hacc[0][0], hacc[0][1], fb[(q - 1) % 3][ki][0], gb[(q - 1) & 1][ki][0]);   // tile (0,0)
+          rm_dmma(hacc[1][0], hacc[1][1], fb[(q - 1) % 3][ki][0], gb[(q - 1) & 1][ki][1]);   // tile (0,1)
+          rm_dmma(hacc[2][0], hacc[2][1], fb[(q - 1) % 3][ki][1], gb[(q - 1) & 1][ki][1]);   // tile (1,1)
+          if (ki == 0 && q < 8) {   // G'(q) is complete by now: C-fragment layout -> shared memory -> B-fragment layout
+            double* Gq = Gb + (q & 1) * RM_GBUF;
+            sts128(Gq + gs0, gacc[0][0][0], gacc[0][0][1]);
+            sts128(Gq + gs1, gacc[0][1][0], gacc[0][1][1]);
+            if (p1on) {
+              sts128(Gq + 128 + gs0, gacc[1][0][0], gacc[1][0][1]);
+              sts128(Gq + 128 + gs1, gacc[1][1][0], gacc[1][1][1]);
+            }
+            __syncwarp();
+          }
+          if (ki == 1 && q < 8) {
+            const double* Gq = Gb + (q & 1) * RM_GBUF;
+#pragma unroll
+            for (int kj = 0; kj < 3; ++kj) { gb[q & 1][kj][0] = Gq[gl0 + 64 * kj]; gb[q & 1][kj][1] = Gq[gl1 + 64 * kj]; }
+          }
+        }
+      } else {   // q == 0: nothing to overlap the round trip of G'(0) with
+        double* Gq = Gb;
+        sts128(Gq + gs0, gacc[0][0][0], gacc[0][0][1]);
+        sts128(Gq + gs1, gacc[0][1][0], gacc[0][1][1]);
+        if (p1on) {
+          sts128(Gq + 128 + gs0, gacc[1][0][0], gacc[1][0][1]);
+          sts128(Gq + 128 + gs1, gacc[1][1][0], gacc[1][1][1]);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int kj = 0; kj < 3; ++kj) { gb[0][kj][0] = Gq[gl0 + 64 * kj]; gb[0][kj][1] = Gq[gl1 + 64 * kj]; }
       }
-      __syncwarp();   // G' complete; every lane has read the instance's P
-      double hacc[3][2];
-#pragma unroll
-      for (int T = 0; T < 3; ++T) { hacc[T][0] = wc[T][0]; hacc[T][1] = wc[T][1]; }
-#pragma unroll
-      for (int ki = 0; ki < 3; ++ki) {
-        const double gb0 = Gq[gl0 + 64 * ki], gb1 = Gq[gl1 + 64 * ki];
-        rm_dmma(hacc[0][0], hacc[0][1], fb[ki][0], gb0);   // tile (0,0)
-        rm_dmma(hacc[1][0], hacc[1][1], fb[ki][0], gb1);   // tile (0,1)
-        rm_dmma(hacc[2][0], hacc[2][1], fb[ki][1], gb1);   // tile (1,1)
-      }
-#pragma unroll
-      for (int T = 0; T < 3; ++T) sts128(PHq + 64 * T + hs, hacc[T][0], hacc[T][1]);
     }
-    __syncwarp();   // H' of all eight instances visible; nobody reads the records any more
-    if (it + 1 < N) fetch(k - 1);
+    {
+      double* PH7 = wbase + 7 * RM_STRIDE + RM_PH;
+#pragma unroll
+      for (int T = 0; T < 3; ++T) sts128(PH7 + 64 * T + hs, hacc[T][0], hacc[T][1]);
+    }
+    __syncwarp();   // H' of all eight instances visible
+    RM_TICK(tm_tensor)
+    pair_sync();
+    RM_TICK(tm_sync)
 
     // ---------------- scalar phase (four lanes per instance): L D L^T, gains, P'
     const double* Hq = Ps;
@@ -264,7 +353,17 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
     r12_store_direct<4>(Ps, hx0, j0, true);
     r12_store_direct<8>(Ps, hx1, j1, true);
     r12_store_direct<12>(Ps, hx2, j2, true);
+    RM_TICK(tm_scalar)
+    pair_sync();
+    RM_TICK(tm_sync)
   }
+#ifdef RM_TIMING
+  if (lane == 0 && a.iters) {   // (a.iters is unused by the LQR sweep: the timing build borrows it)
+    long long* o = reinterpret_cast<long long*>(a.iters) + 4 * ((long long)blockIdx.x * WARPS + warp);
+    o[0] = tm_wait; o[1] = tm_tensor; o[2] = tm_scalar; o[3] = tm_sync;
+  }
+#endif
+  if (PAIRED && warp < 4) pair_sync();   // the partner's last scalar phase
   __syncwarp();
 
   // ---------------- outputs (the rules of k_ric12<RIC_LQR>)
