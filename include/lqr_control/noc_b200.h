@@ -127,7 +127,10 @@ typedef enum {
   NOC_OPT_NO_TENSOR_SWEEP = 6,     /* 1: the n=12 LTV sweep over A_THEN_B records forms its products with DFMA chains (k_ric12) instead
                                       of FP64 tensor-core tiles (k_ric12_mma); both are bit-identical to the oracle — DMMA evaluates
                                       the same ascending fma chain (tools/ubench/dmma_order.cu) — this is the A/B switch */
-  NOC_OPT_COUNT = 7
+  NOC_OPT_TENSOR_SWEEP_VARIANT = 7, /* measurements: 0 = default (records staged in shared memory by TMA, eight free-running warps per
+                                      SM), 1 = + phase interlock of the two warps of a scheduler, 2 = no staging: fragments read
+                                      straight from L2, twelve warps per SM.  All bit-identical; 0 is the fastest */
+  NOC_OPT_COUNT = 8
 } noc_option;
 int noc_set_option(noc_ctx* ctx, int option, int64_t value);
 /* Device memory for callers that do not link the CUDA runtime themselves (the C++ facade, cgo / ctypes bindings):

@@ -310,10 +310,10 @@ int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
 }
 
 // The LTV sweep with its products on the FP64 tensor cores (riccati12_mma.cuh): A_THEN_B records, bit-identical to k_ric12
-int launch_ric12_mma(noc_ctx* ctx, const Ric12Args& a) {
-  constexpr int W = 8, CTAS = 1;   // one CTA of eight warps per SM: the phase interlock pairs warps w and w+4
-  auto kern = k_ric12_mma<W, CTAS>;
-  const size_t smem = ric12_mma_smem_bytes(W);
+template <int W, int CTAS, bool DIRECT>
+int launch_ric12_mma_cfg(noc_ctx* ctx, const Ric12Args& a) {
+  auto kern = k_ric12_mma<W, CTAS, DIRECT>;
+  const size_t smem = ric12_mma_smem_bytes<DIRECT>(W);
   int rc = configure_kernel(ctx, (const void*)kern, smem, true);
   if (rc) return rc;
   const unsigned grid = (unsigned)((a.batch + 8LL * W - 1) / (8LL * W));
@@ -323,6 +323,13 @@ int launch_ric12_mma(noc_ctx* ctx, const Ric12Args& a) {
   }
   NOC_CUDA(ctx, cudaGetLastError());
   return NOC_OK;
+}
+int launch_ric12_mma(noc_ctx* ctx, const Ric12Args& a) {
+  switch (ctx->opt[NOC_OPT_TENSOR_SWEEP_VARIANT]) {
+    case 1: return launch_ric12_mma_cfg<8, 1, false>(ctx, a);   // + phase interlock of scheduler mates (3.06 ms)
+    case 2: return launch_ric12_mma_cfg<4, 3, true>(ctx, a);    // fragments straight from L2, 12 warps per SM (3.05 ms)
+    default: return launch_ric12_mma_cfg<4, 2, false>(ctx, a);  // records staged by TMA, 2 CTAs x 4 warps per SM (2.87 ms)
+  }
 }
 
 template <int MODE>

@@ -47,7 +47,24 @@ constexpr int RM_ZPAD = 16;         // zeros: the padding rows 12..15 of P in th
 constexpr int RM_WARP_DOUBLES = 8 * RM_STRIDE + 2 * RM_GBUF + RM_ZPAD;
 constexpr int RM_BAR_DOUBLES = 8;
 
-inline size_t ric12_mma_smem_bytes(int warps) { return sizeof(double) * (size_t)(RM_BAR_DOUBLES + warps * RM_WARP_DOUBLES); }
+// DIRECT variant: no staged records — the F' fragments are read straight from global memory (the records of step k-1 are
+// pulled into L2 by bulk prefetches during step k), so an instance needs only its P / H' slot and twelve warps fit an SM
+constexpr int RMD_STRIDE = 196;     // 1568 B = 32 B modulo 128 B
+constexpr int RMD_WARP_DOUBLES = 8 * RMD_STRIDE + 2 * RM_GBUF + RM_ZPAD;
+
+template <bool DIRECT>
+inline size_t ric12_mma_smem_bytes(int warps) {
+  return sizeof(double) * (size_t)(RM_BAR_DOUBLES + warps * (DIRECT ? RMD_WARP_DOUBLES : RM_WARP_DOUBLES));
+}
+
+__device__ __forceinline__ double rm_ldg_stream(const double* p) {   // read-once data: no L1 allocation
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];\n" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void rm_prefetch_l2(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(p), "r"(bytes) : "memory");
+}
 
 // FP64 tensor-core tile D(8x8) += A(8x4) B(4x8).  Fragments of lane (g, t): a = A[g][t], b = B[t][g], {d0, d1} = D[g][2t], D[g][2t+1].
 __device__ __forceinline__ void rm_dmma(double& d0, double& d1, double a, double b) {
@@ -69,20 +86,30 @@ __host__ __device__ constexpr int rm_perm(int p) { return p < 4 ? 15 - p : p - 4
 // H'(r, c), r <= c (positions of the permuted order), inside the instance's tile store: tiles (0,0), (0,1), (1,1)
 __device__ __forceinline__ int rm_hoff(int r, int c) { return ((r >> 3) + (c >> 3)) * 64 + (r & 7) * 8 + (c & 7); }
 
-template <int WARPS, int MIN_CTAS>
+// column j of P' (rows 0..ROWS-1 held, valid for i <= j) -> the upper triangle of the stride-12 store
+template <int ROWS>
+__device__ __forceinline__ void rm_store_upper(double* Ps, const double* h, int j) {
+#pragma unroll
+  for (int i = 0; i < ROWS; ++i)
+    if (i <= j) Ps[i * 12 + j] = h[i];
+}
+
+template <int WARPS, int MIN_CTAS, bool DIRECT>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12Args a) {
   extern __shared__ __align__(128) double smem[];
-  constexpr bool PAIRED = (WARPS == 8);
+  constexpr bool PAIRED = (WARPS == 8) && !DIRECT;
+  constexpr int STRIDE = DIRECT ? RMD_STRIDE : RM_STRIDE;
+  constexpr int PHOFF = DIRECT ? 0 : RM_PH;
   // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps the TMA operands (shared-memory
   // destination, mbarrier, global source) in uniform registers — computed from threadIdx alone every bulk copy became an
   // ELECT / R2UR waterfall loop of 17 instructions (155 per warp-step, profiles/ncu_r02_k_ric12_mma_v1.txt)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;   // tensor phase: fragment coordinates; scalar phase: instance slot g, lane t of it
-  double* wbase = smem + RM_BAR_DOUBLES + warp * RM_WARP_DOUBLES;
-  double* Gb = wbase + 8 * RM_STRIDE;
+  double* wbase = smem + RM_BAR_DOUBLES + warp * (DIRECT ? RMD_WARP_DOUBLES : RM_WARP_DOUBLES);
+  double* Gb = wbase + 8 * STRIDE;
   double* zpad = Gb + 2 * RM_GBUF + (lane & 3);
-  double* base = wbase + g * RM_STRIDE;    // own instance in the scalar phase
-  double* Ps = base + RM_PH;
+  double* base = wbase + g * STRIDE;    // own instance in the scalar phase
+  double* Ps = base + PHOFF;
   const unsigned bar = smem_u32(smem) + 8u * warp;
 
   const long long w0 = ((long long)blockIdx.x * WARPS + warp) * 8;
@@ -101,17 +128,23 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
   unsigned phase = 0;
   auto fetch = [&](int k) {
     if (rm_elect_one()) {
-      mbar_expect_tx(bar, 8u * 1536u);
       const double* src = rec0 + (size_t)k * R12_REC;
+      if (!DIRECT) mbar_expect_tx(bar, 8u * 1536u);
 #pragma unroll
-      for (int qq = 0; qq < 8; ++qq)
-        bulk_g2s(fs0_u32 + (unsigned)(qq * RM_STRIDE * 8), src + (size_t)(qq < nvalid ? qq : nvalid - 1) * rstride, 1536u, bar);
+      for (int qq = 0; qq < 8; ++qq) {
+        const double* sq = src + (size_t)(qq < nvalid ? qq : nvalid - 1) * rstride;
+        if (DIRECT) rm_prefetch_l2(sq, 1536u);
+        else bulk_g2s(fs0_u32 + (unsigned)(qq * STRIDE * 8), sq, 1536u, bar);
+      }
     }
   };
-  if (lane == 0) mbar_init(bar, 1);
-  mbar_fence_init();
+  if (!DIRECT) {
+    if (lane == 0) mbar_init(bar, 1);
+    mbar_fence_init();
+  }
   __syncwarp();
   fetch(N - 1);
+  if (DIRECT && N > 1) fetch(N - 2);
 
   // ---- lane constants of the tensor phase
   // B fragments of F' (and A fragments of F'^T): F'[4ki+t][8ni+g] = F[4ki+t][perm(8ni+g)], element offset fo[ni] + ki*fs[ni]
@@ -120,8 +153,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
   const int fo0 = (g < 4) ? 144 + t * 4 + (3 - g) : t * 12 + (g - 4);
   const int fs0 = (g < 4) ? 16 : 48;
   const int fo1 = t * 12 + 4 + g;
-  // A fragments of P: P[8mi+g][4ki+t]; rows 12..15 are padding (zero)
-  const int po0 = g * 12 + t, po1 = (8 + (g & 3)) * 12 + t;
+  // A fragments of P: P[8mi+g][4ki+t]; rows 12..15 are padding (zero).  Inside the sweep only the UPPER triangle of P is
+  // kept in shared memory (the scalar phase stores P'[i][j], i <= j, once; the mirrored copy cost as many wavefronts
+  // again, with bank conflicts): an element below the diagonal is read from its mirror image, which is the same double.
+  auto ptri = [](int r, int c) { return r <= c ? r * 12 + c : c * 12 + r; };
+  int po[2][3];
+#pragma unroll
+  for (int ki = 0; ki < 3; ++ki) { po[0][ki] = ptri(g, 4 * ki + t); po[1][ki] = ptri(8 + (g & 3), 4 * ki + t); }
   const bool p1on = g < 4;
   // G' buffer, element (l, c) at l*16 + (c ^ swz(l)), swz(l) = 8*(l&1) + 4*((l>>1)&1): C-fragment stores (rows g, 8+g;
   // 16-byte pairs) and B-fragment loads (rows 4ki+t) are both bank-conflict free
@@ -170,8 +208,10 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
 #endif
   for (int it = 0; it < N; ++it) {
     const int k = N - 1 - it;
-    mbar_wait(bar, phase);
-    phase ^= 1u;
+    if (!DIRECT) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    }
     __syncwarp();
     RM_TICK(tm_wait)
 
@@ -184,50 +224,69 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
     //                          B-fragment layout (consumed one slot later).
     // The first version issued block after block (loads, 12 DMMAs, stores, barrier, loads, 9 DMMAs, stores): 4,700 cycles
     // per warp-step for 2,688 cycles of DMMA issue.
-    double fb[3][3][2];      // F' fragments, ring over instances q-1, q, q+1
+    constexpr int FD = DIRECT ? 2 : 1;   // F' fragments are requested FD instances ahead (L2 latency vs shared memory)
+    double fb[4][3][2];      // F' fragments, ring over instances q-1 .. q+FD
     double pa[2][3][2];      // P fragments, instances q, q+1
     double gb[2][3][2];      // G' fragments (B layout), instances q-1, q
     double hacc[3][2];
-    auto load_frags = [&](int q) {
-      const double* Fq = wbase + q * RM_STRIDE + RM_FS;
-      const double* PHq = wbase + q * RM_STRIDE + RM_PH;
-      const double* P1 = p1on ? PHq + po1 : zpad;      // padding rows of the second M tile read zeros
+    const double* rec_k = rec0 + (size_t)k * R12_REC;
+    auto load_f = [&](int q) {
+      if (DIRECT) {
+        const double* Fq = rec_k + (size_t)(q < nvalid ? q : nvalid - 1) * rstride;
+#pragma unroll
+        for (int ki = 0; ki < 3; ++ki) {
+          fb[q % 4][ki][0] = rm_ldg_stream(Fq + fo0 + ki * fs0);
+          fb[q % 4][ki][1] = rm_ldg_stream(Fq + fo1 + ki * 48);
+        }
+      } else {
+        const double* Fq = wbase + q * STRIDE + RM_FS;
+#pragma unroll
+        for (int ki = 0; ki < 3; ++ki) {
+          fb[q % 4][ki][0] = Fq[fo0 + ki * fs0];
+          fb[q % 4][ki][1] = Fq[fo1 + ki * 48];
+        }
+      }
+    };
+    auto load_p = [&](int q) {
+      const double* PHq = wbase + q * STRIDE + PHOFF;
 #pragma unroll
       for (int ki = 0; ki < 3; ++ki) {
-        fb[q % 3][ki][0] = Fq[fo0 + ki * fs0];
-        fb[q % 3][ki][1] = Fq[fo1 + ki * 48];
-        pa[q & 1][ki][0] = PHq[po0 + 4 * ki];
-        pa[q & 1][ki][1] = P1[4 * ki];
+        pa[q & 1][ki][0] = PHq[po[0][ki]];
+        pa[q & 1][ki][1] = p1on ? PHq[po[1][ki]] : zpad[0];      // padding rows of the second M tile read zeros
       }
     };
     const bool more = it + 1 < N;
-    if (more && rm_elect_one()) mbar_expect_tx(bar, 8u * 1536u);
+    if (!DIRECT && more && rm_elect_one()) mbar_expect_tx(bar, 8u * 1536u);
     const double* src_next = rec0 + (size_t)(k - 1) * R12_REC;
-    load_frags(0);
+    if (DIRECT && it + 2 < N) fetch(k - 2);   // L2 prefetch two steps ahead (the first two were requested in the prologue)
+#pragma unroll
+    for (int q0 = 0; q0 < FD; ++q0) load_f(q0);
+    load_p(0);
 #pragma unroll
     for (int q = 0; q <= 8; ++q) {
       double gacc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};   // [mi][ni][e]
       if (q < 8) {
 #pragma unroll
         for (int ki = 0; ki < 3; ++ki) {
-          rm_dmma(gacc[0][0][0], gacc[0][0][1], pa[q & 1][ki][0], fb[q % 3][ki][0]);
-          rm_dmma(gacc[0][1][0], gacc[0][1][1], pa[q & 1][ki][0], fb[q % 3][ki][1]);
-          rm_dmma(gacc[1][0][0], gacc[1][0][1], pa[q & 1][ki][1], fb[q % 3][ki][0]);
-          rm_dmma(gacc[1][1][0], gacc[1][1][1], pa[q & 1][ki][1], fb[q % 3][ki][1]);
+          rm_dmma(gacc[0][0][0], gacc[0][0][1], pa[q & 1][ki][0], fb[q % 4][ki][0]);
+          rm_dmma(gacc[0][1][0], gacc[0][1][1], pa[q & 1][ki][0], fb[q % 4][ki][1]);
+          rm_dmma(gacc[1][0][0], gacc[1][0][1], pa[q & 1][ki][1], fb[q % 4][ki][0]);
+          rm_dmma(gacc[1][1][0], gacc[1][1][1], pa[q & 1][ki][1], fb[q % 4][ki][1]);
           if (ki == 0 && q >= 2) {   // H'(q-2), issued a slot ago, has long landed
-            double* PHp = wbase + (q - 2) * RM_STRIDE + RM_PH;
+            double* PHp = wbase + (q - 2) * STRIDE + PHOFF;
 #pragma unroll
             for (int T = 0; T < 3; ++T) sts128(PHp + 64 * T + hs, hacc[T][0], hacc[T][1]);
           }
-          if (ki == 1 && q + 1 < 8) load_frags(q + 1);
+          if (ki == 1 && q + 1 < 8) load_p(q + 1);
+          if (ki == 1 && q + FD < 8) load_f(q + FD);
         }
         // every lane's fragments of instance q are in registers (the DMMAs above consumed them): its record slot is free
-        if (more && rm_elect_one())
-          bulk_g2s(fs0_u32 + (unsigned)(q * RM_STRIDE * 8), src_next + (size_t)(q < nvalid ? q : nvalid - 1) * rstride, 1536u, bar);
+        if (!DIRECT && more && rm_elect_one())
+          bulk_g2s(fs0_u32 + (unsigned)(q * STRIDE * 8), src_next + (size_t)(q < nvalid ? q : nvalid - 1) * rstride, 1536u, bar);
       }
       if (q >= 1) {   // H'(q-1) = W' + F'^T G'
         if (q == 8) {   // (no G' slot to hide the store of H'(6) in)
-          double* PHp = wbase + 6 * RM_STRIDE + RM_PH;
+          double* PHp = wbase + 6 * STRIDE + PHOFF;
 #pragma unroll
           for (int T = 0; T < 3; ++T) sts128(PHp + 64 * T + hs, hacc[T][0], hacc[T][1]);
         }
@@ -235,9 +294,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
         for (int T = 0; T < 3; ++T) { hacc[T][0] = wc[T][0]; hacc[T][1] = wc[T][1]; }
 #pragma unroll
         for (int ki = 0; ki < 3; ++ki) {
-          rm_dmma(hacc[0][0], hacc[0][1], fb[(q - 1) % 3][ki][0], gb[(q - 1) & 1][ki][0]);   // tile (0,0)
-          rm_dmma(hacc[1][0], hacc[1][1], fb[(q - 1) % 3][ki][0], gb[(q - 1) & 1][ki][1]);   // tile (0,1)
-          rm_dmma(hacc[2][0], hacc[2][1], fb[(q - 1) % 3][ki][1], gb[(q - 1) & 1][ki][1]);   // tile (1,1)
+          rm_dmma(hacc[0][0], hacc[0][1], fb[(q - 1) % 4][ki][0], gb[(q - 1) & 1][ki][0]);   // tile (0,0)
+          rm_dmma(hacc[1][0], hacc[1][1], fb[(q - 1) % 4][ki][0], gb[(q - 1) & 1][ki][1]);   // tile (0,1)
+          rm_dmma(hacc[2][0], hacc[2][1], fb[(q - 1) % 4][ki][1], gb[(q - 1) & 1][ki][1]);   // tile (1,1)
           if (ki == 0 && q < 8) {   // G'(q) is complete by now: C-fragment layout -> shared memory -> B-fragment layout
             double* Gq = Gb + (q & 1) * RM_GBUF;
             sts128(Gq + gs0, gacc[0][0][0], gacc[0][0][1]);
@@ -268,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
       }
     }
     {
-      double* PH7 = wbase + 7 * RM_STRIDE + RM_PH;
+      double* PH7 = wbase + 7 * STRIDE + PHOFF;
 #pragma unroll
       for (int T = 0; T < 3; ++T) sts128(PH7 + 64 * T + hs, hacc[T][0], hacc[T][1]);
     }
@@ -346,13 +405,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
       for (int i = 0; i < 12; ++i) hx2[i] = fmad(hr[i], kk[2][c], hx2[i]);
     }
     __syncwarp();   // every lane has taken what it needs from H': P' may overwrite the slot
-    r12_store_mirror<4>(Ps, hx0, j0, true);
-    r12_store_mirror<8>(Ps, hx1, j1, true);
-    r12_store_mirror<12>(Ps, hx2, j2, true);
-    __syncwarp();
-    r12_store_direct<4>(Ps, hx0, j0, true);
-    r12_store_direct<8>(Ps, hx1, j1, true);
-    r12_store_direct<12>(Ps, hx2, j2, true);
+    rm_store_upper<4>(Ps, hx0, j0);
+    rm_store_upper<8>(Ps, hx1, j1);
+    rm_store_upper<12>(Ps, hx2, j2);
     RM_TICK(tm_scalar)
     pair_sync();
     RM_TICK(tm_sync)
@@ -364,6 +419,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
   }
 #endif
   if (PAIRED && warp < 4) pair_sync();   // the partner's last scalar phase
+  __syncwarp();
+  for (int e = t; e < 144; e += 4) {      // P0 as a full symmetric matrix for the outputs
+    const int i = e / 12, j = e % 12;
+    if (i > j) Ps[e] = Ps[j * 12 + i];
+  }
   __syncwarp();
 
   // ---------------- outputs (the rules of k_ric12<RIC_LQR>)
@@ -394,7 +454,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
     double xv[12];
 #pragma unroll
     for (int j = 0; j < 12; ++j) xv[j] = x[j];
-    double* rs = base + RM_FS;   // the record slot is dead
+    double* rs = Gb + g * 12;    // the G' buffers are dead
 #pragma unroll
     for (int rr = 0; rr < 3; ++rr) {
       const int i = t + 4 * rr;

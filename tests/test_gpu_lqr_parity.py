@@ -12,17 +12,18 @@ from noc_b200 import problems as pb
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[(0, 0), (1, 0), (1, 1)],
-                ids=["small-batch-kernel", "tensor-core-sweep", "dfma-sweep"])
+@pytest.fixture(scope="module", params=[(0, 0, 0), (1, 0, 0), (1, 0, 1), (1, 0, 2), (1, 1, 0)],
+                ids=["small-batch-kernel", "tensor-core-sweep", "tensor-core-sweep-interlock", "tensor-core-sweep-direct", "dfma-sweep"])
 def solver(request):
     """Every test of this module runs three times: batches of at most two instances per SM go to the warp-per-instance
     recursion (k_ric12_tp<DFMA>, one chunk) by default; with NOC_OPT_NO_SMALL_BATCH_KERNEL they go to the
-    8-instances-per-warp sweeps — k_ric12_mma (products on the FP64 tensor cores, A_THEN_B records) and, with
-    NOC_OPT_NO_TENSOR_SWEEP, k_ric12 (DFMA chains).  All three must reproduce the oracle bit for bit."""
+    8-instances-per-warp sweeps — k_ric12_mma (products on the FP64 tensor cores, A_THEN_B records; its three staging
+    variants) and, with NOC_OPT_NO_TENSOR_SWEEP, k_ric12 (DFMA chains).  All must reproduce the oracle bit for bit."""
     from noc_b200 import capi
     s = capi.Solver(0)
     s.set_option(capi.OPT_NO_SMALL_BATCH_KERNEL, request.param[0])
     s.set_option(capi.OPT_NO_TENSOR_SWEEP, request.param[1])
+    s.set_option(capi.OPT_TENSOR_SWEEP_VARIANT, request.param[2])
     yield s
     s.close()
 

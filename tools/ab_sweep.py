@@ -26,8 +26,9 @@ def main():
     s.linearize_batch(prob, batch, xbar, ubar, AB)
     out = {}
     res = {}
-    for name, flag in (("k_ric12_mma", 0), ("k_ric12", 1)):
+    for name, flag, variant in (("k_ric12_mma", 0, 0), ("k_ric12_mma_interlock", 0, 1), ("k_ric12_mma_direct", 0, 2), ("k_ric12", 1, 0)):
         s.set_option(capi.OPT_NO_TENSOR_SWEEP, flag)
+        s.set_option(capi.OPT_TENSOR_SWEEP_VARIANT, variant)
         K = torch.empty(batch, N, 4, 12, dtype=torch.float64, device=dev)
         P0 = torch.empty(batch, 12, 12, dtype=torch.float64, device=dev)
         cost = torch.empty(batch, dtype=torch.float64, device=dev)
@@ -47,9 +48,11 @@ def main():
         ms = e0.elapsed_time(e1) / reps
         out[name] = {"ms": ms, "solves_per_s": batch / ms * 1e3, "hbm_frac": batch * N * 1920 / (ms * 1e-3) / 1e9 / 6550.4}
         res[name] = (K, P0, cost, status)
-    a, b = res["k_ric12_mma"], res["k_ric12"]
-    out["bit_identical"] = bool(all(torch.equal(x.view(torch.int64) if x.dtype == torch.float64 else x,
-                                                y.view(torch.int64) if y.dtype == torch.float64 else y) for x, y in zip(a, b)))
+    b = res["k_ric12"]
+    out["bit_identical"] = {n: bool(all(torch.equal(x.view(torch.int64) if x.dtype == torch.float64 else x,
+                                                     y.view(torch.int64) if y.dtype == torch.float64 else y) for x, y in zip(a, b)))
+                            for n, a in res.items() if n != "k_ric12"}
+    a = res["k_ric12_mma"]
     out["status_ok"] = bool((a[3] == 0).all().item())
     out["batch"], out["N"] = batch, N
     print(json.dumps(out))

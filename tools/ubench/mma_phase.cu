@@ -19,12 +19,12 @@ __global__ void k_fill(double* AB, long long n) {
   }
 }
 
-template <int W, int C>
+template <int W, int C, bool D>
 void run(const Ric12Args& a0, long long* dtm, int batch, int N, const char* name) {
   Ric12Args a = a0;
   a.iters = reinterpret_cast<int32_t*>(dtm);
-  auto kern = k_ric12_mma<W, C>;
-  const size_t smem = ric12_mma_smem_bytes(W);
+  auto kern = k_ric12_mma<W, C, D>;
+  const size_t smem = ric12_mma_smem_bytes<D>(W);
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
   const unsigned grid = (batch + 8 * W - 1) / (8 * W);
@@ -55,7 +55,9 @@ int main(int argc, char** argv) {
   CK(cudaMemcpy(W, w.data(), 400 * 8, cudaMemcpyHostToDevice));
   Ric12Args a{};
   a.AB = AB; a.W = W; a.Qf = W + 256; a.K = K; a.P0 = P0; a.batch = batch; a.N = N;
-  run<8, 1>(a, dtm, batch, N, "8 warps x 1 CTA (phase interlock)");
-  run<4, 2>(a, dtm, batch, N, "4 warps x 2 CTAs (free-running)");
+  run<8, 1, false>(a, dtm, batch, N, "TMA-staged records, 8 warps x 1 CTA (phase interlock)");
+  run<4, 2, false>(a, dtm, batch, N, "TMA-staged records, 4 warps x 2 CTAs (free-running)");
+  run<4, 3, true>(a, dtm, batch, N, "fragments from L2, 4 warps x 3 CTAs");
+  run<4, 2, true>(a, dtm, batch, N, "fragments from L2, 4 warps x 2 CTAs");
   return 0;
 }
