@@ -231,14 +231,14 @@ def bind_to_gpu_numa(torch, local):
 
 def current_kernel_traffic():
     """dram bytes per launch of the headline kernel from the committed ncu capture — only if that capture was taken on
-    the kernel source this library was built from (sha256 of riccati12.cuh); otherwise None, never a stale number."""
+    the kernel source this library was built from (sha256 of riccati12_mma.cuh); otherwise None, never a stale number."""
     import hashlib
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         rec = json.load(open(tp))
-        sha = hashlib.sha256(open(os.path.join(ROOT, "noc_b200", "csrc", "riccati12.cuh"), "rb").read()).hexdigest()
-        if rec.get("riccati12_cuh_sha256") == sha:
-            return rec.get("k_ric12_dram_bytes_per_launch_65536"), rec.get("source")
+        sha = hashlib.sha256(open(os.path.join(ROOT, "noc_b200", "csrc", "riccati12_mma.cuh"), "rb").read()).hexdigest()
+        if rec.get("riccati12_mma_cuh_sha256") == sha:
+            return rec.get("k_ric12_mma_dram_bytes_per_launch_65536"), rec.get("source")
     except Exception:
         pass
     return None, None
@@ -492,9 +492,25 @@ def _run_noc(args):
         solver.set_option(capi.OPT_TIME_PARALLEL_DFMA, 0)
         solver.set_option(capi.OPT_TIME_PARALLEL_CHUNKS, 0)
         dmma["what"] = ("k_ric12_tp<DMMA> vs <DFMA>, chunks = 1: one warp per instance, G = P F and H = W + F'G as "
-                        "mma.sync.m8n8k4.f64 tiles (24 per step) vs DFMA chains; same records and outputs as `value` "
-                        "(tolerance parity, tests/test_gpu_time_parallel.py); the headline k_ric12 (4 lanes per instance, "
-                        "DFMA, bitwise parity) is `value`")
+                        "mma.sync.m8n8k4.f64 tiles (24 per step) vs DFMA chains; same records and outputs as `value`; the "
+                        "headline kernel (`value`) is k_ric12_mma: eight instances per warp, the same products as 21 DMMAs "
+                        "per instance-step, bit-identical to the oracle")
+        # A/B of the headline kernel: the same call with the products as DFMA chains (k_ric12, round 1's kernel)
+        solver.set_option(capi.OPT_NO_TENSOR_SWEEP, 1)
+        fn = lambda: solver.lqr_solve_batch(p_ltv, B, d_AB, d_qr, x0dev=d_x0, K=d_K, K0=d_K0, cost=d_cost, status=d_status)
+        fn()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(5):
+            fn()
+        s1.record(stream)
+        torch.cuda.synchronize()
+        solver.set_option(capi.OPT_NO_TENSOR_SWEEP, 0)
+        tms = s0.elapsed_time(s1) / 5
+        dmma["dfma_chains_k_ric12"] = {"ms_per_step": tms, "value": B / tms * 1e3, "unit": UNIT,
+                                       "hbm_frac": B * N * BYTES_PER_STEP / (tms * 1e-3) / 1e9 / measured_peaks()[0]["hbm_gbs"],
+                                       "what": "NOC_OPT_NO_TENSOR_SWEEP: the headline call on k_ric12 (DFMA chains), bit-identical outputs"}
     del d_AB, d_K
     torch.cuda.empty_cache()
 
@@ -556,7 +572,8 @@ def _run_noc(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                          "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peaks_kind,
-                         "kernel": "k_ric12<LAYOUT_A_THEN_B,RIC_LQR>", "kernel_ms": ric_avg_ms, "kernel_launches": ric_n,
+                         "kernel": "k_ric12_mma (n=12 LTV sweep, products on the FP64 tensor cores, A_THEN_B records)",
+                         "kernel_ms": ric_avg_ms, "kernel_launches": ric_n,
                          "algorithmic_bytes_per_launch": B * N * BYTES_PER_STEP,
                          "kernel_share_of_step": ric_ms / ms if world == 1 else None,
                          "fp64": {"achieved_tflops_symmetric_count": fp64_ach, "peak_tflops_measured_dfma": fp64_peak,

@@ -432,7 +432,7 @@ int launch_ric12_tp(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const d
   a.batch = batch; a.N = p->N;
   plan_time_parallel(p->N, &a.chunks, &a.len);
   bool dfma = ctx->opt[NOC_OPT_TIME_PARALLEL_DFMA] != 0;   // comparison build of the same kernel without tensor cores
-  if (bitwise) { a.chunks = 1; a.len = p->N; dfma = true; }
+  if (bitwise) { a.chunks = 1; a.len = p->N; }   // (DMMA evaluates the same ascending fma chains: tools/ubench/dmma_order.cu)
   else if (ctx->opt[NOC_OPT_TIME_PARALLEL_CHUNKS] > 0) {          // forced plan (measurements): C chunks of equal length
     a.chunks = (int)std::min<int64_t>(ctx->opt[NOC_OPT_TIME_PARALLEL_CHUNKS], std::min<int64_t>(TP_MAX_CHUNKS, p->N));
     a.len = a.chunks > 1 ? std::max(1, p->N / a.chunks) : p->N;
