@@ -252,7 +252,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
 #pragma unroll
       for (int ki = 0; ki < 3; ++ki) {
         pa[q & 1][ki][0] = PHq[po[0][ki]];
-        pa[q & 1][ki][1] = p1on ? PHq[po[1][ki]] : zpad[0];      // padding rows of the second M tile read zeros
+        double p1 = 0.0;                                          // padding rows of the second M tile are zeros
+        if (p1on) p1 = PHq[po[1][ki]];                            // (a predicated load: half the wavefronts)
+        pa[q & 1][ki][1] = p1;
       }
     };
     const bool more = it + 1 < N;
