@@ -130,7 +130,9 @@ typedef enum {
   NOC_OPT_TENSOR_SWEEP_VARIANT = 7, /* measurements: 0 = default (records staged in shared memory by TMA, eight free-running warps per
                                       SM), 1 = + phase interlock of the two warps of a scheduler, 2 = no staging: fragments read
                                       straight from L2, twelve warps per SM.  All bit-identical; 0 is the fastest */
-  NOC_OPT_COUNT = 8
+  NOC_OPT_NO_WAVE_PLAN = 8,        /* 1: SLQ backward sweeps use the fixed launch shapes of round 1 (seven warps per CTA above two
+                                      instances-slots per SM, else one) instead of the balanced wave plan */
+  NOC_OPT_COUNT = 9
 } noc_option;
 int noc_set_option(noc_ctx* ctx, int option, int64_t value);
 /* Device memory for callers that do not link the CUDA runtime themselves (the C++ facade, cgo / ctypes bindings):

@@ -14,6 +14,7 @@
 #include <mutex>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -64,7 +65,7 @@ struct noc_ctx {
   // scheduler options (noc_set_option)
   int64_t opt[NOC_OPT_COUNT] = {0};
   // kernels whose function attributes (dynamic shared memory, carve-out) have been set on this context's device
-  std::unordered_set<const void*> configured;
+  std::unordered_map<const void*, size_t> configured;   // kernel -> largest dynamic shared-memory size it was configured for
   // scratch budgets already granted, per call signature (scratch_budget)
   struct BudgetKey { int entry; int n, N, extra; int64_t batch; size_t budget; };
   std::vector<BudgetKey> budgets;
@@ -271,10 +272,11 @@ int check_prob(noc_ctx* ctx, const noc_problem_t* p, int64_t batch) {
 // Function attributes are per device; a context is bound to one device, so each kernel is configured once per
 // context (the SLQ loop launches the same instantiations hundreds of times per call).
 int configure_kernel(noc_ctx* ctx, const void* kern, size_t smem, bool carveout) {
-  if (ctx->configured.count(kern)) return NOC_OK;
+  auto it = ctx->configured.find(kern);
+  if (it != ctx->configured.end() && it->second >= smem) return NOC_OK;
   NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (carveout) NOC_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-  ctx->configured.insert(kern);
+  ctx->configured[kern] = smem;
   return NOC_OK;
 }
 
@@ -285,11 +287,38 @@ bool misaligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u)
 template <int MODE> struct RicCfg { static constexpr int warps = 4, min_ctas = 2; };
 template <> struct RicCfg<RIC_AFFINE> { static constexpr int warps = 7, min_ctas = 1; };
 
+// Wave plan of a latency-bound sweep over a work list (the SLQ backward pass, whose list shrinks from iteration to
+// iteration).  Every warp runs the same N dependent steps, so a launch costs (number of rounds) x T(w), where w is the
+// number of warps resident per SM and T(w) = T(1) (1 + slope (w - 1)) grows slowly with w (n=12: 0.43 -> 0.76 ms from one
+// to seven warps per SM at N=200; profiles/launches_cfg3_slq_r01d.csv).  The wide configuration (one CTA of `wide`
+// warps per SM) pays T(wide) per wave however few SMs the last wave fills; one-warp CTAs spread breadth-first over the
+// SMs, and capping their residency at w per SM (by the size of the dynamic shared-memory request) turns e.g. 1.14 wide
+// waves (2 x T(7)) into two balanced rounds of four warps per SM (2 x T(4)).  Returns 0 for the wide configuration,
+// else the residency cap w of the one-warp configuration.
+constexpr size_t kSmemPerSm = 233472, kSmemPerCtaReserved = 1024, kSmemMaxDynamic = 232448;
+int plan_waves(int64_t nw, int sms, int wide, size_t narrow_smem, double slope) {
+  auto T = [&](int w) { return 1.0 + slope * (w - 1); };
+  const int narrow_max = (int)std::min<size_t>(kSmemPerSm / (narrow_smem + kSmemPerCtaReserved), 16);
+  double best = (double)((nw + (int64_t)wide * sms - 1) / ((int64_t)wide * sms)) * T(wide);
+  int pick = 0;
+  for (int w = 1; w <= narrow_max; ++w) {
+    const double c = (double)((nw + (int64_t)w * sms - 1) / ((int64_t)w * sms)) * T(w);
+    if (c < best - 1e-9) { best = c; pick = w; }
+  }
+  return pick;
+}
+// dynamic shared-memory request that lets exactly `w` CTAs share an SM
+size_t smem_for_residency(int w, size_t need) {
+  size_t s = (kSmemPerSm / (size_t)w - kSmemPerCtaReserved) & ~(size_t)127;
+  return std::min(std::max(s, need), kSmemMaxDynamic);
+}
+
 template <int LAYOUT, int MODE, bool FUSED, int W, int MIN_CTAS, bool BOX = false>
-int launch_ric12_cfg(noc_ctx* ctx, const Ric12Args& a) {
+int launch_ric12_cfg(noc_ctx* ctx, const Ric12Args& a, int residency = 0) {
   auto kern = k_ric12<LAYOUT, MODE, FUSED, W, MIN_CTAS, BOX>;
-  const size_t smem = ric12_smem_bytes<MODE, FUSED>(W);
-  int rc = configure_kernel(ctx, (const void*)kern, smem, true);
+  const size_t need = ric12_smem_bytes<MODE, FUSED>(W);
+  const size_t smem = residency > 0 ? smem_for_residency(residency, need) : need;
+  int rc = configure_kernel(ctx, (const void*)kern, residency > 0 ? kSmemMaxDynamic : need, true);
   if (rc) return rc;
   const long long per_cta = 8LL * W;
   const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
@@ -303,6 +332,11 @@ int launch_ric12_cfg(noc_ctx* ctx, const Ric12Args& a) {
 
 template <int LAYOUT, int MODE, bool FUSED = false, bool BOX = false>
 int launch_ric12(noc_ctx* ctx, const Ric12Args& a) {
+  if (MODE == RIC_AFFINE && !ctx->opt[NOC_OPT_NO_WAVE_PLAN]) {
+    const int w = plan_waves((a.batch + 7) / 8, ctx->sm_count, RicCfg<MODE>::warps, ric12_smem_bytes<MODE, FUSED>(1), 0.128);
+    if (w > 0) return launch_ric12_cfg<LAYOUT, MODE, FUSED, 1, 1, BOX>(ctx, a, w);
+    return launch_ric12_cfg<LAYOUT, MODE, FUSED, RicCfg<MODE>::warps, RicCfg<MODE>::min_ctas, BOX>(ctx, a);
+  }
   // short work lists (the tail of an SLQ solve, small batches): one warp per CTA, so that the few warps spread over
   // all SMs instead of sharing a handful — the sweep is then latency-bound and a warp alone on an SM steps ~2x faster
   if (a.batch <= 8LL * 2 * ctx->sm_count) return launch_ric12_cfg<LAYOUT, MODE, FUSED, 1, 1, BOX>(ctx, a);
@@ -341,10 +375,11 @@ template <int MODE> struct Ric24Cfg { static constexpr int warps = 8; };
 template <> struct Ric24Cfg<RIC_AFFINE> { static constexpr int warps = 7; };
 
 template <int LAYOUT, int MODE, bool FUSED, int W, bool BOX = false>
-int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a) {
+int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a, int residency = 0) {
   auto kern = k_ric24<LAYOUT, MODE, FUSED, W, BOX>;
-  const size_t smem = ric24_smem_bytes<MODE, FUSED, BOX>(W);
-  int rc = configure_kernel(ctx, (const void*)kern, smem, true);
+  const size_t need = ric24_smem_bytes<MODE, FUSED, BOX>(W);
+  const size_t smem = residency > 0 ? smem_for_residency(residency, need) : need;
+  int rc = configure_kernel(ctx, (const void*)kern, residency > 0 ? kSmemMaxDynamic : need, true);
   if (rc) return rc;
   const long long per_cta = 2LL * W;
   const unsigned grid = (unsigned)((a.batch + per_cta - 1) / per_cta);
@@ -358,6 +393,11 @@ int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a) {
 
 template <int LAYOUT, int MODE, bool FUSED = false, bool BOX = false>
 int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
+  if (MODE == RIC_AFFINE && !ctx->opt[NOC_OPT_NO_WAVE_PLAN]) {   // (n=24: 0.62 -> 0.90 ms from one to seven warps per SM at N=100)
+    const int w = plan_waves((a.batch + 1) / 2, ctx->sm_count, Ric24Cfg<MODE>::warps, ric24_smem_bytes<MODE, FUSED, BOX>(1), 0.075);
+    if (w > 0) return launch_ric24_cfg<LAYOUT, MODE, FUSED, 1, BOX>(ctx, a, w);
+    return launch_ric24_cfg<LAYOUT, MODE, FUSED, Ric24Cfg<MODE>::warps, BOX>(ctx, a);
+  }
   // short work lists: one warp (two instances) per CTA so that the latency-bound tail spreads over all SMs
   if (a.batch <= 2LL * 2 * ctx->sm_count) return launch_ric24_cfg<LAYOUT, MODE, FUSED, 1, BOX>(ctx, a);
   return launch_ric24_cfg<LAYOUT, MODE, FUSED, Ric24Cfg<MODE>::warps, BOX>(ctx, a);
