@@ -132,7 +132,10 @@ typedef enum {
                                       straight from L2, twelve warps per SM.  All bit-identical; 0 is the fastest */
   NOC_OPT_NO_WAVE_PLAN = 8,        /* 1: SLQ backward sweeps use the fixed launch shapes of round 1 (seven warps per CTA above two
                                       instances-slots per SM, else one) instead of the balanced wave plan */
-  NOC_OPT_COUNT = 9
+  NOC_OPT_DEFERRED_BACKTRACK = 9,  /* 1: the SLQ line search settles the rejected instances beside the next backward sweep, on the
+                                      auxiliary stream, and they rejoin the work list one sweep later (same results; measured slower
+                                      on the BASELINE configs — the extra sweeps of the stragglers cost more) */
+  NOC_OPT_COUNT = 10
 } noc_option;
 int noc_set_option(noc_ctx* ctx, int option, int64_t value);
 /* Device memory for callers that do not link the CUDA runtime themselves (the C++ facade, cgo / ctypes bindings):

@@ -48,7 +48,7 @@ struct noc_ctx {
   cudaStream_t copy_stream = nullptr;   // device->host copies of finished chunks, overlapped with the next chunk
   cudaStream_t aux_stream = nullptr;    // every other inner chunk of a from-x0 call: neighbouring sweeps overlap at their edges
   cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr, defer_ev = nullptr;
   cudaEvent_t pipe_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // host-AB pipeline: in / swept / out x 2 buffers
   std::string err;
   int64_t launches = 0;
@@ -844,7 +844,26 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
   int count = (int)batch;
   int32_t* cur = (int32_t*)didx0;
   int32_t* nxt = (int32_t*)didx1;
-  for (int it = 0; it < p->max_iter && count > 0; ++it) {
+  // Deferred backtracking (opt-in, NOC_OPT_DEFERRED_BACKTRACK: measured SLOWER, see the end of this comment).  The instances whose full step was rejected (1-2 % per iteration without input limits) get
+  // all their shorter step lengths as parallel candidates; that round is a latency-bound launch set (0.2-0.7 ms) the
+  // whole batch used to wait for.  It now runs on the auxiliary stream while the main stream goes on with the next
+  // backward sweep of everybody else; the settled instances rejoin the work list one sweep later (they carry their own
+  // iteration index, iters[b], so records and limits are per instance and the results do not depend on the schedule).
+  // `pending_bit`: the flag bit the round in flight marks its continuing instances with (alternating 4 / 8).
+  // Measured on config 3 (16,384 x N=200): 70.1 ms synchronous; 87.5 ms deferring throughout (75 sweeps instead of 50: a
+  // straggler that backtracks 25 times finishes 25 latency-bound sweeps later); 76.0 ms deferring only while the list
+  // fills a wide wave (59 sweeps).  The hidden round is worth less than the sweeps it adds, so the default stays
+  // synchronous; results are identical either way (tests/test_gpu_dare_slq_parity.py runs both).
+  const bool defer_ok = ctx->opt[NOC_OPT_DEFERRED_BACKTRACK] != 0;
+  int pending_bit = 0;
+  cudaEvent_t pending_ev = nullptr;
+  cudaStream_t const main_stream = ctx->stream;
+  struct RestoreStream { noc_ctx* c; cudaStream_t s; ~RestoreStream() { c->stream = s; cudaStreamSynchronize(c->aux_stream); } } restore{ctx, main_stream};
+  const int sweep_limit = p->max_iter * (p->n_alpha + 1) + 2;   // (a bound, never reached: every sweep advances somebody)
+  for (int it = 0; it < sweep_limit && (count > 0 || pending_bit); ++it) {
+   int new_pending_bit = 0;
+   cudaEvent_t new_pending_ev = nullptr;
+   if (count > 0) {
     // a1 happens inside the sweep (k_ric12 / k_ric24 <…, RIC_AFFINE, FUSED>)
     // a2+a3: affine backward pass (regularisation retries in-kernel)
     ra.AB = (const double*)dAB; ra.idx = cur; ra.xbar = (const double*)dx; ra.ubar = (const double*)du;
@@ -874,6 +893,7 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
     fa.iter = it; fa.max_iter = p->max_iter; fa.n_alpha = p->n_alpha; fa.dt = p->dt; fa.tol = p->tol;
     fa.armijo = p->armijo; fa.u_min = p->u_min; fa.u_max = p->u_max;
     fa.mu = (double*)dmu; fa.delta = (double*)ddelta; fa.reg_schedule = p->reg_schedule;
+    fa.cont_bit = 1;
     int32_t hc[2] = {0, 0};
     const int32_t* list = cur;
     int list_count = count;
@@ -915,7 +935,47 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
       const size_t per_cand = sizeof(double) * ((N + 1) * n + N * m + (N + 1));
       if (trial == 0 && list_count > 0 && J > 0) {
         const int round_J = ((size_t)list_count * J > 2 * (size_t)count) ? std::min(J, 4) : J;
-        if ((size_t)list_count * round_J * per_cand <= ((size_t)2 << 30)) {
+        // (only while the sweeps are throughput-bound, i.e. the work list fills at least one wide wave: a deferred instance
+        // finishes one sweep later, and in the latency-bound tail every extra sweep costs what the hidden round saves —
+        // deferring throughout took config 3 from 70 to 88 ms, 75 sweeps instead of 50)
+        const bool head = (size_t)count >= (size_t)ctx->sm_count * (MODEL == 0 ? 56 : 14);
+        if (defer_ok && head && round_J == J && (size_t)list_count * J * per_cand <= ((size_t)2 << 30)) {
+          // one round settles every rejected instance: run it beside the next sweep
+          void *dxc, *duc, *dlcc;
+          const size_t rc_ = (size_t)list_count * J;
+          int e1 = scratch(ctx, SCR_XC, sizeof(double) * rc_ * (N + 1) * n, &dxc);
+          int e2 = e1 ? e1 : scratch(ctx, SCR_UC, sizeof(double) * rc_ * N * m, &duc);
+          int e3 = e2 ? e2 : scratch(ctx, SCR_LCC, sizeof(double) * rc_ * (N + 1), &dlcc);
+          if (e3) return e3;
+          new_pending_bit = (it & 1) ? 8 : 4;
+          new_pending_ev = (it & 1) ? ctx->join_ev : ctx->fork_ev;
+          NOC_CUDA(ctx, cudaEventRecord(ctx->defer_ev, main_stream));
+          NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->defer_ev, 0));
+          ctx->stream = ctx->aux_stream;   // the launches below (and their profiling events) go to the auxiliary stream
+          fa.idx = list; fa.trial = 1; fa.cand_J = J; fa.cand_first = 1; fa.cand_last = 1;
+          fa.xc = (double*)dxc; fa.uc = (double*)duc; fa.lcc = (double*)dlcc;
+          fa.count = (int)rc_;
+          fa.cont_bit = new_pending_bit;
+          {
+            LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+            k_slq_rollout<MODEL><<<(unsigned)((rc_ + FC::inst - 1) / FC::inst), FC::threads, fwd_smem, ctx->stream>>>(fa);
+          }
+          {
+            const long long total = (long long)rc_ * (p->N + 1);
+            LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+            k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fa);
+          }
+          fa.count = list_count;
+          {
+            LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+            k_slq_accept_cand<MODEL><<<(unsigned)((list_count + 3) / 4), 128, 0, ctx->stream>>>(fa);
+          }
+          ctx->stream = main_stream;
+          NOC_CUDA(ctx, cudaGetLastError());
+          NOC_CUDA(ctx, cudaEventRecord(new_pending_ev, ctx->aux_stream));
+          fa.cand_J = 0; fa.cont_bit = 1;
+          list_count = 0;
+        } else if ((size_t)list_count * round_J * per_cand <= ((size_t)2 << 30)) {
           int first = 1;
           while (list_count > 0 && first < p->n_alpha) {
             const int Jr = std::min(round_J, p->n_alpha - first);
@@ -962,16 +1022,26 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
         }
       }
     }
+   }  // count > 0
+    int32_t hn = 0;
+    int mask = 1;
+    if (pending_bit) {   // the round deferred one sweep ago has to be complete before its instances rejoin
+      NOC_CUDA(ctx, cudaStreamWaitEvent(main_stream, pending_ev, 0));
+      mask |= pending_bit;
+    }
     {  // instances that go on to the next iteration -> sorted work list
       LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-      k_compact_flags<<<1, 1024, 0, ctx->stream>>>((int32_t*)dflags, 1, batch, nxt, (int32_t*)dcount);
+      k_compact_flags<<<1, 1024, 0, ctx->stream>>>((int32_t*)dflags, mask, batch, nxt, (int32_t*)dcount);
     }
     NOC_CUDA(ctx, cudaGetLastError());
-    NOC_CUDA(ctx, cudaMemcpyAsync(hc, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    NOC_CUDA(ctx, cudaMemcpyAsync(&hn, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
     NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    count = hc[0];
+    count = hn;
     std::swap(cur, nxt);
+    pending_bit = new_pending_bit;
+    pending_ev = new_pending_ev;
   }
+  NOC_CUDA(ctx, cudaStreamSynchronize(ctx->aux_stream));
   return flush_out(ctx, false);
 }
 
@@ -1090,6 +1160,7 @@ int noc_create(noc_ctx** out, int device_id) {
   for (auto& e : c->chunk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming) == cudaSuccess;
   ok = ok && cudaEventCreateWithFlags(&c->join_ev, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&c->defer_ev, cudaEventDisableTiming) == cudaSuccess;
   for (auto& e : c->pipe_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {   // noc_destroy releases whatever was created (every handle starts as nullptr)
     cudaGetLastError();
@@ -1114,6 +1185,7 @@ void noc_destroy(noc_ctx* ctx) {
     if (e) cudaEventDestroy(e);
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
+  if (ctx->defer_ev) cudaEventDestroy(ctx->defer_ev);
   if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

@@ -120,6 +120,7 @@ __global__ void __launch_bounds__(128) k_slq_init(const double* __restrict__ x0,
 
 struct SlqFwdArgs {
   const int32_t* idx;       // [count] active instances
+  int cont_bit;             // the flag bit an instance that continues gets (1; 4 or 8 from a deferred backtracking round)
   int32_t* flags;           // [batch] bit 0: continues with the next SLQ iteration; bit 1: trial rejected, try the next
                             // step length.  k_compact_flags turns the bits into SORTED work lists: a list in
                             // instance order keeps the per-instance streams of a warp at a regular stride (an
@@ -350,8 +351,11 @@ __global__ void __launch_bounds__(128) k_slq_stage_cost(const SlqFwdArgs a) {
 // (3) per instance: J = sum of the stage costs in ascending k (the oracle's order), Armijo test, bookkeeping,
 // convergence test, next work list / retry list
 // bookkeeping of an accepted step (trial index `accepted`, cost Jacc): records, convergence test, next work list
+// (The iteration index is the INSTANCE's own count, iters[b]: with deferred backtracking, noc_b200.cu, an instance that
+// needed a shorter step rejoins the work list one sweep later than the instances that did not.)
 __device__ __forceinline__ void slq_record_step(const SlqFwdArgs& a, long long b, double Jold, double Jacc, int accepted) {
-  if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + a.iter] = accepted;
+  const int itb = a.iters[b];
+  if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + itb] = accepted;
   if (a.reg_schedule == 1) {   // accepted step: relax the regularisation
     double mu = a.mu[b], dl = a.delta[b];
     reg_decrease(mu, dl);
@@ -360,26 +364,27 @@ __device__ __forceinline__ void slq_record_step(const SlqFwdArgs& a, long long b
   const double denom = (Jold > 1e-12) ? Jold : 1e-12;
   const double rel = (Jold - Jacc) / denom;
   a.J[b] = Jacc;
-  a.iters[b] = a.iter + 1;
+  a.iters[b] = itb + 1;
   if (rel < a.tol) {
     a.status[b] = 0;
     return;
   }
-  if (a.iter + 1 < a.max_iter) a.flags[b] |= 1;
+  if (itb + 1 < a.max_iter) a.flags[b] |= a.cont_bit;
 }
 
 // no step length passed (the nominal has been put back).  Default schedule: the instance stops with LS_FAIL.  Adaptive
 // schedule: mu is raised and the iteration is repeated from the same nominal (recorded as alpha_idx = -2) unless mu
 // leaves its range.  Called by one lane.
 __device__ __forceinline__ void slq_line_search_failed(const SlqFwdArgs& a, long long b) {
-  a.iters[b] = a.iter + 1;
+  const int itb = a.iters[b];
+  a.iters[b] = itb + 1;
   if (a.reg_schedule == 1) {
     double mu = a.mu[b], dl = a.delta[b];
     reg_increase(mu, dl);
     a.mu[b] = mu; a.delta[b] = dl;
     if (!(mu > 1e6)) {
-      if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + a.iter] = -2;
-      if (a.iter + 1 < a.max_iter) a.flags[b] |= 1;
+      if (a.alpha_idx) a.alpha_idx[(size_t)b * a.max_iter + itb] = -2;
+      if (itb + 1 < a.max_iter) a.flags[b] |= a.cont_bit;
       return;
     }
   }
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
   if (a.trial == 0 && a.bstatus[b] != 0) {  // regularisation exhausted in the backward pass
     if (lane == 0) {
       a.status[b] = 4;
-      a.iters[b] = a.iter + 1;
+      a.iters[b] = a.iters[b] + 1;
     }
     return;
   }

@@ -9,10 +9,15 @@ from noc_b200 import problems as pb
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def solver():
+@pytest.fixture(scope="module", params=[(0, 0), (1, 1)], ids=["default-schedule", "fixed-shapes+deferred-backtracking"])
+def solver(request):
+    """Every test of this module runs under both SLQ schedules: the default (balanced wave plan, the line search settled
+    before the next sweep) and round 1's fixed launch shapes with the line search's backtracking round deferred beside
+    the next sweep (NOC_OPT_NO_WAVE_PLAN, NOC_OPT_DEFERRED_BACKTRACK).  A schedule never changes a result."""
     from noc_b200 import capi
     s = capi.Solver(0)
+    s.set_option(capi.OPT_NO_WAVE_PLAN, request.param[0])
+    s.set_option(capi.OPT_DEFERRED_BACKTRACK, request.param[1])
     yield s
     s.close()
 
