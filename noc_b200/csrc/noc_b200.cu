@@ -21,6 +21,7 @@
 #include "pipeline_kernels.cuh"
 #include "riccati12.cuh"
 #include "riccati24.cuh"
+#include "riccati24_mma.cuh"
 #include "riccati_generic.cuh"
 #include "riccati_scan.cuh"
 #include "riccati12_mma.cuh"
@@ -222,7 +223,7 @@ int scratch_budget(noc_ctx* ctx, int entry, int n, int N, int extra, int64_t bat
 enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
        SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC, SCR_FLAGS, SCR_XC, SCR_UC, SCR_LCC,
        SCR_PIPE_AB0, SCR_PIPE_AB1, SCR_PIPE_X0, SCR_PIPE_X1, SCR_PIPE_QR0, SCR_PIPE_QR1, SCR_PIPE_OUT0,
-       SCR_PIPE_OUT_LAST = SCR_PIPE_OUT0 + 9, SCR_ARGMIN_PART, SCR_COMM_PAIRS, SCR_COMM_COST, SCR_DELTA, SCR_END };
+       SCR_PIPE_OUT_LAST = SCR_PIPE_OUT0 + 9, SCR_ARGMIN_PART, SCR_COMM_PAIRS, SCR_COMM_COST, SCR_DELTA, SCR_PREP, SCR_END };
 
 // W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
 // Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
@@ -391,8 +392,61 @@ int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a, int residency = 0) {
   return NOC_OK;
 }
 
+// The n=24 recursion with its products on the FP64 tensor cores (riccati24_mma.cuh): one instance per warp, A_THEN_B
+// records or the fused linearisation, bit-identical to k_ric24.  Two CTAs of six warps per SM; work lists that do not
+// fill the GPU run as one-warp CTAs (breadth-first over the SMs) with the residency cap of the wave plan.
+constexpr int kRic24MmaWarps = 6, kRic24MmaCtas = 2;
+template <int MODE, bool FUSED, int W, int CTAS, bool BOX, bool PREP>
+int launch_ric24_mma_cfg(noc_ctx* ctx, const Ric24Args& a, const double* prep, int residency = 0) {
+  auto kern = k_ric24_mma<MODE, FUSED, W, CTAS, BOX, PREP>;
+  const size_t need = ric24_mma_smem_bytes<MODE, FUSED, BOX, PREP>(W);
+  const size_t smem = residency > 0 ? smem_for_residency(residency, need) : need;
+  int rc = configure_kernel(ctx, (const void*)kern, residency > 0 ? kSmemMaxDynamic : need, true);
+  if (rc) return rc;
+  const unsigned grid = (unsigned)((a.batch + W - 1) / W);
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+    kern<<<grid, W * 32, smem, ctx->stream>>>(a, prep);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  return NOC_OK;
+}
+template <int MODE, bool FUSED, bool BOX, bool PREP>
+int launch_ric24_mma_shape(noc_ctx* ctx, const Ric24Args& a, const double* prep) {
+  const int wide = kRic24MmaWarps * kRic24MmaCtas;
+  int w = 0;
+  if (MODE == RIC_AFFINE && !ctx->opt[NOC_OPT_NO_WAVE_PLAN])
+    w = plan_waves(a.batch, ctx->sm_count, wide, ric24_mma_smem_bytes<MODE, FUSED, BOX, PREP>(1), 0.10);
+  else if (a.batch <= (long long)wide * ctx->sm_count)
+    w = (int)std::min<long long>(12, (a.batch + ctx->sm_count - 1) / ctx->sm_count);
+  if (w > 0) return launch_ric24_mma_cfg<MODE, FUSED, 1, 1, BOX, PREP>(ctx, a, prep, w);
+  return launch_ric24_mma_cfg<MODE, FUSED, kRic24MmaWarps, kRic24MmaCtas, BOX, PREP>(ctx, a, prep);
+}
+// `prep_buf` (RIC_AFFINE): room for batch x N x M24_PREP_DOUBLES doubles, or nullptr — then (and for RIC_LQR) the record
+// is evaluated inside the sweep
+template <int MODE, bool FUSED, bool BOX>
+int launch_ric24_mma(noc_ctx* ctx, const Ric24Args& a, double* prep_buf = nullptr) {
+  if constexpr (MODE == RIC_AFFINE) {
+    if (prep_buf) {
+      const long long pairs = a.batch * a.N;
+      int rc = configure_kernel(ctx, (const void*)k_prep24, PREP24_SMEM, false);
+      if (rc) return rc;
+      {
+        LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+        k_prep24<<<(unsigned)((pairs + PREP24_PAIRS - 1) / PREP24_PAIRS), PREP24_THREADS, PREP24_SMEM, ctx->stream>>>(a, prep_buf);
+      }
+      NOC_CUDA(ctx, cudaGetLastError());
+      return launch_ric24_mma_shape<MODE, FUSED, BOX, true>(ctx, a, prep_buf);
+    }
+  }
+  return launch_ric24_mma_shape<MODE, FUSED, BOX, false>(ctx, a, nullptr);
+}
+
 template <int LAYOUT, int MODE, bool FUSED = false, bool BOX = false>
-int launch_ric24(noc_ctx* ctx, const Ric24Args& a) {
+int launch_ric24(noc_ctx* ctx, const Ric24Args& a, double* prep_buf = nullptr) {
+  if constexpr (LAYOUT == 0 && (MODE == RIC_LQR || FUSED)) {
+    if (!ctx->opt[NOC_OPT_NO_TENSOR_SWEEP]) return launch_ric24_mma<MODE, FUSED, BOX>(ctx, a, prep_buf);
+  }
   if (MODE == RIC_AFFINE && !ctx->opt[NOC_OPT_NO_WAVE_PLAN]) {   // (n=24: 0.62 -> 0.90 ms from one to seven warps per SM at N=100)
     const int w = plan_waves((a.batch + 1) / 2, ctx->sm_count, Ric24Cfg<MODE>::warps, ric24_smem_bytes<MODE, FUSED, BOX>(1), 0.075);
     if (w > 0) return launch_ric24_cfg<LAYOUT, MODE, FUSED, 1, BOX>(ctx, a, w);
@@ -821,7 +875,9 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
   if ((rc = scratch(ctx, SCR_RETRY1, sizeof(int32_t) * B, &dretry1))) return rc;
   if ((rc = scratch(ctx, SCR_XN, sizeof(double) * B * (N + 1) * n, &dxn))) return rc;
   if ((rc = scratch(ctx, SCR_UN, sizeof(double) * B * N * m, &dun))) return rc;
-  void *dlc, *dflags;
+  void *dlc, *dflags, *dprep = nullptr;
+  // n=24 on the tensor cores: the step records of k_prep24 (Jacobian entries, W e, ubar), one per (work-list slot, k)
+  if (MODEL == 1 && !ctx->opt[NOC_OPT_NO_TENSOR_SWEEP] && (rc = scratch(ctx, SCR_PREP, sizeof(double) * B * N * M24_PREP_DOUBLES, &dprep))) return rc;
   if ((rc = scratch(ctx, SCR_LC, sizeof(double) * B * (N + 1), &dlc))) return rc;
   if ((rc = scratch(ctx, SCR_FLAGS, sizeof(int32_t) * B, &dflags))) return rc;
   NOC_CUDA(ctx, cudaMemsetAsync(dflags, 0, sizeof(int32_t) * B, ctx->stream));
@@ -877,7 +933,7 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
     }
     else {
       ra.u_min = p->u_min; ra.u_max = p->u_max;
-      rc = boxed ? launch_ric24<0, RIC_AFFINE, true, true>(ctx, ra) : launch_ric24<0, RIC_AFFINE, true>(ctx, ra);
+      rc = boxed ? launch_ric24<0, RIC_AFFINE, true, true>(ctx, ra, (double*)dprep) : launch_ric24<0, RIC_AFFINE, true>(ctx, ra, (double*)dprep);
     }
     if (rc) return rc;
     // a4: closed-loop rollouts with backtracking, acceptance, convergence, next work list.  One launch per step
@@ -1094,7 +1150,8 @@ int slq_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double* 
              int32_t* alpha_idx, int32_t* status) {
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m, N = p->N, B = (size_t)batch;
-  const size_t per_inst = sizeof(double) * (2 * (N + 1) * n + 3 * N * m + N * m * n + (N + 1) + 8) + 4 * (size_t)(8 + p->max_iter);
+  const size_t per_inst = sizeof(double) * (2 * (N + 1) * n + 3 * N * m + N * m * n + (N + 1) + 8 + (MODEL == 1 ? N * M24_PREP_DOUBLES : 0)) +
+                          4 * (size_t)(8 + p->max_iter);
   size_t have = 0, budget = 0;
   for (auto* v : {&ctx->scratch, &ctx->out_slots, &ctx->in_slots})
     for (auto& b : *v) have += b.cap;

@@ -32,8 +32,12 @@ def main():
     path = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 40
     ranges = [a.split(":") for a in sys.argv[2:] if ":" in a]
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    sel = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--kernel=")]   # report with several kernels: pick one by name
+    out = subprocess.run(["ncu", "-i", path] + (["--kernel-name", "regex:" + sel[0]] if sel else []) + ["--page", "source", "--csv"],
+                         capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
+    nxt = [i for i, r in enumerate(rows) if i > 0 and r and r[0] == "Kernel Name"]   # keep the first kernel's block only
+    if nxt: rows = rows[:nxt[0]]
     kname = rows[0][1]
     hdr = rows[1]
     ci = {h: i for i, h in enumerate(hdr)}
@@ -42,7 +46,7 @@ def main():
     funcs = sass_lines(None)
     names = list(funcs)
     demangled = subprocess.run(["c++filt"] + names, capture_output=True, text=True).stdout.splitlines()
-    norm = lambda s: re.sub(r"\((int|bool)\)", "", s).replace("true", "1").replace("false", "0").replace(" ", "")
+    norm = lambda s: re.sub(r"\((int|bool)\)", "", s).replace("true", "1").replace("false", "0").replace("const", "").replace(" ", "")
     match = [n for n, d in zip(names, demangled) if norm(d) == norm(kname)]
     if not match: sys.exit(f"kernel {kname} not found in the cubin")
     lmap = funcs[match[0]]
