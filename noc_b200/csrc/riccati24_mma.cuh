@@ -158,27 +158,56 @@ __host__ __device__ constexpr bool m24_tile_nz(int ki, int ni) {
   return false;
 }
 
-// one column of the left-looking L D L^T (LdlReg<8>::factor, column j), so that the factorisation can be issued in pieces
-// between the DMMAs of the tensor phase
-template <int J>
-__device__ __forceinline__ bool m24_ldl_col(LdlReg<8>& ch, const double* U) {
-  double v[8];
-#pragma unroll
-  for (int l = 0; l < J; ++l) v[l] = ch.L[J][l] * ch.D[l];
-  double s = U[J * 8 + J];
-#pragma unroll
-  for (int l = 0; l < J; ++l) s = fmad(-ch.L[J][l], v[l], s);
-  const bool bad = !(s > R12_PIVOT_MIN) || !(s < R12_PIVOT_MAX);
-  ch.D[J] = s;
-  ch.r[J] = rcp_rn_normal(s);
-#pragma unroll
-  for (int i = J + 1; i < 8; ++i) {
-    double tt = U[i * 8 + J];
-#pragma unroll
-    for (int l = 0; l < J; ++l) tt = fmad(-ch.L[i][l], v[l], tt);
-    ch.L[i][J] = tt * ch.r[J];
+// L D L^T of Huu (8 x 8) DISTRIBUTED over the warp, right-looking, one pivot per call.  After the DMMAs of H' tile (0,0)
+// lane (g, t) holds Huu[a][b0] and Huu[a][b1], a = 7 - g, b0 = 7 - 2t, b1 = 6 - 2t (the C fragment in the permuted order);
+// entries with b > a are dead slots.  Pivot l: D[l] and then column l of L are broadcast by shuffles and every lane applies
+// update l to its own two entries, U[a][b] = fma(-L[a][l], L[b][l] D[l], U[a][b]) for b > l — the spec's left-looking chains
+// term by term and in the same ascending order (§2.3 step 3), so the result is bit-identical to LdlReg<8>::factor, at 12
+// FP64 instructions per pivot instead of 14-30 (every lane used to run the whole factorisation redundantly: 22 % of the
+// sweep's instructions).  Column l of L goes to shared memory (Ls[i*8+l]) for the gain solves; r[] = 1/D stays in registers.
+template <int L>
+__device__ __forceinline__ bool m24_ldl_pivot(double& u0, double& u1, double (&r)[8], double* Ls, int lane) {
+  constexpr int tl = (7 - L) >> 1;             // the lanes t == tl hold column L ...
+  constexpr bool slot1 = (L & 1) == 0;         // ... in u1 (L even) or u0 (L odd)
+  const int g = lane >> 2, t = lane & 3, a = 7 - g;
+  const double mine = slot1 ? u1 : u0;
+  const double d = __shfl_sync(0xffffffffu, mine, (7 - L) * 4 + tl);
+  const bool bad = !(d > R12_PIVOT_MIN) || !(d < R12_PIVOT_MAX);
+  r[L] = rcp_rn_normal(d);
+  if (L < 7) {
+    const double lv = mine * r[L];             // L[a][L] on the lanes t == tl
+    if (t == tl && a > L) Ls[a * 8 + L] = lv;
+    const double la = __shfl_sync(0xffffffffu, lv, (lane & ~3) | tl);
+    const double lb0 = __shfl_sync(0xffffffffu, lv, (2 * t) * 4 + tl);        // row b0 = 7 - 2t lives on g' = 2t
+    const double lb1 = __shfl_sync(0xffffffffu, lv, (2 * t + 1) * 4 + tl);    // row b1 = 6 - 2t on g' = 2t + 1
+    const double n0 = fmad(-la, lb0 * d, u0), n1 = fmad(-la, lb1 * d, u1);
+    if (7 - 2 * t > L) u0 = n0;
+    if (6 - 2 * t > L) u1 = n1;
   }
   return bad;
+}
+// the spec's forward / backward substitution (LdlReg<8>::solve_neg) with L read from shared memory (broadcast loads)
+__device__ __forceinline__ void m24_solve_neg(const double* Ls, const double (&r)[8], const double (&rhs)[8], double (&out)[8]) {
+  double Lr[8][8];
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+#pragma unroll
+    for (int l = 0; l < i; ++l) Lr[i][l] = Ls[i * 8 + l];
+  double y[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    double sacc = rhs[i];
+#pragma unroll
+    for (int l = 0; l < i; ++l) sacc = fmad(-Lr[i][l], y[l], sacc);
+    y[i] = sacc;
+  }
+#pragma unroll
+  for (int i = 7; i >= 0; --i) {
+    double sacc = (-y[i]) * r[i];
+#pragma unroll
+    for (int l = i + 1; l < 8; ++l) sacc = fmad(-Lr[l][i], out[l], sacc);
+    out[i] = sacc;
+  }
 }
 
 template <int MODE, bool FUSED, int WARPS, int MIN_CTAS, bool BOX = false, bool PREP = false>
@@ -450,7 +479,12 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
 #pragma unroll
         for (int mi = 0; mi < 3; ++mi) sts128(Gb + buf * 192 + mi * 64 + cs_off, gacc[buf][mi][0], gacc[buf][mi][1]);
       };
-      LdlReg<8> ch;
+      // RIC_LQR: the Hxx tiles of H' stay in registers — they are the accumulators of P' (48 wavefronts less per step).  The
+      // SLQ pass has no registers to spare for them (204 bytes of spills, 2.84 -> 3.01 ms): its tiles wait in the P slots.
+      constexpr bool KEEP_HXX = !AFF;
+      double pacc[6][2];
+      double ldr[8], lu0 = 0.0, lu1 = 0.0;   // the distributed factorisation: 1 / D and the lane's two entries of Huu
+      double* Ls = Hu;                         // column store of L: the unused slot of the u-row tiles
       gprod(0, 0);
       gstore(0);
       __syncwarp();
@@ -463,6 +497,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
         double hacc2[4][2];
 #pragma unroll
         for (int mi = 0; mi <= nj; ++mi) {
+          if (mi == 0 && nj > 0) { hacc2[0][0] = 0.0; hacc2[0][1] = 0.0; continue; }   // W is block diagonal: Hux starts from 0
           const double2 wv = lds128(Wt + m24_t4(mi, nj) * 64 + g * 8 + 2 * t);
           hacc2[mi][0] = wv.x; hacc2[mi][1] = wv.y;
         }
@@ -481,16 +516,26 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
           }
           Us[(7 - g) * 8 + (7 - 2 * t)] = d0;
           Us[(7 - g) * 8 + (6 - 2 * t)] = d1;
+          lu0 = d0; lu1 = d1;
         } else {
           sts128(Hu + nj * 64 + cs_off, hacc2[0][0], hacc2[0][1]);
 #pragma unroll
-          for (int mi = 1; mi <= nj; ++mi) sts128(Pt + m24_t3(mi - 1, nj - 1) * 64 + cs_off, hacc2[mi][0], hacc2[mi][1]);
+          for (int mi = 1; mi <= nj; ++mi) {
+            if (KEEP_HXX) { pacc[m24_t3(mi - 1, nj - 1)][0] = hacc2[mi][0]; pacc[m24_t3(mi - 1, nj - 1)][1] = hacc2[mi][1]; }
+            else sts128(Pt + m24_t3(mi - 1, nj - 1) * 64 + cs_off, hacc2[mi][0], hacc2[mi][1]);
+          }
         }
         __syncwarp();
         // the factorisation, two columns per column tile of H', in the shadow of the DMMAs still to come
-        if (nj == 0) { failed |= m24_ldl_col<0>(ch, Us); failed |= m24_ldl_col<1>(ch, Us); }
-        if (nj == 1) { failed |= m24_ldl_col<2>(ch, Us); failed |= m24_ldl_col<3>(ch, Us); failed |= m24_ldl_col<4>(ch, Us); }
-        if (nj == 2) { failed |= m24_ldl_col<5>(ch, Us); failed |= m24_ldl_col<6>(ch, Us); failed |= m24_ldl_col<7>(ch, Us); }
+        if (nj == 0) { failed |= m24_ldl_pivot<0>(lu0, lu1, ldr, Ls, lane); failed |= m24_ldl_pivot<1>(lu0, lu1, ldr, Ls, lane); }
+        if (nj == 1) {
+          failed |= m24_ldl_pivot<2>(lu0, lu1, ldr, Ls, lane); failed |= m24_ldl_pivot<3>(lu0, lu1, ldr, Ls, lane);
+          failed |= m24_ldl_pivot<4>(lu0, lu1, ldr, Ls, lane);
+        }
+        if (nj == 2) {
+          failed |= m24_ldl_pivot<5>(lu0, lu1, ldr, Ls, lane); failed |= m24_ldl_pivot<6>(lu0, lu1, ldr, Ls, lane);
+          failed |= m24_ldl_pivot<7>(lu0, lu1, ldr, Ls, lane);
+        }
       }
       if (AFF && !xlane) base[O_HV + (7 - p)] = hacc;
       __syncwarp();
@@ -507,7 +552,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
         double rhs[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) rhs[c] = (AFF && !xlane) ? hur[c] : hux[c];
-        ch.solve_neg(rhs, kk);
+        m24_solve_neg(Ls, ldr, rhs, kk);
       }
       bool cl[8] = {false, false, false, false, false, false, false, false};
       if (AFF) {
@@ -539,11 +584,12 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
             __syncwarp();
             ldl_mask<8>(Us, cl, ws);
             __syncwarp();
-            failed |= ch.factor(ws);
+            LdlReg<8> chm;
+            failed |= chm.factor(ws);
             double rhs[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) rhs[c] = cl[c] ? 0.0 : hux[c];
-            ch.solve_neg(rhs, kk);
+            chm.solve_neg(rhs, kk);
             if (lane == 0) {
 #pragma unroll
               for (int c = 0; c < 8; c += 2) sts128(base + O_KF + c, kf[c], kf[c + 1]);
@@ -604,9 +650,10 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
         for (int ki = 0; ki < 2; ++ki)
 #pragma unroll
           for (int ni = 0; ni < 3; ++ni) bf[ki][ni] = Kb[(4 * ki + t) * 24 + 8 * ni + g];
-        double pacc[6][2];
+        if (!KEEP_HXX) {
 #pragma unroll
-        for (int T = 0; T < 6; ++T) { const double2 v = lds128(Pt + T * 64 + cs_off); pacc[T][0] = v.x; pacc[T][1] = v.y; }
+          for (int T = 0; T < 6; ++T) { const double2 v = lds128(Pt + T * 64 + cs_off); pacc[T][0] = v.x; pacc[T][1] = v.y; }
+        }
 #pragma unroll
         for (int ki = 0; ki < 2; ++ki)
 #pragma unroll
