@@ -70,9 +70,10 @@ inline size_t ric24_mma_smem_bytes(int warps) {
   return sizeof(double) * (size_t)(M24_BAR_DOUBLES + M24_WT_DOUBLES + warps * m24_warp_doubles<MODE, FUSED, BOX, PREP>());
 }
 
-// one thread per (work-list slot w, step k, vehicle v); a CTA's 64 records are assembled in shared memory and written out
-// as one contiguous 58 KB block (every thread storing its own 456 bytes straight to global memory ran at 0.9 TB/s)
-constexpr int PREP24_THREADS = 128, PREP24_PAIRS = PREP24_THREADS / 2;
+// Two threads per (work-list slot w, step k, vehicle v) — one evaluates the Jacobian, the other h0 and ubar (different warps:
+// no divergence) — and a CTA's 64 records are assembled in shared memory and written out as one contiguous 58 KB block
+// (every thread storing its own 456 bytes straight to global memory ran at 0.9 TB/s).
+constexpr int PREP24_PAIRS = 64, PREP24_THREADS = 4 * PREP24_PAIRS;
 constexpr size_t PREP24_SMEM = sizeof(double) * (1024 + PREP24_PAIRS * M24_PREP_DOUBLES);
 __global__ void __launch_bounds__(PREP24_THREADS) k_prep24(const Ric24Args a, double* __restrict__ prep) {
   extern __shared__ __align__(16) double psm[];
@@ -83,8 +84,8 @@ __global__ void __launch_bounds__(PREP24_THREADS) k_prep24(const Ric24Args a, do
   const int N = a.N;
   const long long total = a.batch * N;
   const long long wk0 = (long long)blockIdx.x * PREP24_PAIRS;
-  const long long wk = wk0 + (threadIdx.x >> 1);
-  const int v = threadIdx.x & 1;
+  const int role = threadIdx.x / (2 * PREP24_PAIRS), pr = (threadIdx.x >> 1) % PREP24_PAIRS, v = threadIdx.x & 1;
+  const long long wk = wk0 + pr;
   if (wk < total) {
     const long long w = wk / N;
     const int k = (int)(wk - w * N);
@@ -92,41 +93,49 @@ __global__ void __launch_bounds__(PREP24_THREADS) k_prep24(const Ric24Args a, do
     const size_t xsb = a.xbar_sb ? (size_t)a.xbar_sb : (size_t)(N + 1) * 24, xsk = a.xbar_sk ? (size_t)a.xbar_sk : 24;
     const double* xs = a.xbar + (size_t)b * xsb + (size_t)k * xsk;
     const double* us = a.ubar + ((size_t)b * N + k) * 8;
-    double* out = so + (threadIdx.x >> 1) * M24_PREP_DOUBLES;
-    double xk[12], uk[4];
+    double* out = so + pr * M24_PREP_DOUBLES;
+    if (role == 0) {
+      double xk[12], uk[4];   // (16-byte loads: a warp's 8-byte loads of 32 different records kept the LSU busy, not the FP64 pipe)
 #pragma unroll
-    for (int i = 0; i < 12; ++i) xk[i] = xs[12 * v + i];
+      for (int i = 0; i < 12; i += 2) { const double2 q = __ldg(reinterpret_cast<const double2*>(xs + 12 * v + i)); xk[i] = q.x; xk[i + 1] = q.y; }
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { uk[c] = us[4 * v + c]; out[M24_PREP_U + 4 * v + c] = uk[c]; }
-    {
+      for (int c = 0; c < 4; c += 2) { const double2 q = __ldg(reinterpret_cast<const double2*>(us + 4 * v + c)); uk[c] = q.x; uk[c + 1] = q.y; }
       double* o = out + M24_JE * v;
       int e = 0;
       model::quad_jac_discrete(
           xk, uk, a.dt,
           [&](int i, int jj, double val) { if (!model::quad_jac_is_const_A(i, jj) && !model::dual_coupled_diag(i, jj)) o[e++] = val; },
           [&](int i, int jj, double val) { if (!model::quad_jac_is_const_B(i, jj)) o[e++] = val; });
-    }
-    // h0 for the vehicle's own columns (W block diagonal: the chain runs over the own block, as in k_ric24)
-    const double* xg = a.xgoal + (size_t)b * 24;
-    double ex[24];
+    } else {
+      // h0 for the vehicle's own columns (W block diagonal: the chain runs over the own block, as in k_ric24)
+      const double* xg = a.xgoal + (size_t)b * 24;
+      double ex[24];
 #pragma unroll
-    for (int i = 0; i < 24; ++i) ex[i] = xs[i] - xg[i];
-#pragma unroll 1
-    for (int c = 12 * v; c < 12 * v + 12; ++c) {
-      double h = 0.0;
+      for (int i = 0; i < 24; i += 2) {
+        const double2 q = __ldg(reinterpret_cast<const double2*>(xs + i)), r = __ldg(reinterpret_cast<const double2*>(xg + i));
+        ex[i] = q.x - r.x; ex[i + 1] = q.y - r.y;
+      }
+#pragma unroll 2
+      for (int c = 12 * v; c < 12 * v + 12; ++c) {
+        double h = 0.0;
 #pragma unroll
-      for (int i = 0; i < 24; ++i) h = fmad(Ws[i * 32 + c], ex[i], h);
-      out[M24_PREP_H0 + 8 + c] = h;
-    }
-    double eu[8];
+        for (int i = 0; i < 24; ++i) h = fmad(Ws[i * 32 + c], ex[i], h);
+        out[M24_PREP_H0 + 8 + c] = h;
+      }
+      double eu[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) eu[i] = us[i] - model::kHover;
-#pragma unroll 1
-    for (int c = 4 * v; c < 4 * v + 4; ++c) {
-      double h = 0.0;
+      for (int i = 0; i < 8; i += 2) {
+        const double2 q = __ldg(reinterpret_cast<const double2*>(us + i));
+        eu[i] = q.x - model::kHover; eu[i + 1] = q.y - model::kHover;
+        if ((i >> 2) == v) { out[M24_PREP_U + i] = q.x; out[M24_PREP_U + i + 1] = q.y; }
+      }
+#pragma unroll 2
+      for (int c = 4 * v; c < 4 * v + 4; ++c) {
+        double h = 0.0;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) h = fmad(Ws[(24 + i) * 32 + 24 + c], eu[i], h);
-      out[M24_PREP_H0 + 7 - c] = h;
+        for (int i = 0; i < 8; ++i) h = fmad(Ws[(24 + i) * 32 + 24 + c], eu[i], h);
+        out[M24_PREP_H0 + 7 - c] = h;
+      }
     }
   }
   __syncthreads();
@@ -146,6 +155,13 @@ __host__ __device__ constexpr int m24_t3(int mi, int nj) { return mi * (7 - mi) 
 __host__ __device__ constexpr int m24_t4(int mi, int nj) { return mi * (9 - mi) / 2 + (nj - mi); }
 // element (r, c) of a stored tile
 __host__ __device__ constexpr int m24_el(int r, int c) { return r * 8 + (c ^ (4 * ((r >> 1) & 1))); }
+
+// Record built in the kernel (FUSED): the columns of row l are stored XOR 4*((l>>1)&1), so that the B-fragment loads
+// (rows 4ki+t, eight consecutive columns) of a half-warp fall into four different bank groups; with the plain row
+// strides of 24 (A) and 8 (B) doubles the rows t and t+2 collided (2 wavefronts per load instead of 1).  Records that
+// arrive from HBM by bulk copy keep the caller's layout.
+__host__ __device__ constexpr int m24_aoff(int l, int c, bool swz) { return l * 24 + (swz ? (c ^ (4 * ((l >> 1) & 1))) : c); }
+__host__ __device__ constexpr int m24_boff(int l, int u, bool swz) { return 576 + l * 8 + (swz ? (u ^ (4 * ((l >> 1) & 1))) : u); }
 
 // Built-in dual model (FUSED): is the 4 x 8 tile of F' = [B | A] (rows 4ki .., positions 8ni ..) structurally non-zero?
 // Four of the 24 tiles are not (vehicle 1's attitude rows in vehicle 0's columns and the like): a DMMA with an all-zero
@@ -210,6 +226,117 @@ __device__ __forceinline__ void m24_solve_neg(const double* Ls, const double (&r
   }
 }
 
+// ---- input box, warp-cooperative restatement of box_qp_gen<8> for one instance per warp: the same
+// operations on the same values in the same order (bit-identical iterates, clamped sets and exits), but the two parts
+// that every lane used to run redundantly are spread over the lanes — the matrix-vector product of the objective (row a on
+// lane a) and the masked factorisation (m24_ldl_pivot) — and nothing lives in local memory.
+// U: Quu row-major, lower triangle valid (shared); ws: 32 doubles x | r | xc | rc; Ls: column store of the masked factor.
+__device__ __forceinline__ double m24_qp_eval(const double* U, const double (&g)[8], const double* x, double* r, int lane) {
+  const int a = lane & 7;
+  double sacc = 0.0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) sacc = fmad(b <= a ? U[a * 8 + b] : U[b * 8 + a], x[b], sacc);
+  __syncwarp();   // (every lane is done with the previous contents of r)
+  r[a] = sacc;
+  __syncwarp();
+  double f = 0.0;
+#pragma unroll
+  for (int b = 0; b < 8; ++b) f = fmad(x[b], fmad(0.5, r[b], g[b]), f);
+  return f;
+}
+__device__ __forceinline__ bool m24_ldl_masked(const double* U, unsigned clmask, double (&r)[8], double* Ls, int lane) {
+  const int g = lane >> 2, t = lane & 3, a = 7 - g, b0 = 7 - 2 * t, b1 = 6 - 2 * t;
+  auto um = [&](int aa, int bb) {
+    const bool c = (((clmask >> aa) | (clmask >> bb)) & 1u) != 0;
+    return c ? (aa == bb ? 1.0 : 0.0) : U[aa * 8 + bb];
+  };
+  double u0 = b0 <= a ? um(a, b0) : 0.0, u1 = b1 <= a ? um(a, b1) : 0.0;
+  __syncwarp();   // (the previous factor's readers are done with Ls)
+  bool bad = false;
+  bad |= m24_ldl_pivot<0>(u0, u1, r, Ls, lane); bad |= m24_ldl_pivot<1>(u0, u1, r, Ls, lane);
+  bad |= m24_ldl_pivot<2>(u0, u1, r, Ls, lane); bad |= m24_ldl_pivot<3>(u0, u1, r, Ls, lane);
+  bad |= m24_ldl_pivot<4>(u0, u1, r, Ls, lane); bad |= m24_ldl_pivot<5>(u0, u1, r, Ls, lane);
+  bad |= m24_ldl_pivot<6>(u0, u1, r, Ls, lane); bad |= m24_ldl_pivot<7>(u0, u1, r, Ls, lane);
+  __syncwarp();
+  return bad;
+}
+__device__ __forceinline__ void m24_box_qp(const double* U, const double (&g)[8], const double (&lo)[8], const double (&hi)[8],
+                                           double (&xio)[8], unsigned& clmask, double* ws, double* Ls, int lane) {
+  double* x = ws;
+  double* r = ws + 8;
+  double* xc = ws + 16;
+  double* rc = ws + 24;
+  double gmax = 0.0;
+  __syncwarp();
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    if (lane == 0) x[a] = r12_clamp(xio[a], lo[a], hi[a]);
+    if (fabs(g[a]) > gmax) gmax = fabs(g[a]);
+  }
+  __syncwarp();
+  double f = m24_qp_eval(U, g, x, r, lane);
+  auto finish = [&]() {
+#pragma unroll
+    for (int a = 0; a < 8; ++a) xio[a] = x[a];
+  };
+  auto clamped_set = [&](double (&grad)[8], int& nfree, double& gn) {
+    unsigned m = 0;
+    nfree = 0; gn = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const double ga = r[a] + g[a], xa = x[a];
+      grad[a] = ga;
+      const bool c = (xa <= lo[a] && ga > 0.0) || (xa >= hi[a] && ga < 0.0);
+      if (c) m |= 1u << a;
+      else { ++nfree; if (fabs(ga) > gn) gn = fabs(ga); }
+    }
+    return m;
+  };
+  for (int it = 0; it < R12_QP_MAXIT; ++it) {
+    double grad[8], gn;
+    int nfree;
+    clmask = clamped_set(grad, nfree, gn);
+    if (nfree == 0 || gn < R12_QP_GTOL * (1.0 + gmax)) { finish(); return; }
+    double qr[8];
+    if (m24_ldl_masked(U, clmask, qr, Ls, lane)) { finish(); return; }
+    double rhs[8], dx[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) rhs[a] = ((clmask >> a) & 1u) ? 0.0 : grad[a];
+    m24_solve_neg(Ls, qr, rhs, dx);
+    double sdotg = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) sdotg = fmad(grad[a], dx[a], sdotg);
+    if (!(sdotg < 0.0)) { finish(); return; }
+    double step = 1.0;
+    bool ok = false;
+    for (int ls = 0; ls < R12_QP_MAXLS; ++ls) {
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) xc[a] = r12_clamp(fmad(step, dx[a], x[a]), lo[a], hi[a]);
+      }
+      __syncwarp();
+      const double fc = m24_qp_eval(U, g, xc, rc, lane);
+      if (fc - f <= R12_QP_ARMIJO * (step * sdotg)) {
+        __syncwarp();
+        if (lane < 8) { x[lane] = xc[lane]; r[lane] = rc[lane]; }
+        __syncwarp();
+        f = fc;
+        ok = true;
+        break;
+      }
+      step = step * 0.5;
+    }
+    if (!ok) { finish(); return; }
+  }
+  {   // iteration cap: the clamped set of the last accepted point
+    double grad[8], gn;
+    int nfree;
+    clmask = clamped_set(grad, nfree, gn);
+  }
+  finish();
+}
+
 template <int MODE, bool FUSED, int WARPS, int MIN_CTAS, bool BOX = false, bool PREP = false>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24Args a, const double* __restrict__ prep) {
   static_assert(MODE == RIC_LQR || MODE == RIC_AFFINE, "LQR sweep or SLQ backward pass");
@@ -258,8 +385,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   const int dir0 = g * 8 + 4 * (0 ^ s_g) + t, dir1 = g * 8 + 4 * (1 ^ s_g) + t;          // element (g, 4h+t)
   const int mir0 = t * 8 + (g ^ (4 * s_t)), mir1 = (4 + t) * 8 + (g ^ (4 * s_t));        // element (4h+t, g)
   const int dia0 = (g <= t) ? dir0 : mir0, dia1 = (g <= 4 + t) ? dir1 : mir1;            // diagonal tile: upper part only
-  const int fo_u = 576 + t * 8 + (7 - g);   // F'[4ki+t][g]      = B[4ki+t][7-g]:        + 32 ki
-  const int fo_x = t * 24 + g;              // F'[4ki+t][8ni+g]  = A[4ki+t][8(ni-1)+g]:  + 96 ki + 8 (ni-1)
+  constexpr bool SWZ = FUSED;               // m24_aoff / m24_boff: rows 4ki+t have (l>>1)&1 == s_t
+  const int fo_u = 576 + t * 8 + (SWZ ? ((7 - g) ^ (4 * s_t)) : (7 - g));   // F'[4ki+t][g]      = B[4ki+t][7-g]:        + 32 ki
+  const int fo_x = t * 24 + (SWZ ? (g ^ (4 * s_t)) : g);                    // F'[4ki+t][8ni+g]  = A[4ki+t][8(ni-1)+g]:  + 96 ki + 8 (ni-1)
   // Hux^T A fragments of the P' product: Hux[4ki+t][8mi+g] = H'(7-4ki-t, 8+8mi+g)
   const int ar0 = m24_el(0, 0) + (7 - t) * 8 + (g ^ (4 * (((7 - t) >> 1) & 1)));
   const int ar1 = (3 - t) * 8 + (g ^ (4 * (((3 - t) >> 1) & 1)));
@@ -270,7 +398,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   const int j = xlane ? p - 8 : 0;
   const double* Hcol = Hu + (1 + (j >> 3)) * 64;    // Hux[a][j] = Hcol[m24_el(7 - a, j & 7)]
   const int jc = j & 7;
-  const int fcol = xlane ? (p - 8) : 576 + (7 - p);  // F[l][own column] = Fs[fcol + l * fcs]
+  const int fcol = xlane ? (p - 8) : 576 + (7 - p);  // F[l][own column] = Fs[fcol + l * fcs] (rows with (l>>1)&1: fcol ^ 4)
+  const int fcolx = SWZ ? (fcol ^ 4) : fcol;
   const int fcs = xlane ? 24 : 8;
   const int wcol = m24_perm(p);                      // own row / column of W
 
@@ -306,10 +435,10 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   if (PREP) {
     const double zx[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, zu[4] = {0, 0, 0, 0};
     int e = 0;
-    auto note = [&](int off) {
+    auto note = [&](int i, int jj, bool isB) {
 #pragma unroll
       for (int v = 0; v < 2; ++v) {
-        const int id = M24_JE * v + e, o = off + (off < 576 ? (12 * v) * 24 + 12 * v : (12 * v) * 8 + 4 * v);
+        const int id = M24_JE * v + e, o = isB ? m24_boff(12 * v + i, 4 * v + jj, SWZ) : m24_aoff(12 * v + i, 12 * v + jj, SWZ);
         if (id == lane) so0 = o;
         if (id == lane + 32) so1 = o;
         if (id == lane + 64) so2 = o;
@@ -318,8 +447,8 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
     };
     model::quad_jac_discrete(
         zx, zu, a.dt,
-        [&](int i, int jj, double) { if (!model::quad_jac_is_const_A(i, jj) && !model::dual_coupled_diag(i, jj)) note(i * 24 + jj); },
-        [&](int i, int jj, double) { if (!model::quad_jac_is_const_B(i, jj)) note(576 + i * 8 + jj); });
+        [&](int i, int jj, double) { if (!model::quad_jac_is_const_A(i, jj) && !model::dual_coupled_diag(i, jj)) note(i, jj, false); },
+        [&](int i, int jj, double) { if (!model::quad_jac_is_const_B(i, jj)) note(i, jj, true); });
   }
   auto scatter_prep = [&](int k) {
     const double* pr = base + M24P_PR + M24_PREP_DOUBLES * (k & 1);
@@ -337,16 +466,14 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
     for (int i = 0; i < 12; ++i) xk[i] = Xs[12 * v + i];
 #pragma unroll
     for (int c = 0; c < 4; ++c) uk[c] = a.ubar ? Xs[24 + 4 * v + c] : model::kHover;
-    double* FA = Fs + (12 * v) * 24 + 12 * v;
-    double* FB = Fs + 576 + (12 * v) * 8 + 4 * v;
     int e = 0;
     model::quad_jac_discrete(
         xk, uk, a.dt,
         [&](int i, int jj, double val) {
-          if (!model::quad_jac_is_const_A(i, jj) && !model::dual_coupled_diag(i, jj) && ((e++) & 15) == t16) FA[i * 24 + jj] = val;
+          if (!model::quad_jac_is_const_A(i, jj) && !model::dual_coupled_diag(i, jj) && ((e++) & 15) == t16) Fs[m24_aoff(12 * v + i, 12 * v + jj, SWZ)] = val;
         },
         [&](int i, int jj, double val) {
-          if (!model::quad_jac_is_const_B(i, jj) && ((e++) & 15) == t16) FB[i * 8 + jj] = val;
+          if (!model::quad_jac_is_const_B(i, jj) && ((e++) & 15) == t16) Fs[m24_boff(12 * v + i, 4 * v + jj, SWZ)] = val;
         });
   };
 
@@ -376,9 +503,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
       __syncwarp();
       if (lane == 0) {   // state-independent entries: per-vehicle constants first, then the coupling (it overwrites (3+i,3+i))
         for (int v = 0; v < 2; ++v)
-          model::quad_jac_constants(a.dt, [&](int i, int jj, double val) { Fs[(12 * v + i) * 24 + 12 * v + jj] = val; },
-                                    [&](int i, int jj, double val) { Fs[576 + (12 * v + i) * 8 + 4 * v + jj] = val; });
-        model::dual_coupling_jac(a.dt, [&](int i, int jj, double val) { Fs[i * 24 + jj] = val; });
+          model::quad_jac_constants(a.dt, [&](int i, int jj, double val) { Fs[m24_aoff(12 * v + i, 12 * v + jj, SWZ)] = val; },
+                                    [&](int i, int jj, double val) { Fs[m24_boff(12 * v + i, 4 * v + jj, SWZ)] = val; });
+        model::dual_coupling_jac(a.dt, [&](int i, int jj, double val) { Fs[m24_aoff(i, jj, SWZ)] = val; });
       }
     } else {
       fetch_rec(N - 1);
@@ -451,13 +578,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
         if (PREP) {   // h0 = W e came with the record: one step of the F^T Vx chain per k-step of the G' products
           if (i & 1) return;
           const int l = i >> 1;
-          hacc = fmad(Fs[fcol + l * fcs], base[O_VS + l], hacc);
+          hacc = fmad(Fs[(((l >> 1) & 1) ? fcolx : fcol) + l * fcs], base[O_VS + l], hacc);
         } else if (i < 24) {   // W is block diagonal: the foreign block contributes exact zeros and is skipped (as k_ric24)
           if (xlane) hacc = fmad(__ldg(a.W + i * 32 + wcol), base[M24_ES + i], hacc);
           else if (i < 8) hacc = fmad(__ldg(a.W + (24 + i) * 32 + wcol), base[M24_ES + 24 + i], hacc);
         } else {
           const int l = i - 24;
-          hacc = fmad(Fs[fcol + l * fcs], base[O_VS + l], hacc);
+          hacc = fmad(Fs[(((l >> 1) & 1) ? fcolx : fcol) + l * fcs], base[O_VS + l], hacc);
         }
       };
 
@@ -580,16 +707,15 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
           }
           if (!inside) {
             double* ws = base + O_QP;
-            box_qp_gen<8>(Us, hur, lo, hi, kf, cl, ws);
-            __syncwarp();
-            ldl_mask<8>(Us, cl, ws);
-            __syncwarp();
-            LdlReg<8> chm;
-            failed |= chm.factor(ws);
+            unsigned clmask = 0;
+            m24_box_qp(Us, hur, lo, hi, kf, clmask, ws, Ls, lane);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) cl[c] = ((clmask >> c) & 1u) != 0;
+            failed |= m24_ldl_masked(Us, clmask, ldr, Ls, lane);
             double rhs[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) rhs[c] = cl[c] ? 0.0 : hux[c];
-            chm.solve_neg(rhs, kk);
+            m24_solve_neg(Ls, ldr, rhs, kk);
             if (lane == 0) {
 #pragma unroll
               for (int c = 0; c < 8; c += 2) sts128(base + O_KF + c, kf[c], kf[c + 1]);
