@@ -531,7 +531,7 @@ def _run_noc(args):
         if world == 1:
             for key, fn in (("config1", bb.config1), ("config4_share", bb.config4_share), ("config3", lambda: bb.slq(3)),
                             ("config5", lambda: bb.slq(5)), ("config3b_box", lambda: bb.slq(3, box=(0.0, 4.0))),
-                            ("config5b_box", lambda: bb.slq(5, box=(0.0, 4.0))), ("generic_kernel", bb.generic)):
+                            ("config5b_box", lambda: bb.slq(5, box=(0.0, 4.0))), ("n24_sweeps", bb.ric24), ("generic_kernel", bb.generic)):
                 try:
                     extra[key] = fn()
                 except Exception as ex:

@@ -458,13 +458,13 @@ int launch_ric24(noc_ctx* ctx, const Ric24Args& a, double* prep_buf = nullptr) {
 }
 
 // packs the weights for the n=24 kernels into scratch: W[1024] | Qf[576]
-int build_w24(noc_ctx* ctx, const double* dQRQf, const double** W, const double** Qf) {
+int build_w24(noc_ctx* ctx, const double* dQRQf, const double** W, const double** Qf, bool dare = false) {
   void* w = nullptr;
   int rc = scratch(ctx, SCR_W, sizeof(double) * (32 * 32 + 576), &w);
   if (rc) return rc;
   {
     LaunchScope ls(ctx, NOC_KERNEL_SETUP);
-    k_build_w<<<1, 256, 0, ctx->stream>>>(dQRQf, (double*)w, 24, 8, 24 * 24 + 8 * 8);
+    k_build_w<<<1, 256, 0, ctx->stream>>>(dQRQf, (double*)w, 24, 8, dare ? 0 : 24 * 24 + 8 * 8);
   }
   NOC_CUDA(ctx, cudaGetLastError());
   *W = (const double*)w;
@@ -1468,7 +1468,9 @@ int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, co
   if (p->max_iter < 1) return fail(ctx, NOC_ERR_BAD_ARG, "max_iter must be >= 1");
   if (batch == 0) return NOC_OK;
   const bool tuned = p->n == 12 && p->m == 4;
-  if (tuned && misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned");
+  // n=24, m=8, A_THEN_B records: the warp-per-instance tensor-core kernel (riccati24_mma.cuh) in its fixed-point mode
+  const bool tuned24 = p->n == 24 && p->m == 8 && p->layout == NOC_LAYOUT_A_THEN_B && !ctx->opt[NOC_OPT_NO_TENSOR_SWEEP];
+  if ((tuned || tuned24) && misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned");
   NOC_CUDA(ctx, cudaSetDevice(ctx->device));
   const size_t B = (size_t)batch, n = (size_t)p->n, m = (size_t)p->m;
   const void *dAB, *dQ;
@@ -1479,8 +1481,16 @@ int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, co
   if ((rc = stage_out(ctx, 1, K, sizeof(double) * B * m * n, &dK))) return rc;
   if ((rc = stage_out(ctx, 2, iters, sizeof(int32_t) * B, &dit))) return rc;
   if ((rc = stage_out(ctx, 3, status, sizeof(int32_t) * B, &dst))) return rc;
+  if (tuned24) {
+    Ric24Args a{};
+    if ((rc = build_w24(ctx, (const double*)dQ, &a.W, &a.Qf, true))) return rc;
+    a.AB = (const double*)dAB; a.K0 = (double*)dK; a.P0 = (double*)dP; a.iters = (int32_t*)dit; a.status = (int32_t*)dst;
+    a.tol = p->tol; a.max_iter = p->max_iter; a.batch = batch; a.N = 1;
+    if ((rc = launch_ric24_mma_shape<RIC_DARE, false, false, false>(ctx, a, nullptr))) return rc;
+    return flush_out(ctx, p->flags & NOC_FLAG_ASYNC);
+  }
   if (!tuned) {
-    // every other dimension (n=24, m=8 included): the thread-per-instance completeness kernel, same arithmetic
+    // every other dimension (and n=24, m=8 with ROWS_AB records): the thread-per-instance completeness kernel, same arithmetic
     RicGenArgs g{};
     g.AB = (const double*)dAB; g.QRQf = (const double*)dQ; g.K0 = (double*)dK; g.P0 = (double*)dP;
     g.iters = (int32_t*)dit; g.status = (int32_t*)dst; g.batch = batch; g.n = p->n; g.m = p->m; g.N = 1;

@@ -62,6 +62,10 @@ struct Ric24Args {
   int reg_schedule;      // noc_reg_schedule
   long long batch;
   int N;
+  // RIC_DARE (k_ric24_mma): AB is one LTI record per instance, Qf holds Q; P0 / K0 receive P and the stationary gain
+  int32_t* iters;        // [batch]
+  double tol;
+  int max_iter;
 };
 
 template <int MODE, bool FUSED, bool BOX = false>

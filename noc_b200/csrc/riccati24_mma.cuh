@@ -339,7 +339,9 @@ __device__ __forceinline__ void m24_box_qp(const double* U, const double (&g)[8]
 
 template <int MODE, bool FUSED, int WARPS, int MIN_CTAS, bool BOX = false, bool PREP = false>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24Args a, const double* __restrict__ prep) {
-  static_assert(MODE == RIC_LQR || MODE == RIC_AFFINE, "LQR sweep or SLQ backward pass");
+  static_assert(MODE == RIC_LQR || MODE == RIC_AFFINE || MODE == RIC_DARE, "LQR sweep, SLQ backward pass or DARE iteration");
+  static_assert(MODE != RIC_DARE || !FUSED, "RIC_DARE iterates on one LTI record from HBM");
+  constexpr bool DARE = MODE == RIC_DARE;
   static_assert(MODE != RIC_AFFINE || FUSED, "the SLQ backward pass linearises in the kernel");
   static_assert(!BOX || MODE == RIC_AFFINE, "input box: SLQ only");
   static_assert(!PREP || MODE == RIC_AFFINE, "k_prep24 serves the SLQ backward pass");
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   const int fcs = xlane ? 24 : 8;
   const int wcol = m24_perm(p);                      // own row / column of W
 
-  const double* rec = FUSED ? nullptr : a.AB + (size_t)b * N * R24_REC;
+  const double* rec = FUSED ? nullptr : a.AB + (size_t)b * (DARE ? 1 : N) * R24_REC;
   const unsigned fs_u32 = smem_u32(Fs);
   unsigned phase = 0;
   const size_t xsb = a.xbar_sb ? (size_t)a.xbar_sb : (size_t)(N + 1) * 24, xsk = a.xbar_sk ? (size_t)a.xbar_sk : 24;
@@ -482,6 +484,9 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   bool failed = false, reg_fail = false;
   double dV1 = 0.0, dV2 = 0.0;
   int kfail = -1;
+  int dare_iters = 0;
+  bool converged = false;
+  double kk_last[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 
   for (;;) {   // (re)start of a sweep (RIC_AFFINE: again with a larger mu after a failed factorisation)
     failed = false;
@@ -508,7 +513,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
         model::dual_coupling_jac(a.dt, [&](int i, int jj, double val) { Fs[m24_aoff(i, jj, SWZ)] = val; });
       }
     } else {
-      fetch_rec(N - 1);
+      fetch_rec(DARE ? 0 : N - 1);
     }
     if (AFF) {
       // xgoal -> shared; Vx <- Qf (xbar_N - xgoal), one row per lane (row chain, ascending)
@@ -535,22 +540,28 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
     }
     __syncwarp();
 
-    for (int it = 0; it < N; ++it) {
-      const int k = N - 1 - it;
-      const bool more = it + 1 < N;
-      if (!FUSED) {
+    // RIC_DARE: the fixed-point iteration P <- step(P) on the one record, whose fragments stay in registers; stops when
+    // max|P' - P| < tol max|P'| (oracle: noc_oracle_dare; same bits, hence the same iteration count)
+    const int steps = DARE ? a.max_iter : N;
+    double fb[6][4];
+    for (int it = 0; it < steps; ++it) {
+      const int k = DARE ? 0 : N - 1 - it;
+      const bool more = !DARE && it + 1 < N;
+      if (!FUSED && (!DARE || it == 0)) {
         mbar_wait(bar, phase);
         phase ^= 1u;
       }
       __syncwarp();
 
       // ---------------- fragments: all of F' (24) and P (18) into registers
-      double fb[6][4], pa[3][6];
+      double pa[3][6];
+      if (!DARE || it == 0) {
 #pragma unroll
-      for (int ki = 0; ki < 6; ++ki) {
-        fb[ki][0] = Fs[fo_u + 32 * ki];
+        for (int ki = 0; ki < 6; ++ki) {
+          fb[ki][0] = Fs[fo_u + 32 * ki];
 #pragma unroll
-        for (int ni = 1; ni < 4; ++ni) fb[ki][ni] = Fs[fo_x + 96 * ki + 8 * (ni - 1)];
+          for (int ni = 1; ni < 4; ++ni) fb[ki][ni] = Fs[fo_x + 96 * ki + 8 * (ni - 1)];
+        }
       }
 #pragma unroll
       for (int mi = 0; mi < 3; ++mi)
@@ -749,6 +760,12 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
         if (lane < 8) __stcs(a.kff + ((size_t)b * N + k) * 8 + lane, base[O_KF + lane]);
       }
       if (failed && kfail < 0) kfail = k;
+      if (DARE) {
+        dare_iters = it + 1;        // (the failing iteration counts: the oracle returns -it)
+        if (failed) break;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) kk_last[c] = kk[c];
+      }
       // K_k: to global memory (row a of K is 24 consecutive doubles over the lanes) and, for the P' product, to shared
       double* Kb = Gb;
       if (xlane) {
@@ -758,7 +775,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
 #pragma unroll
           for (int c = 0; c < 8; ++c) __stcs(Kp + c * 24 + j, kk[c]);
         }
-        if (k == 0 && a.K0) {
+        if (!DARE && k == 0 && a.K0) {
           double* kp = a.K0 + (size_t)b * 192;
 #pragma unroll
           for (int c = 0; c < 8; ++c) kp[c * 24 + j] = kk[c];
@@ -798,9 +815,29 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
           __syncwarp();
           scatter_prep(k - 1);
         }
+        if (DARE) {
+          // max|P' - P| and max|P'| over the upper triangle (P, P' symmetric): the lane's entries of the six tiles, then the warp
+          double dmax = 0.0, pmax = 0.0;
+#pragma unroll
+          for (int mi = 0; mi < 3; ++mi)
+#pragma unroll
+            for (int nj = mi; nj < 3; ++nj) {
+              const int T = m24_t3(mi, nj);
+              const double2 old = lds128(Pt + T * 64 + cs_off);
+              if (mi < nj || g <= 2 * t) { dmax = fmax(dmax, fabs(pacc[T][0] - old.x)); pmax = fmax(pmax, fabs(pacc[T][0])); }
+              if (mi < nj || g <= 2 * t + 1) { dmax = fmax(dmax, fabs(pacc[T][1] - old.y)); pmax = fmax(pmax, fabs(pacc[T][1])); }
+            }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+            pmax = fmax(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+          }
+          converged = dmax < a.tol * pmax;
+        }
 #pragma unroll
         for (int T = 0; T < 6; ++T) sts128(Pt + T * 64 + cs_off, pacc[T][0], pacc[T][1]);
       }
+      if (DARE && converged) break;
     }  // steps
     __syncwarp();
     if (!AFF) break;
@@ -828,8 +865,28 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
     }
     return;
   }
-  // ---------------- RIC_LQR outputs (the rules of k_ric24<RIC_LQR>)
   const double nanv = qnan();
+  auto pel = [&](int i, int c) {   // P[i][c] from the upper tiles
+    const int r = i <= c ? i : c, cc = i <= c ? c : i;
+    return Pt[m24_t3(r >> 3, cc >> 3) * 64 + m24_el(r & 7, cc & 7)];
+  };
+  if (DARE) {   // outputs of k_ric_generic's DARE mode: P, the stationary gain, the iteration count, OK / NOT_PD / MAX_ITER
+    if (a.K0 && xlane) {
+      double* kp = a.K0 + (size_t)b * 192;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) kp[c * 24 + j] = failed ? nanv : kk_last[c];
+    }
+    if (a.P0) {
+      double* po = a.P0 + (size_t)b * 576;
+      for (int e = lane; e < 576; e += 32) po[e] = failed ? nanv : pel(e / 24, e % 24);
+    }
+    if (lane == 0) {
+      if (a.iters) a.iters[b] = dare_iters;
+      if (a.status) a.status[b] = failed ? 1 : (converged ? 0 : 2);
+    }
+    return;
+  }
+  // ---------------- RIC_LQR outputs (the rules of k_ric24<RIC_LQR>)
   if (failed && xlane) {
     if (a.K)
       for (int k2 = 0; k2 <= kfail; ++k2) {
@@ -841,10 +898,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
       for (int c = 0; c < 8; ++c) kp[c * 24 + j] = nanv;
     }
   }
-  auto pel = [&](int i, int c) {   // P0[i][c] from the upper tiles
-    const int r = i <= c ? i : c, cc = i <= c ? c : i;
-    return Pt[m24_t3(r >> 3, cc >> 3) * 64 + m24_el(r & 7, cc & 7)];
-  };
   if (a.P0) {
     double* po = a.P0 + (size_t)b * 576;
     for (int e = lane; e < 576; e += 32) po[e] = failed ? nanv : pel(e / 24, e % 24);

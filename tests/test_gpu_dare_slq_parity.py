@@ -127,11 +127,14 @@ def test_dare_other_dimensions_bitexact(oracle, solver, n, m, layout):
     else:
         Q = np.diag(rng.uniform(0.5, 2.0, n)); R = np.diag(rng.uniform(0.1, 1.0, m))
     qr = np.concatenate([Q.ravel(), R.ravel()])
-    for max_iter in (10000, 7):
+    # (24, 8) with A_THEN_B records runs on k_ric24_mma<RIC_DARE> (tensor cores); with the option set, on k_ric_generic
+    for max_iter, no_tensor in ((10000, 0), (7, 0), (10000, 1)):
+        solver.set_option(capi.OPT_NO_TENSOR_SWEEP, no_tensor)
         prob = capi.problem(capi.MODEL_LTV_USER, 1, n=n, m=m, layout=layout, tol=1e-12, max_iter=max_iter)
         P = np.empty((batch, n, n)); K = np.empty((batch, m, n))
         iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
         solver.dare_solve_batch(prob, batch, AB, qr, P, K, iters, status)
+        solver.set_option(capi.OPT_NO_TENSOR_SWEEP, 0)
         for b in range(batch):
             Pr, Kr, it = oracle.dare(ABs[b][0], ABs[b][1], Q, R, tol=1e-12, max_iter=max_iter)
             assert it > 0 and iters[b] == it

@@ -9,10 +9,14 @@ pytestmark = pytest.mark.gpu
 M = pb.MODEL_DUAL24
 
 
-@pytest.fixture(scope="module")
-def solver():
+@pytest.fixture(scope="module", params=[0, 1], ids=["tensor-core-sweep", "dfma-sweep"])
+def solver(request):
+    """Every test of this module runs twice: on k_ric24_mma (one instance per warp, products on the FP64 tensor cores, step
+    records by k_prep24 in the SLQ backward pass — the default for A_THEN_B records and the built-in model) and, with
+    NOC_OPT_NO_TENSOR_SWEEP, on k_ric24 (DFMA chains, two instances per warp).  Both must reproduce the oracle bit for bit."""
     from noc_b200 import capi
     s = capi.Solver(0)
+    s.set_option(capi.OPT_NO_TENSOR_SWEEP, request.param)
     yield s
     s.close()
 
@@ -61,6 +65,34 @@ def test_lqr24_dense_weights_random_ltv_and_not_pd(oracle, solver):
         assert np.array_equal(K[ok], ref["K"][ok])
         okp = ~np.isnan(ref["P0"])
         assert np.array_equal(np.isnan(P0), ~okp) and np.array_equal(P0[okp], ref["P0"][okp])
+
+
+def test_from_x0_dual24_wild_states_match_dense_oracle(oracle, solver):
+    """Both n=24 kernels skip structural zeros of the dual model's Jacobian — k_ric24 entry by entry, k_ric24_mma the four
+    all-zero 4x8 tiles of [B | A] — while the oracle multiplies them.  Same bits as long as the intermediates are finite,
+    also far from hover (every quadrant of the sincos reduction, pitch near +-pi/2, body rates of tens of rad/s); states
+    that make the sweep fail must fail identically (status NOT_PD, NaN outputs)."""
+    from noc_b200 import capi
+    batch, N = 48, 40
+    Q, R, Qf = pb.default_weights(M)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    rng = np.random.default_rng(78)
+    x0 = pb.sample_x0(batch, seed=44, model=M)
+    for v in (0, 12):
+        x0[:, v + 6:v + 9] = rng.uniform(-3.1, 3.1, size=(batch, 3))
+        x0[:, v + 9:v + 12] = rng.uniform(-40.0, 40.0, size=(batch, 3))
+    x0[:16, 7] = np.pi / 2 + rng.uniform(-2e-3, 2e-3, size=16)
+    x0[16:20, 21:24] *= 1e3
+    ref = oracle.lqr_from_x0_batch(M, N, 0.02, x0, qr)
+    K = np.empty((batch, N, 8, 24)); K0 = np.empty((batch, 8, 24)); P0 = np.empty((batch, 24, 24)); cost = np.empty(batch)
+    status = np.full(batch, -1, dtype=np.int32)
+    solver.lqr_solve_from_x0(capi.problem(M, N), batch, x0, qr, K=K, K0=K0, P0=P0, cost=cost, status=status)
+    assert np.array_equal(status, ref["status"])
+    assert (status == 0).sum() >= batch // 2
+    assert np.array_equal(K0, ref["K0"], equal_nan=True) and np.array_equal(P0, ref["P0"], equal_nan=True)
+    assert np.array_equal(cost, ref["cost"], equal_nan=True)
+    refK = oracle.lqr_batch(24, 8, N, oracle.make_ab_batch(M, N, 0.02, x0), qr, x0dev=x0)["K"]
+    assert np.array_equal(K, refK, equal_nan=True)
 
 
 def test_from_x0_dual24_bitexact(oracle, solver):

@@ -212,7 +212,10 @@ class Bench:
         ms, prof = self.profiled(fn, 2)
         its = dit.cpu().numpy().astype(np.int64); st = dst.cpu().numpy()
         kms = prof["riccati"]["ms"]
-        kern = f"k_ric{n}<RIC_AFFINE,FUSED" + (",BOX>" if box else ">")
+        kern = (f"k_ric12<RIC_AFFINE,FUSED" + (",BOX>" if box else ">")) if n == 12 else \
+               ("k_ric24_mma<RIC_AFFINE,FUSED" + (",BOX" if box else "") + ",PREP> (FP64 tensor cores: 125 DMMAs per step; step records by k_prep24)")
+        skips = ("the fused sweep skips the Jacobian's zeros" if n == 12 else
+                 "the tensor sweep issues 125 of the 144 dense 8x8x4 tiles: four tiles of [B|A] are structurally zero")
         out = {"config": f"{cfg}b" if box else cfg,
                "what": f"SLQ/iLQR n={n} m={m} N={N}, hover start, waypoint goals, tol 1e-8, max 50 iterations, 11 step lengths" +
                        (f", input box [{box[0]}, {box[1]}] (control-limited DDP)" if box else ""),
@@ -221,7 +224,7 @@ class Bench:
                "status_counts": {int(k): int((st == k).sum()) for k in np.unique(st)}, "kernel_ms": prof,
                "roofline": fp64_roofline(float(its.sum()) * N * (FLOPS_STEP[n] + FLOPS_AFFINE[n]), kms, kern,
                                          f"SLQ iterations x N x ({FLOPS_STEP[n]} + {FLOPS_AFFINE[n]} affine) for the backward "
-                                         "pass (dense symmetric count; the fused sweep skips the Jacobian's zeros; "
+                                         f"pass (dense symmetric count; {skips}; "
                                          "regularisation-retry sweeps and the forward pass are not credited)"),
                "backward_share_of_solve": kms / ms}
         if self.cpu:
@@ -234,6 +237,43 @@ class Bench:
                                    "cores": o.max_threads(), "kind": "port", "sample": f"the first {smp} instances, {dt:.2f} s"}
             out["sample_parity_bit_exact"] = bool(np.array_equal(its[:smp], ref["iters"]) and
                                                   np.array_equal(dc.cpu().numpy()[:smp], ref["cost"]))
+        return out
+
+    # ------------------------------------------------------------------------------------------- n=24 sweeps, tensor vs DFMA
+    def ric24(self):
+        """The n=24 / m=8 sweeps alone (8192 x N=100): LTV sweep over A_k,B_k records in HBM and the fused from-x0 sweep, on
+        k_ric24_mma (FP64 tensor cores, default) and on k_ric24 (DFMA chains, NOC_OPT_NO_TENSOR_SWEEP) — same bits."""
+        torch, s, capi, pb = self.torch, self.s, self.capi, self.pb
+        nb, N = (1024 if self.quick else 8192), 100
+        qr = self.T(pb.pack_qrqf(*pb.default_weights(1)))
+        x0 = self.T(pb.sample_x0(nb, seed=9, model=1))
+        xbar = torch.empty(nb, N + 1, 24, **self.f64); AB = torch.empty(nb, N, 768, **self.f64)
+        K = torch.empty(nb, N, 8, 24, **self.f64); K0 = torch.empty(nb, 8, 24, **self.f64); cost = torch.empty(nb, **self.f64)
+        st = torch.empty(nb, **self.i32)
+        pm = capi.problem(1, N, flags=capi.FLAG_ASYNC)
+        pl = capi.problem(capi.MODEL_LTV_USER, N, n=24, m=8, flags=capi.FLAG_ASYNC)
+        s.rollout_open_loop(pm, nb, x0, None, xbar); s.linearize_batch(pm, nb, xbar, None, AB)
+        out = {"batch": nb, "N": N, "what": "n=24 m=8 sweeps: LTV over HBM records (all K_k written) and fused from-x0 (K0 + cost)"}
+        ref = None
+        for name, off in (("tensor", 0), ("dfma", 1)):
+            s.set_option(capi.OPT_NO_TENSOR_SWEEP, off)
+            f1 = lambda: s.lqr_solve_batch(pl, nb, AB, qr, x0dev=x0, K=K, K0=K0, cost=cost, status=st)
+            f2 = lambda: s.lqr_solve_from_x0(pm, nb, x0, qr, K0=K0, cost=cost, status=st)
+            f1(); _, p1 = self.profiled(f1, 3)
+            kk = K.clone()
+            f2(); _, p2 = self.profiled(f2, 3)
+            ms = p1["riccati"]["ms"]
+            blk = {"ltv_kernel_ms": ms, "ltv_solves_per_s": nb / ms * 1e3,
+                   "ltv_roofline": fp64_roofline(float(nb) * N * FLOPS_STEP[24], ms,
+                                                 "k_ric24_mma<RIC_LQR> (144 DMMAs per step)" if not off else "k_ric24<RIC_LQR>",
+                                                 "batch x N x 71,595 (dense symmetric count)"),
+                   "ltv_hbm_frac": nb * N * BYTES_STEP[24] / (ms * 1e-3) / 1e9 / hbm_peak_gbs(),
+                   "fused_kernel_ms": p2["riccati"]["ms"], "fused_solves_per_s": nb / p2["riccati"]["ms"] * 1e3,
+                   "status_not_ok": int((st != 0).sum().item())}
+            if ref is None: ref = kk
+            else: blk["gains_bit_identical_to_tensor"] = bool(torch.equal(ref, kk))
+            out[name] = blk
+        s.set_option(capi.OPT_NO_TENSOR_SWEEP, 0)
         return out
 
     # ------------------------------------------------------------------------------------------- thread-per-instance kernel
@@ -281,15 +321,24 @@ class Bench:
             its = dit.cpu().numpy().astype(np.int64)
             out["dare_n24"] = {"batch": nb2, "ms": ms2, "solves_per_s": nb2 / ms2 * 1e3, "iterations": int(its.max()),
                                "status_not_ok": int((dst2 != 0).sum().item()),
-                               "roofline": fp64_roofline(float(its.sum()) * FLOPS_STEP[24], ms2, "k_ric_generic",
+                               "roofline": fp64_roofline(float(its.sum()) * FLOPS_STEP[24], ms2,
+                                                         "k_ric24_mma<RIC_DARE> (FP64 tensor cores, record fragments resident in registers)",
                                                          "iterations x 71,595")}
+            # the thread-per-instance kernel it replaced (still the path for ROWS_AB records and other shapes)
+            s.set_option(capi.OPT_NO_TENSOR_SWEEP, 1)
+            nb3 = min(nb2, 512)
+            fn3 = lambda: s.dare_solve_batch(pd, nb3, o_rec, d_qr, dP, dK, dit, dst2)
+            fn3()
+            ms3 = ev_time(torch, self.stream, fn3, 1)
+            s.set_option(capi.OPT_NO_TENSOR_SWEEP, 0)
+            out["dare_n24"]["k_ric_generic"] = {"batch": nb3, "ms": ms3, "solves_per_s": nb3 / ms3 * 1e3}
         return out
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", nargs="*", default=[], help="blocks to run: 1 3 3b 4 5 5b generic")
+    ap.add_argument("--only", nargs="*", default=[], help="blocks to run: 1 3 3b 4 5 5b ric24 generic")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--box", type=float, nargs=2, default=[0.0, 4.0], metavar=("U_MIN", "U_MAX"))
     args = ap.parse_args()
@@ -302,7 +351,7 @@ def main():
     b = Bench(torch, s, stream, dev, quick=args.quick, cpu=not args.no_cpu)
     want = lambda k: not args.only or k in args.only
     blocks = (("1", b.config1), ("4", b.config4_share), ("3", lambda: b.slq(3)), ("5", lambda: b.slq(5)),
-              ("3b", lambda: b.slq(3, box=tuple(args.box))), ("5b", lambda: b.slq(5, box=tuple(args.box))), ("generic", b.generic))
+              ("3b", lambda: b.slq(3, box=tuple(args.box))), ("5b", lambda: b.slq(5, box=tuple(args.box))), ("ric24", b.ric24), ("generic", b.generic))
     for key, fn in blocks:
         if want(key):
             print(json.dumps(fn()), flush=True)
