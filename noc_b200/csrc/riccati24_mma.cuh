@@ -73,7 +73,7 @@ inline size_t ric24_mma_smem_bytes(int warps) {
 // Two threads per (work-list slot w, step k, vehicle v) — one evaluates the Jacobian, the other h0 and ubar (different warps:
 // no divergence) — and a CTA's 64 records are assembled in shared memory and written out as one contiguous 58 KB block
 // (every thread storing its own 456 bytes straight to global memory ran at 0.9 TB/s).
-constexpr int PREP24_PAIRS = 64, PREP24_THREADS = 4 * PREP24_PAIRS;
+constexpr int PREP24_PAIRS = 32, PREP24_THREADS = 4 * PREP24_PAIRS;   // 37 KB per CTA: six CTAs of four warps per SM
 constexpr size_t PREP24_SMEM = sizeof(double) * (1024 + PREP24_PAIRS * M24_PREP_DOUBLES);
 __global__ void __launch_bounds__(PREP24_THREADS) k_prep24(const Ric24Args a, double* __restrict__ prep) {
   extern __shared__ __align__(16) double psm[];
