@@ -308,6 +308,19 @@ int plan_waves(int64_t nw, int sms, int wide, size_t narrow_smem, double slope) 
   }
   return pick;
 }
+// The same plan from a measured table: narrow_cost[w-1] = T(w) / T(1) for w = 1 .. narrow_max one-warp CTAs per SM, wide_cost
+// for a full wave of the wide configuration.  (k_ric24_mma, tools/probe_ric24.py: 1, 1.01, 1.03, 1.06 up to one warp per
+// scheduler, 1.47 / 1.52 at six / eight, 2.2 for twelve in two six-warp CTAs — not a straight line; and the one-warp
+// build's 255 registers allow eight CTAs per SM, not the ten its shared memory would.)
+int plan_waves_table(int64_t nw, int sms, int wide, double wide_cost, const double* narrow_cost, int narrow_max) {
+  double best = (double)((nw + (int64_t)wide * sms - 1) / ((int64_t)wide * sms)) * wide_cost;
+  int pick = 0;
+  for (int w = 1; w <= narrow_max; ++w) {
+    const double c = (double)((nw + (int64_t)w * sms - 1) / ((int64_t)w * sms)) * narrow_cost[w - 1];
+    if (c < best - 1e-9) { best = c; pick = w; }
+  }
+  return pick;
+}
 // dynamic shared-memory request that lets exactly `w` CTAs share an SM
 size_t smem_for_residency(int w, size_t need) {
   size_t s = (kSmemPerSm / (size_t)w - kSmemPerCtaReserved) & ~(size_t)127;
@@ -415,10 +428,11 @@ template <int MODE, bool FUSED, bool BOX, bool PREP>
 int launch_ric24_mma_shape(noc_ctx* ctx, const Ric24Args& a, const double* prep) {
   const int wide = kRic24MmaWarps * kRic24MmaCtas;
   int w = 0;
+  static const double narrow_cost[8] = {1.0, 1.01, 1.03, 1.06, 1.27, 1.47, 1.50, 1.52};
   if (MODE == RIC_AFFINE && !ctx->opt[NOC_OPT_NO_WAVE_PLAN])
-    w = plan_waves(a.batch, ctx->sm_count, wide, ric24_mma_smem_bytes<MODE, FUSED, BOX, PREP>(1), 0.10);
-  else if (a.batch <= (long long)wide * ctx->sm_count)
-    w = (int)std::min<long long>(12, (a.batch + ctx->sm_count - 1) / ctx->sm_count);
+    w = plan_waves_table(a.batch, ctx->sm_count, wide, BOX ? 1.9 : 2.2, narrow_cost, 8);
+  else if (a.batch <= (long long)wide * ctx->sm_count)   // one launch of a small batch: spread it, at most 8 one-warp CTAs per SM
+    w = (a.batch <= 8LL * ctx->sm_count) ? (int)((a.batch + ctx->sm_count - 1) / ctx->sm_count) : 0;
   if (w > 0) return launch_ric24_mma_cfg<MODE, FUSED, 1, 1, BOX, PREP>(ctx, a, prep, w);
   return launch_ric24_mma_cfg<MODE, FUSED, kRic24MmaWarps, kRic24MmaCtas, BOX, PREP>(ctx, a, prep);
 }
