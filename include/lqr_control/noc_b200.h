@@ -124,9 +124,11 @@ typedef enum {
   NOC_OPT_TIME_PARALLEL_CHUNKS = 4,/* > 0: force that many horizon chunks (1 = plain warp-per-instance recursion); 0 = planned */
   NOC_OPT_NO_SMALL_BATCH_KERNEL = 5, /* 1: noc_lqr_solve_batch keeps the 8-instances-per-warp sweep also for batches of at most two
                                       instances per SM (default: those run one instance per warp, bit-identical, ~1.6x sooner) */
-  NOC_OPT_NO_TENSOR_SWEEP = 6,     /* 1: the n=12 LTV sweep over A_THEN_B records forms its products with DFMA chains (k_ric12) instead
-                                      of FP64 tensor-core tiles (k_ric12_mma); both are bit-identical to the oracle — DMMA evaluates
-                                      the same ascending fma chain (tools/ubench/dmma_order.cu) — this is the A/B switch */
+  NOC_OPT_NO_TENSOR_SWEEP = 6,     /* 1: the sweeps that form their products on FP64 tensor-core tiles fall back to DFMA chains — the
+                                      n=12 LTV sweep over A_THEN_B records (k_ric12_mma -> k_ric12) and every n=24 path over A_THEN_B
+                                      records or the built-in dual model: LTV sweep, from-x0, SLQ backward pass, DARE (k_ric24_mma ->
+                                      k_ric24 / k_ric_generic).  All are bit-identical to the oracle — DMMA evaluates the same
+                                      ascending fma chain (tools/ubench/dmma_order.cu) — this is the A/B switch */
   NOC_OPT_TENSOR_SWEEP_VARIANT = 7, /* measurements: 0 = default (records staged in shared memory by TMA, eight free-running warps per
                                       SM), 1 = + phase interlock of the two warps of a scheduler, 2 = no staging: fragments read
                                       straight from L2, twelve warps per SM.  All bit-identical; 0 is the fastest */
