@@ -584,12 +584,15 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
       __syncwarp();   // every lane has its fragments (the record and P may be overwritten); e is visible
       if (!FUSED && more) fetch_rec(k - 1);
       if (PREP && more) fetch_prep(k - 1);
+      double vx_odd = 0.0;        // Vx is read in 16-byte pairs (broadcast): twelve wavefronts per step instead of 24
       auto hstep = [&](int i) {   // i = 0..47
         if (!AFF) return;
         if (PREP) {   // h0 = W e came with the record: one step of the F^T Vx chain per k-step of the G' products
           if (i & 1) return;
           const int l = i >> 1;
-          hacc = fmad(Fs[(((l >> 1) & 1) ? fcolx : fcol) + l * fcs], base[O_VS + l], hacc);
+          double vx = vx_odd;
+          if ((l & 1) == 0) { const double2 v = lds128(base + O_VS + l); vx = v.x; vx_odd = v.y; }
+          hacc = fmad(Fs[(((l >> 1) & 1) ? fcolx : fcol) + l * fcs], vx, hacc);
         } else if (i < 24) {   // W is block diagonal: the foreign block contributes exact zeros and is skipped (as k_ric24)
           if (xlane) hacc = fmad(__ldg(a.W + i * 32 + wcol), base[M24_ES + i], hacc);
           else if (i < 8) hacc = fmad(__ldg(a.W + (24 + i) * 32 + wcol), base[M24_ES + 24 + i], hacc);
