@@ -436,12 +436,11 @@ int launch_ric24_mma_shape(noc_ctx* ctx, const Ric24Args& a, const double* prep)
   if (w > 0) return launch_ric24_mma_cfg<MODE, FUSED, 1, 1, BOX, PREP>(ctx, a, prep, w);
   return launch_ric24_mma_cfg<MODE, FUSED, kRic24MmaWarps, kRic24MmaCtas, BOX, PREP>(ctx, a, prep);
 }
-// `prep_buf` (RIC_AFFINE): room for batch x N x M24_PREP_DOUBLES doubles, or nullptr — then (and for RIC_LQR) the record
-// is evaluated inside the sweep
+// `prep_buf` (RIC_AFFINE): room for batch x N x M24_PREP_DOUBLES doubles — the step records k_prep24 leaves for the sweep
 template <int MODE, bool FUSED, bool BOX>
 int launch_ric24_mma(noc_ctx* ctx, const Ric24Args& a, double* prep_buf = nullptr) {
   if constexpr (MODE == RIC_AFFINE) {
-    if (prep_buf) {
+    {
       const long long pairs = a.batch * a.N;
       int rc = configure_kernel(ctx, (const void*)k_prep24, PREP24_SMEM, false);
       if (rc) return rc;
@@ -452,14 +451,15 @@ int launch_ric24_mma(noc_ctx* ctx, const Ric24Args& a, double* prep_buf = nullpt
       NOC_CUDA(ctx, cudaGetLastError());
       return launch_ric24_mma_shape<MODE, FUSED, BOX, true>(ctx, a, prep_buf);
     }
+  } else {
+    return launch_ric24_mma_shape<MODE, FUSED, BOX, false>(ctx, a, nullptr);
   }
-  return launch_ric24_mma_shape<MODE, FUSED, BOX, false>(ctx, a, nullptr);
 }
 
 template <int LAYOUT, int MODE, bool FUSED = false, bool BOX = false>
 int launch_ric24(noc_ctx* ctx, const Ric24Args& a, double* prep_buf = nullptr) {
   if constexpr (LAYOUT == 0 && (MODE == RIC_LQR || FUSED)) {
-    if (!ctx->opt[NOC_OPT_NO_TENSOR_SWEEP]) return launch_ric24_mma<MODE, FUSED, BOX>(ctx, a, prep_buf);
+    if (!ctx->opt[NOC_OPT_NO_TENSOR_SWEEP] && (MODE != RIC_AFFINE || prep_buf)) return launch_ric24_mma<MODE, FUSED, BOX>(ctx, a, prep_buf);
   }
   if (MODE == RIC_AFFINE && !ctx->opt[NOC_OPT_NO_WAVE_PLAN]) {   // (n=24: 0.62 -> 0.90 ms from one to seven warps per SM at N=100)
     const int w = plan_waves((a.batch + 1) / 2, ctx->sm_count, Ric24Cfg<MODE>::warps, ric24_smem_bytes<MODE, FUSED, BOX>(1), 0.075);
@@ -769,7 +769,8 @@ int from_x0_impl(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
   // 16 for n=24), about eight per call: a chunk that ends mid-wave pays for the full wave, and the smaller the last
   // chunk, the shorter the copy that nothing hides (B = 65536: 4 x 16384 = 8 waves took 2.53 ms of sweeps, 7 chunks
   // of one wave take 2.2 ms)
-  const size_t wave = (size_t)ctx->sm_count * (MODEL == 0 ? 64 : 16);
+  // instances resident per SM: n=12 eight per warp x eight warps; n=24 one per warp x twelve warps (k_ric24_mma) or two x eight
+  const size_t wave = (size_t)ctx->sm_count * (MODEL == 0 ? 64 : (ctx->opt[NOC_OPT_NO_TENSOR_SWEEP] ? 16 : 12));
   size_t inner_pref = overlap ? std::max<size_t>(1, (B / wave + 4) / 8) * wave : outer;
   if (overlap && ctx->opt[NOC_OPT_CHUNK_WAVES] > 0) inner_pref = (size_t)ctx->opt[NOC_OPT_CHUNK_WAVES] * wave;
   void* dxbar = nullptr;
@@ -1134,7 +1135,8 @@ int from_x0_device_chunks(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, c
                                                                                      (long long)n, (long long)(B * n));
   }
   NOC_CUDA(ctx, cudaGetLastError());
-  const size_t wave = (size_t)ctx->sm_count * (MODEL == 0 ? 64 : 16);
+  // instances resident per SM: n=12 eight per warp x eight warps; n=24 one per warp x twelve warps (k_ric24_mma) or two x eight
+  const size_t wave = (size_t)ctx->sm_count * (MODEL == 0 ? 64 : (ctx->opt[NOC_OPT_NO_TENSOR_SWEEP] ? 16 : 12));
   const size_t inner = chunked ? std::max<size_t>(1, (B / wave + 4) / 8) * wave : B;
   int chunk_no = 0;
   for (size_t off = 0; off < B; off += inner, ++chunk_no) {

@@ -36,14 +36,8 @@ constexpr int M24_PT = 768;      // P: upper tiles (0,0) (0,1) (0,2) (1,1) (1,2)
 constexpr int M24_HU = 1152;     // u-row tiles of H': (0,1) (0,2) (0,3) at +64, +128, +192 (slot 0 unused)
 constexpr int M24_GB = 1408;     // G' column tiles, two buffers of three tiles; scalar phase: K[8][24]; epilogue: row sums
 constexpr int M24_US = 1792;     // Huu[8][8] row-major, lower triangle valid (LdlReg / box_qp_gen read it)
-constexpr int M24_XS = 1856;     // FUSED / AFFINE: two buffers of xbar_k[24] | ubar_k[8]
-constexpr int M24_ES = 1920;     // AFFINE: e = [xbar_k - xgoal ; ubar_k - u_h]
-constexpr int M24_VS = 1952;     // AFFINE: Vx[24]
-constexpr int M24_HV = 1976;     // AFFINE: h_u[8]
-constexpr int M24_KF = 1984;     // AFFINE: feed-forward k[8]
-constexpr int M24_RR = 1992;     // AFFINE: Huu k [8]
-constexpr int M24_XG = 2000;     // AFFINE: xgoal[24]
-constexpr int M24_QP = 2024;     // BOX: workspace of the 8x8 box QP (112)
+constexpr int M24_XS = 1856;     // RIC_LQR + FUSED: two buffers of xbar_k[24] | ubar_k[8]   (RIC_AFFINE: the M24P_* slots below)
+constexpr int M24_XS_END = 1920;
 constexpr int M24_WT_DOUBLES = 640;   // per CTA: the ten upper tiles of W' in C-fragment order
 constexpr int M24_BAR_DOUBLES = 8;
 
@@ -57,13 +51,15 @@ constexpr int M24_BAR_DOUBLES = 8;
 constexpr int M24_JE = 37;                       // state-dependent entries per vehicle: 25 of A, 12 of B
 constexpr int M24_PREP_H0 = 2 * M24_JE, M24_PREP_U = M24_PREP_H0 + 32, M24_PREP_DOUBLES = M24_PREP_U + 8;   // 114
 constexpr int M24P_PR = 1856;                    // PREP: two buffers of M24_PREP_DOUBLES
-constexpr int M24P_VS = M24P_PR + 2 * M24_PREP_DOUBLES, M24P_HV = M24P_VS + 24, M24P_KF = M24P_HV + 8, M24P_RR = M24P_KF + 8,
-              M24P_QP = M24P_RR + 8;
+constexpr int M24P_VS = M24P_PR + 2 * M24_PREP_DOUBLES,   // Vx[24]
+              M24P_HV = M24P_VS + 24,                     // h_u[8]
+              M24P_KF = M24P_HV + 8,                      // feed-forward k[8]
+              M24P_RR = M24P_KF + 8,                      // Huu k [8]
+              M24P_QP = M24P_RR + 8;                      // BOX: workspace of the 8x8 box QP (32 doubles used)
 
 template <int MODE, bool FUSED, bool BOX, bool PREP = false>
 __host__ __device__ constexpr int m24_warp_doubles() {
-  return PREP ? (BOX ? M24P_QP + QP_WS_DOUBLES<8>() : M24P_QP)
-              : (MODE == RIC_AFFINE ? (BOX ? M24_QP + QP_WS_DOUBLES<8>() : M24_QP) : (FUSED ? M24_ES : M24_XS));
+  return PREP ? (BOX ? M24P_QP + 32 : M24P_QP) : (FUSED ? M24_XS_END : M24_XS);
 }
 template <int MODE, bool FUSED, bool BOX, bool PREP = false>
 inline size_t ric24_mma_smem_bytes(int warps) {
@@ -344,14 +340,13 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   constexpr bool DARE = MODE == RIC_DARE;
   static_assert(MODE != RIC_AFFINE || FUSED, "the SLQ backward pass linearises in the kernel");
   static_assert(!BOX || MODE == RIC_AFFINE, "input box: SLQ only");
-  static_assert(!PREP || MODE == RIC_AFFINE, "k_prep24 serves the SLQ backward pass");
+  static_assert(PREP == (MODE == RIC_AFFINE), "the SLQ backward pass, and only it, takes its step records from k_prep24");
   extern __shared__ __align__(128) double smem[];
   constexpr int WD = m24_warp_doubles<MODE, FUSED, BOX, PREP>();
   constexpr bool AFF = MODE == RIC_AFFINE;
   constexpr bool BUILD = FUSED && !PREP;   // the record is evaluated in the sweep
   constexpr bool TMA = !FUSED || PREP;     // something arrives by bulk copy on the warp's mbarrier
-  constexpr int O_VS = PREP ? M24P_VS : M24_VS, O_HV = PREP ? M24P_HV : M24_HV, O_KF = PREP ? M24P_KF : M24_KF,
-                O_RR = PREP ? M24P_RR : M24_RR, O_QP = PREP ? M24P_QP : M24_QP;
+  constexpr int O_VS = M24P_VS, O_HV = M24P_HV, O_KF = M24P_KF, O_RR = M24P_RR, O_QP = M24P_QP;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   double* Wt = smem + M24_BAR_DOUBLES;
@@ -403,7 +398,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   const int fcol = xlane ? (p - 8) : 576 + (7 - p);  // F[l][own column] = Fs[fcol + l * fcs] (rows with (l>>1)&1: fcol ^ 4)
   const int fcolx = SWZ ? (fcol ^ 4) : fcol;
   const int fcs = xlane ? 24 : 8;
-  const int wcol = m24_perm(p);                      // own row / column of W
 
   const double* rec = FUSED ? nullptr : a.AB + (size_t)b * (DARE ? 1 : N) * R24_REC;
   const unsigned fs_u32 = smem_u32(Fs);
@@ -517,8 +511,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
     }
     if (AFF) {
       // xgoal -> shared; Vx <- Qf (xbar_N - xgoal), one row per lane (row chain, ascending)
-      if (!PREP && lane < 24) base[M24_XG + lane] = a.xgoal[(size_t)b * 24 + lane];
-      __syncwarp();
       const double* xN = a.xbar + (size_t)b * xsb + (size_t)N * xsk;
       const double* xg = a.xgoal + (size_t)b * 24;
       if (lane < 24) {
@@ -576,10 +568,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
       // ---------------- RIC_AFFINE: h for the own column = W[col][:] e + F[:][col]^T Vx, a 48-long (u-lanes: 32-long) DFMA
       // chain fed to the scheduler in pieces between the DMMAs
       double hacc = 0.0;
-      if (AFF && !PREP) {
-        const double* Xs = base + M24_XS + 32 * (k & 1);
-        base[M24_ES + lane] = lane < 24 ? Xs[lane] - base[M24_XG + lane] : Xs[lane] - model::kHover;
-      }
       if (PREP) hacc = base[M24P_PR + M24_PREP_DOUBLES * (k & 1) + M24_PREP_H0 + lane];
       __syncwarp();   // every lane has its fragments (the record and P may be overwritten); e is visible
       if (!FUSED && more) fetch_rec(k - 1);
@@ -593,12 +581,6 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
           double vx = vx_odd;
           if ((l & 1) == 0) { const double2 v = lds128(base + O_VS + l); vx = v.x; vx_odd = v.y; }
           hacc = fmad(Fs[(((l >> 1) & 1) ? fcolx : fcol) + l * fcs], vx, hacc);
-        } else if (i < 24) {   // W is block diagonal: the foreign block contributes exact zeros and is skipped (as k_ric24)
-          if (xlane) hacc = fmad(__ldg(a.W + i * 32 + wcol), base[M24_ES + i], hacc);
-          else if (i < 8) hacc = fmad(__ldg(a.W + (24 + i) * 32 + wcol), base[M24_ES + 24 + i], hacc);
-        } else {
-          const int l = i - 24;
-          hacc = fmad(Fs[(((l >> 1) & 1) ? fcolx : fcol) + l * fcs], base[O_VS + l], hacc);
         }
       };
 
@@ -711,7 +693,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
           // The whole warp is one instance: no divergence between instances, every shared-memory access a broadcast.
           double lo[8], hi[8];
           bool inside = true;
-          const double* ub = PREP ? base + M24P_PR + M24_PREP_DOUBLES * (k & 1) + M24_PREP_U : base + M24_XS + 32 * (k & 1) + 24;
+          const double* ub = base + M24P_PR + M24_PREP_DOUBLES * (k & 1) + M24_PREP_U;
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const double uc = ub[c];
