@@ -25,6 +25,7 @@
 #include "riccati_generic.cuh"
 #include "riccati_scan.cuh"
 #include "riccati12_mma.cuh"
+#include "riccati12_wpi.cuh"
 #include "slq_kernels.cuh"
 
 namespace {
@@ -378,6 +379,29 @@ int launch_ric12_mma(noc_ctx* ctx, const Ric12Args& a) {
     case 2: return launch_ric12_mma_cfg<4, 3, true>(ctx, a);    // fragments straight from L2, 12 warps per SM (3.05 ms)
     default: return launch_ric12_mma_cfg<4, 2, false>(ctx, a);  // records staged by TMA, 2 CTAs x 4 warps per SM (2.87 ms)
   }
+}
+
+// Short SLQ work lists at n=12 (riccati12_wpi.cuh): one instance per warp on the tensor cores, step records by k_prep12;
+// one-warp CTAs spread breadth-first over the SMs.  `prep_buf`: room for batch x N x W12_PREP_DOUBLES doubles.
+constexpr int kRic12WpiMaxPerSm = 12;   // (tools/probe_slq12.py: 0.19 ms at one warp per SM, 0.36 + 0.05 at twelve, against 0.43-0.45 ms on k_ric12; two rounds beyond)
+int launch_ric12_wpi(noc_ctx* ctx, const Ric12Args& a, double* prep_buf) {
+  const long long recs = a.batch * a.N;
+  int rc = configure_kernel(ctx, (const void*)k_prep12, PREP12_SMEM, false);
+  if (rc) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_LINEARIZE);
+    k_prep12<<<(unsigned)((recs + PREP12_RECS - 1) / PREP12_RECS), PREP12_THREADS, PREP12_SMEM, ctx->stream>>>(a, prep_buf);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  auto kern = k_ric12_wpi<1, 8>;
+  const size_t smem = ric12_wpi_smem_bytes(1);
+  if ((rc = configure_kernel(ctx, (const void*)kern, smem, true))) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+    kern<<<(unsigned)a.batch, 32, smem, ctx->stream>>>(a, prep_buf);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  return NOC_OK;
 }
 
 template <int MODE>
@@ -893,6 +917,9 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
   void *dlc, *dflags, *dprep = nullptr;
   // n=24 on the tensor cores: the step records of k_prep24 (Jacobian entries, W e, ubar), one per (work-list slot, k)
   if (MODEL == 1 && !ctx->opt[NOC_OPT_NO_TENSOR_SWEEP] && (rc = scratch(ctx, SCR_PREP, sizeof(double) * B * N * M24_PREP_DOUBLES, &dprep))) return rc;
+  // n=12: short work lists (at most twelve instances per SM) go to the warp-per-instance tensor kernel, which takes step records too
+  const size_t prep12_cap = (MODEL == 0 && !ctx->opt[NOC_OPT_NO_TENSOR_SWEEP]) ? std::min<size_t>(B, (size_t)kRic12WpiMaxPerSm * ctx->sm_count) : 0;
+  if (prep12_cap && (rc = scratch(ctx, SCR_PREP, sizeof(double) * prep12_cap * N * W12_PREP_DOUBLES, &dprep))) return rc;
   if ((rc = scratch(ctx, SCR_LC, sizeof(double) * B * (N + 1), &dlc))) return rc;
   if ((rc = scratch(ctx, SCR_FLAGS, sizeof(int32_t) * B, &dflags))) return rc;
   NOC_CUDA(ctx, cudaMemsetAsync(dflags, 0, sizeof(int32_t) * B, ctx->stream));
@@ -944,7 +971,8 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
     ra.dt = p->dt;
     if constexpr (MODEL == 0) {
       ra.u_min = p->u_min; ra.u_max = p->u_max;
-      rc = boxed ? launch_ric12<0, RIC_AFFINE, true, true>(ctx, ra) : launch_ric12<0, RIC_AFFINE, true>(ctx, ra);
+      if (!boxed && dprep && (size_t)count <= prep12_cap) rc = launch_ric12_wpi(ctx, ra, (double*)dprep);
+      else rc = boxed ? launch_ric12<0, RIC_AFFINE, true, true>(ctx, ra) : launch_ric12<0, RIC_AFFINE, true>(ctx, ra);
     }
     else {
       ra.u_min = p->u_min; ra.u_max = p->u_max;

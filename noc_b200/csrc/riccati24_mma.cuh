@@ -177,47 +177,49 @@ __host__ __device__ constexpr bool m24_tile_nz(int ki, int ni) {
 // term by term and in the same ascending order (§2.3 step 3), so the result is bit-identical to LdlReg<8>::factor, at 12
 // FP64 instructions per pivot instead of 14-30 (every lane used to run the whole factorisation redundantly: 22 % of the
 // sweep's instructions).  Column l of L goes to shared memory (Ls[i*8+l]) for the gain solves; r[] = 1/D stays in registers.
-template <int L>
-__device__ __forceinline__ bool m24_ldl_pivot(double& u0, double& u1, double (&r)[8], double* Ls, int lane) {
-  constexpr int tl = (7 - L) >> 1;             // the lanes t == tl hold column L ...
-  constexpr bool slot1 = (L & 1) == 0;         // ... in u1 (L even) or u0 (L odd)
-  const int g = lane >> 2, t = lane & 3, a = 7 - g;
+template <int L, int M = 8>
+__device__ __forceinline__ bool m24_ldl_pivot(double& u0, double& u1, double (&r)[M], double* Ls, int lane) {
+  // general M (k_ric12_wpi: M = 4): a = M-1-g, b0 = M-1-2t, b1 = M-2-2t; lanes outside the M x M block hold dead values
+  constexpr int tl = (M - 1 - L) >> 1;                 // the lanes t == tl hold column L ...
+  constexpr bool slot1 = ((M - 1 - L) & 1) == 1;       // ... in u1 or in u0
+  const int g = lane >> 2, t = lane & 3, a = M - 1 - g;
   const double mine = slot1 ? u1 : u0;
-  const double d = __shfl_sync(0xffffffffu, mine, (7 - L) * 4 + tl);
+  const double d = __shfl_sync(0xffffffffu, mine, (M - 1 - L) * 4 + tl);
   const bool bad = !(d > R12_PIVOT_MIN) || !(d < R12_PIVOT_MAX);
   r[L] = rcp_rn_normal(d);
-  if (L < 7) {
+  if (L < M - 1) {
     const double lv = mine * r[L];             // L[a][L] on the lanes t == tl
-    if (t == tl && a > L) Ls[a * 8 + L] = lv;
+    if (t == tl && a > L) Ls[a * M + L] = lv;
     const double la = __shfl_sync(0xffffffffu, lv, (lane & ~3) | tl);
-    const double lb0 = __shfl_sync(0xffffffffu, lv, (2 * t) * 4 + tl);        // row b0 = 7 - 2t lives on g' = 2t
-    const double lb1 = __shfl_sync(0xffffffffu, lv, (2 * t + 1) * 4 + tl);    // row b1 = 6 - 2t on g' = 2t + 1
+    const double lb0 = __shfl_sync(0xffffffffu, lv, (2 * t) * 4 + tl);        // row b0 = M-1-2t lives on g' = 2t
+    const double lb1 = __shfl_sync(0xffffffffu, lv, (2 * t + 1) * 4 + tl);    // row b1 = M-2-2t on g' = 2t + 1
     const double n0 = fmad(-la, lb0 * d, u0), n1 = fmad(-la, lb1 * d, u1);
-    if (7 - 2 * t > L) u0 = n0;
-    if (6 - 2 * t > L) u1 = n1;
+    if (M - 1 - 2 * t > L) u0 = n0;
+    if (M - 2 - 2 * t > L) u1 = n1;
   }
   return bad;
 }
 // the spec's forward / backward substitution (LdlReg<8>::solve_neg) with L read from shared memory (broadcast loads)
-__device__ __forceinline__ void m24_solve_neg(const double* Ls, const double (&r)[8], const double (&rhs)[8], double (&out)[8]) {
-  double Lr[8][8];
+template <int M = 8>
+__device__ __forceinline__ void m24_solve_neg(const double* Ls, const double (&r)[M], const double (&rhs)[M], double (&out)[M]) {
+  double Lr[M][M];
 #pragma unroll
-  for (int i = 1; i < 8; ++i)
+  for (int i = 1; i < M; ++i)
 #pragma unroll
-    for (int l = 0; l < i; ++l) Lr[i][l] = Ls[i * 8 + l];
-  double y[8];
+    for (int l = 0; l < i; ++l) Lr[i][l] = Ls[i * M + l];
+  double y[M];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < M; ++i) {
     double sacc = rhs[i];
 #pragma unroll
     for (int l = 0; l < i; ++l) sacc = fmad(-Lr[i][l], y[l], sacc);
     y[i] = sacc;
   }
 #pragma unroll
-  for (int i = 7; i >= 0; --i) {
+  for (int i = M - 1; i >= 0; --i) {
     double sacc = (-y[i]) * r[i];
 #pragma unroll
-    for (int l = i + 1; l < 8; ++l) sacc = fmad(-Lr[l][i], out[l], sacc);
+    for (int l = i + 1; l < M; ++l) sacc = fmad(-Lr[l][i], out[l], sacc);
     out[i] = sacc;
   }
 }

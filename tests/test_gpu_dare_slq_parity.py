@@ -9,15 +9,19 @@ from noc_b200 import problems as pb
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[(0, 0), (1, 1)], ids=["default-schedule", "fixed-shapes+deferred-backtracking"])
+@pytest.fixture(scope="module", params=[(0, 0, 0), (1, 1, 0), (0, 0, 1)],
+                ids=["default-schedule", "fixed-shapes+deferred-backtracking", "dfma-sweeps"])
 def solver(request):
-    """Every test of this module runs under both SLQ schedules: the default (balanced wave plan, the line search settled
+    """Every test of this module runs under both SLQ schedules — the default (balanced wave plan, the line search settled
     before the next sweep) and round 1's fixed launch shapes with the line search's backtracking round deferred beside
-    the next sweep (NOC_OPT_NO_WAVE_PLAN, NOC_OPT_DEFERRED_BACKTRACK).  A schedule never changes a result."""
+    the next sweep (NOC_OPT_NO_WAVE_PLAN, NOC_OPT_DEFERRED_BACKTRACK) — and on both families of backward-pass kernels: the
+    tensor-core ones (default: short n=12 work lists on k_ric12_wpi, n=24 on k_ric24_mma, both fed by step-record kernels)
+    and, with NOC_OPT_NO_TENSOR_SWEEP, the DFMA kernels k_ric12 / k_ric24.  Neither ever changes a result."""
     from noc_b200 import capi
     s = capi.Solver(0)
     s.set_option(capi.OPT_NO_WAVE_PLAN, request.param[0])
     s.set_option(capi.OPT_DEFERRED_BACKTRACK, request.param[1])
+    s.set_option(capi.OPT_NO_TENSOR_SWEEP, request.param[2])
     yield s
     s.close()
 
