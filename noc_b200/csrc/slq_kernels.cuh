@@ -458,9 +458,18 @@ __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
   double Jc = 0.0;
   bool pass = false;
   if (lane < a.cand_J) {
+    // ordered sum (the oracle's order); the loads of a lane go to its own cache lines, so they are issued 16 at a time —
+    // one at a time the N+1 dependent load latencies, not the additions, were the cost of this kernel
     const double* lc = a.lcc + ((size_t)item * a.cand_J + lane) * (N + 1);
-#pragma unroll 8
-    for (int k = 0; k <= N; ++k) Jc = Jc + lc[k];
+    int k = 0;
+    for (; k + 16 <= N + 1; k += 16) {
+      double v[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) v[q] = __ldcs(lc + k + q);
+#pragma unroll
+      for (int q = 0; q < 16; ++q) Jc = Jc + v[q];
+    }
+    for (; k <= N; ++k) Jc = Jc + lc[k];
     double alpha = 1.0;
     for (int j = 0; j < a.cand_first + lane; ++j) alpha = alpha * 0.5;
     const double expected = -(alpha * dV1 + (alpha * alpha) * dV2);
@@ -478,8 +487,27 @@ __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
   const double2* su = reinterpret_cast<const double2*>(c >= 0 ? a.uc + slot * N * m : a.un + (size_t)b * N * m);
   double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
   double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
-  for (int i = lane; i < (N + 1) * n / 2; i += 32) dxp[i] = sx[i];
-  for (int i = lane; i < N * m / 2; i += 32) dup[i] = su[i];
+  {   // the winning trajectory over the nominal: eight 16-byte loads in flight per lane
+    const int nx = (N + 1) * n / 2, nu = N * m / 2;
+    int i = lane;
+    for (; i + 7 * 32 < nx; i += 8 * 32) {
+      double2 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = sx[i + 32 * q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dxp[i + 32 * q] = v[q];
+    }
+    for (; i < nx; i += 32) dxp[i] = sx[i];
+    i = lane;
+    for (; i + 7 * 32 < nu; i += 8 * 32) {
+      double2 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = su[i + 32 * q];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dup[i + 32 * q] = v[q];
+    }
+    for (; i < nu; i += 32) dup[i] = su[i];
+  }
   if (lane != 0) return;
   if (c < 0) {   // the nominal has been put back
     slq_line_search_failed(a, b);
