@@ -212,7 +212,8 @@ class Bench:
         ms, prof = self.profiled(fn, 2)
         its = dit.cpu().numpy().astype(np.int64); st = dst.cpu().numpy()
         kms = prof["riccati"]["ms"]
-        kern = (f"k_ric12<RIC_AFFINE,FUSED" + (",BOX>" if box else ">")) if n == 12 else \
+        kern = (f"k_ric12<RIC_AFFINE,FUSED" + (",BOX>" if box else "> (work lists of at most 12 instances per SM: k_prep12 + k_ric12_wpi, "
+                                                     "one instance per warp on the FP64 tensor cores)")) if n == 12 else \
                ("k_ric24_mma<RIC_AFFINE,FUSED" + (",BOX" if box else "") + ",PREP> (FP64 tensor cores: 125 DMMAs per step; step records by k_prep24)")
         skips = ("the fused sweep skips the Jacobian's zeros" if n == 12 else
                  "the tensor sweep issues 125 of the 144 dense 8x8x4 tiles: four tiles of [B|A] are structurally zero")
