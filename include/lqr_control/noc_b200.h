@@ -137,7 +137,12 @@ typedef enum {
   NOC_OPT_DEFERRED_BACKTRACK = 9,  /* 1: the SLQ line search settles the rejected instances beside the next backward sweep, on the
                                       auxiliary stream, and they rejoin the work list one sweep later (same results; measured slower
                                       on the BASELINE configs — the extra sweeps of the stragglers cost more) */
-  NOC_OPT_COUNT = 10
+  NOC_OPT_NO_SPECULATIVE_BACKTRACK = 10, /* 1: the SLQ line search tries alpha = 1 first for EVERY instance and backtracks the rejected
+                                      ones in a second launch set.  Default: the (few) instances that needed a shorter step in their
+                                      previous iteration run all their step lengths as candidates beside the others' first trial,
+                                      on the auxiliary stream — same accepted step, one latency-bound launch set less per iteration
+                                       */
+  NOC_OPT_COUNT = 11
 } noc_option;
 int noc_set_option(noc_ctx* ctx, int option, int64_t value);
 /* Device memory for callers that do not link the CUDA runtime themselves (the C++ facade, cgo / ctypes bindings):

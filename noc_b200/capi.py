@@ -26,7 +26,7 @@ LAYOUT_A_THEN_B, LAYOUT_ROWS_AB = 0, 1
 FLAG_NONE, FLAG_ASYNC, FLAG_TIME_PARALLEL = 0, 1, 2
 OPT_SCRATCH_LIMIT_BYTES, OPT_CHUNK_WAVES, OPT_SINGLE_STREAM, OPT_TIME_PARALLEL_DFMA, OPT_TIME_PARALLEL_CHUNKS, \
     OPT_NO_SMALL_BATCH_KERNEL, OPT_NO_TENSOR_SWEEP, OPT_TENSOR_SWEEP_VARIANT, OPT_NO_WAVE_PLAN, \
-    OPT_DEFERRED_BACKTRACK = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
+    OPT_DEFERRED_BACKTRACK, OPT_NO_SPECULATIVE_BACKTRACK = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10
 REG_X10, REG_ADAPTIVE = 0, 1
 
 EXPORTS = [

@@ -224,7 +224,7 @@ int scratch_budget(noc_ctx* ctx, int entry, int n, int N, int extra, int64_t bat
 enum { SCR_W = 0, SCR_XBAR, SCR_AB, SCR_ARGMIN, SCR_K, SCR_KFF, SCR_DV, SCR_MU, SCR_J, SCR_BSTATUS, SCR_STATUS,
        SCR_ITERS, SCR_IDX0, SCR_IDX1, SCR_COUNT, SCR_X, SCR_U, SCR_XN, SCR_UN, SCR_RETRY0, SCR_RETRY1, SCR_LC, SCR_FLAGS, SCR_XC, SCR_UC, SCR_LCC,
        SCR_PIPE_AB0, SCR_PIPE_AB1, SCR_PIPE_X0, SCR_PIPE_X1, SCR_PIPE_QR0, SCR_PIPE_QR1, SCR_PIPE_OUT0,
-       SCR_PIPE_OUT_LAST = SCR_PIPE_OUT0 + 9, SCR_ARGMIN_PART, SCR_COMM_PAIRS, SCR_COMM_COST, SCR_DELTA, SCR_PREP, SCR_END };
+       SCR_PIPE_OUT_LAST = SCR_PIPE_OUT0 + 9, SCR_ARGMIN_PART, SCR_COMM_PAIRS, SCR_COMM_COST, SCR_DELTA, SCR_PREP, SCR_SPEC_LIST, SCR_SPEC_X, SCR_SPEC_U, SCR_SPEC_LC, SCR_END };
 
 // W = symmetric blockdiag(Q, R) as a dense (n+m)x(n+m) matrix, followed by the symmetric terminal weight (n*n).
 // Q / Qf are taken from their upper triangles and R from its lower triangle (the entries the spec reads,
@@ -953,6 +953,23 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
   // fills a wide wave (59 sweeps).  The hidden round is worth less than the sweeps it adds, so the default stays
   // synchronous; results are identical either way (tests/test_gpu_dare_slq_parity.py runs both).
   const bool defer_ok = ctx->opt[NOC_OPT_DEFERRED_BACKTRACK] != 0;
+  // Speculative line search (default; NOC_OPT_NO_SPECULATIVE_BACKTRACK switches it off).  The instances that needed a shorter
+  // step in their previous iteration — in the tail of a solve the same two or three stragglers, iteration after iteration —
+  // used to cost every iteration a second, latency-bound launch set (candidate rollouts + costs + pick: 0.15-0.2 ms while the
+  // GPU idles).  They are flagged instead (SLQ_FLAG_SPEC_NEXT), and in their next forward pass ALL their step lengths,
+  // alpha = 1 included, run as candidates on the auxiliary stream beside everybody else's trial 0; the first passing
+  // candidate in order is exactly the oracle's sequential search.  Only short lists are speculated (kSpecMax).
+  constexpr int kSpecMax = 64;
+  const bool spec_ok = !defer_ok && !ctx->opt[NOC_OPT_NO_SPECULATIVE_BACKTRACK] && p->n_alpha <= 32;
+  int spec_count = 0;
+  void *dslist = nullptr, *dsx = nullptr, *dsu = nullptr, *dslc = nullptr;
+  if (spec_ok) {
+    const size_t cands = (size_t)kSpecMax * p->n_alpha;
+    if ((rc = scratch(ctx, SCR_SPEC_LIST, sizeof(int32_t) * B, &dslist))) return rc;
+    if ((rc = scratch(ctx, SCR_SPEC_X, sizeof(double) * cands * (N + 1) * n, &dsx))) return rc;
+    if ((rc = scratch(ctx, SCR_SPEC_U, sizeof(double) * cands * N * m, &dsu))) return rc;
+    if ((rc = scratch(ctx, SCR_SPEC_LC, sizeof(double) * cands * (N + 1), &dslc))) return rc;
+  }
   int pending_bit = 0;
   cudaEvent_t pending_ev = nullptr;
   cudaStream_t const main_stream = ctx->stream;
@@ -993,6 +1010,40 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
     fa.armijo = p->armijo; fa.u_min = p->u_min; fa.u_max = p->u_max;
     fa.mu = (double*)dmu; fa.delta = (double*)ddelta; fa.reg_schedule = p->reg_schedule;
     fa.cont_bit = 1;
+    fa.spec_mark = spec_ok ? 1 : 0;
+    const bool spec_now = spec_ok && spec_count > 0 && spec_count <= kSpecMax;
+    if (spec_now) {
+      // fork: mark the speculated instances (the ordinary trial 0 skips them), then their candidate round on the auxiliary stream
+      {
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_slq_mark_spec<<<(spec_count + 127) / 128, 128, 0, ctx->stream>>>((const int32_t*)dslist, spec_count, (int32_t*)dflags, 1);
+      }
+      NOC_CUDA(ctx, cudaEventRecord(ctx->fork_ev, main_stream));
+      NOC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
+      ctx->stream = ctx->aux_stream;   // (the launches below and their profiling events go to the auxiliary stream)
+      SlqFwdArgs fs = fa;
+      const size_t rc_ = (size_t)spec_count * p->n_alpha;
+      fs.spec = 1; fs.idx = (const int32_t*)dslist; fs.trial = 0; fs.cand_J = p->n_alpha; fs.cand_first = 0; fs.cand_last = 1;
+      fs.xc = (double*)dsx; fs.uc = (double*)dsu; fs.lcc = (double*)dslc;
+      fs.count = (int)rc_;
+      {
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_slq_rollout<MODEL><<<(unsigned)((rc_ + FC::inst - 1) / FC::inst), FC::threads, fwd_smem, ctx->stream>>>(fs);
+      }
+      {
+        const long long total = (long long)rc_ * (p->N + 1);
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fs);
+      }
+      fs.count = spec_count;
+      {
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_slq_accept_cand<MODEL><<<(unsigned)((spec_count + 3) / 4), 128, 0, ctx->stream>>>(fs);
+      }
+      ctx->stream = main_stream;
+      NOC_CUDA(ctx, cudaGetLastError());
+      NOC_CUDA(ctx, cudaEventRecord(ctx->join_ev, ctx->aux_stream));
+    }
     int32_t hc[2] = {0, 0};
     const int32_t* list = cur;
     int list_count = count;
@@ -1121,6 +1172,11 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
         }
       }
     }
+    if (spec_now) {   // join: the speculative round is complete; its instances lose their mark
+      NOC_CUDA(ctx, cudaStreamWaitEvent(main_stream, ctx->join_ev, 0));
+      LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+      k_slq_mark_spec<<<(spec_count + 127) / 128, 128, 0, ctx->stream>>>((const int32_t*)dslist, spec_count, (int32_t*)dflags, 0);
+    }
    }  // count > 0
     int32_t hn = 0;
     int mask = 1;
@@ -1133,9 +1189,19 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
       k_compact_flags<<<1, 1024, 0, ctx->stream>>>((int32_t*)dflags, mask, batch, nxt, (int32_t*)dcount);
     }
     NOC_CUDA(ctx, cudaGetLastError());
+    int32_t hs = 0;
+    if (spec_ok) {   // the instances that backtracked in this iteration and go on -> the next forward pass's speculative list
+      {
+        LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
+        k_compact_flags<<<1, 1024, 0, ctx->stream>>>((int32_t*)dflags, SLQ_FLAG_SPEC_NEXT, batch, (int32_t*)dslist, (int32_t*)dcount + 2);
+      }
+      NOC_CUDA(ctx, cudaGetLastError());
+      NOC_CUDA(ctx, cudaMemcpyAsync(&hs, (int32_t*)dcount + 2, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     NOC_CUDA(ctx, cudaMemcpyAsync(&hn, dcount, 4, cudaMemcpyDeviceToHost, ctx->stream));
     NOC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     count = hn;
+    spec_count = hs;
     std::swap(cur, nxt);
     pending_bit = new_pending_bit;
     pending_ev = new_pending_ev;

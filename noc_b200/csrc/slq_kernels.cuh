@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(128) k_slq_init(const double* __restrict__ x0,
     for (int i = 0; i < max_iter; ++i) alpha_idx[(size_t)b * max_iter + i] = -1;
 }
 
+constexpr int SLQ_FLAG_SPEC_NEXT = 16;   // backtracked in this iteration: speculate in the next one
+constexpr int SLQ_FLAG_SPEC_NOW = 32;    // handled by the speculative round of this iteration: the ordinary trial 0 skips it
+
 struct SlqFwdArgs {
   const int32_t* idx;       // [count] active instances
   int cont_bit;             // the flag bit an instance that continues gets (1; 4 or 8 from a deferred backtracking round)
@@ -132,6 +135,12 @@ struct SlqFwdArgs {
   int cand_first;           // trial index of candidate 0 (step length 2^-cand_first); candidates are consecutive trials
   int cand_last;            // 1: no step lengths remain after this round (an instance without a winner fails);
                             // 0: it is flagged for the next round instead
+  int spec;                 // 1: SPECULATIVE round — the instances that needed a shorter step in their previous iteration get ALL
+                            // their step lengths (cand_first = 0) as candidates beside everybody else's trial 0, on the auxiliary
+                            // stream: the nominal is read from x / u themselves (no trial 0 has overwritten it) and stays there
+                            // if no candidate passes.  The first passing candidate in order is the oracle's sequential search.
+  int spec_mark;            // 1: instances that end an iteration on a step index > 0 (or a failed line search they repeat) are
+                            // flagged SLQ_FLAG_SPEC_NEXT; their next forward pass is the speculative round
   double* xc;               // [count/cand_J][cand_J][N+1][n]
   double* uc;               // [count/cand_J][cand_J][N][m]
   double* lcc;              // [count/cand_J][cand_J][N+1]
@@ -212,13 +221,14 @@ __global__ void __launch_bounds__(FwdCfg<MODEL>::threads) k_slq_rollout(const Sl
   const int trial = cand ? a.cand_first + item % a.cand_J : a.trial;
   const int N = a.N;
   if (trial == 0 && a.bstatus[b] != 0) valid = false;   // regularisation exhausted: k_slq_accept records it
+  if (!cand && (a.flags[b] & SLQ_FLAG_SPEC_NOW)) valid = false;   // this instance's step lengths are candidates of the speculative round
   double* xb = cand ? a.xc + (size_t)item * (N + 1) * n : a.x + (size_t)b * (N + 1) * n;   // receives the trajectory
   double* ub = cand ? a.uc + (size_t)item * N * m : a.u + (size_t)b * N * m;
   double* xs = a.xn + (size_t)b * (N + 1) * n;   // holds the nominal from trial 0 on
   double* us = a.un + (size_t)b * N * m;
-  const bool first = trial == 0;
-  const double* xnom = first ? xb : xs;          // where this trial reads the nominal
-  const double* unom = first ? ub : us;
+  const bool first = trial == 0 && !a.spec;      // the in-place trial: reads the nominal it overwrites, and saves it
+  const double* xnom = a.spec ? a.x + (size_t)b * (N + 1) * n : (first ? xb : xs);   // where this trial reads the nominal
+  const double* unom = a.spec ? a.u + (size_t)b * N * m : (first ? ub : us);
   const double* Kb = a.K + (size_t)b * N * m * n;
   const double* kb = a.kff + (size_t)b * N * m;
   double alpha = 1.0;
@@ -331,6 +341,7 @@ __global__ void __launch_bounds__(128) k_slq_stage_cost(const SlqFwdArgs a) {
   const bool cand = a.cand_J > 0;
   const long long b = a.idx[cand ? item / a.cand_J : item];
   if (!cand && a.trial == 0 && a.bstatus[b] != 0) return;
+  if (!cand && (a.flags[b] & SLQ_FLAG_SPEC_NOW)) return;
   double x[n], xg[n], u[m];
   const double* xp = cand ? a.xc + ((size_t)item * (N + 1) + k) * n : a.x + ((size_t)b * (N + 1) + k) * n;
 #pragma unroll
@@ -403,6 +414,7 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
   if (item >= a.count) return;   // warp-uniform
   const long long b = a.idx[item];
   const int N = a.N;
+  if (a.flags[b] & SLQ_FLAG_SPEC_NOW) return;   // settled by the speculative round (warp-uniform)
   if (a.trial == 0 && a.bstatus[b] != 0) {  // regularisation exhausted in the backward pass
     if (lane == 0) {
       a.status[b] = 4;
@@ -434,10 +446,16 @@ __global__ void __launch_bounds__(128) k_slq_accept(const SlqFwdArgs a) {
     double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
     for (int i = lane; i < (N + 1) * n / 2; i += 32) dxp[i] = sx[i];
     for (int i = lane; i < N * m / 2; i += 32) dup[i] = su[i];
-    if (lane == 0) slq_line_search_failed(a, b);
+    if (lane == 0) {
+      slq_line_search_failed(a, b);
+      if (a.spec_mark && (a.flags[b] & a.cont_bit)) a.flags[b] |= SLQ_FLAG_SPEC_NEXT;
+    }
     return;
   }
-  if (lane == 0) slq_record_step(a, b, Jold, Jacc, a.trial);
+  if (lane == 0) {
+    slq_record_step(a, b, Jold, Jacc, a.trial);
+    if (a.spec_mark && a.trial > 0 && (a.flags[b] & a.cont_bit)) a.flags[b] |= SLQ_FLAG_SPEC_NEXT;
+  }
 }
 
 // speculative round (cand_J > 0): one WARP per rejected instance.  Lane c sums the stage costs of candidate c
@@ -453,6 +471,13 @@ __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
   if (item >= a.count) return;   // warp-uniform
   const long long b = a.idx[item];
   const int N = a.N;
+  if (a.spec && a.bstatus[b] != 0) {   // regularisation exhausted in the backward pass (k_slq_accept's rule for trial 0)
+    if (lane == 0) {
+      a.status[b] = 4;
+      a.iters[b] = a.iters[b] + 1;
+    }
+    return;
+  }
   const double Jold = a.J[b];
   const double dV1 = a.dV[b * 2], dV2 = a.dV[b * 2 + 1];
   double Jc = 0.0;
@@ -487,7 +512,8 @@ __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
   const double2* su = reinterpret_cast<const double2*>(c >= 0 ? a.uc + slot * N * m : a.un + (size_t)b * N * m);
   double2* dxp = reinterpret_cast<double2*>(a.x + (size_t)b * (N + 1) * n);
   double2* dup = reinterpret_cast<double2*>(a.u + (size_t)b * N * m);
-  {   // the winning trajectory over the nominal: eight 16-byte loads in flight per lane
+  if (c >= 0 || !a.spec) {   // the winning trajectory over the nominal (speculative round without a winner: x / u still hold it)
+    // eight 16-byte loads in flight per lane
     const int nx = (N + 1) * n / 2, nu = N * m / 2;
     int i = lane;
     for (; i + 7 * 32 < nx; i += 8 * 32) {
@@ -511,9 +537,20 @@ __global__ void __launch_bounds__(128) k_slq_accept_cand(const SlqFwdArgs a) {
   if (lane != 0) return;
   if (c < 0) {   // the nominal has been put back
     slq_line_search_failed(a, b);
+    if (a.spec_mark && (a.flags[b] & a.cont_bit)) a.flags[b] |= SLQ_FLAG_SPEC_NEXT;
     return;
   }
   slq_record_step(a, b, Jold, Jacc, a.cand_first + c);
+  if (a.spec_mark && a.cand_first + c > 0 && (a.flags[b] & a.cont_bit)) a.flags[b] |= SLQ_FLAG_SPEC_NEXT;
+}
+
+// SLQ_FLAG_SPEC_NOW on (set = 1) or off the instances of a (short) list.  The bit is set before the forward pass forks and
+// cleared after it has joined: the ordinary kernels on the main stream must see it whenever they run.
+__global__ void k_slq_mark_spec(const int32_t* __restrict__ list, int count, int32_t* __restrict__ flags, int set) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  if (set) flags[list[i]] |= SLQ_FLAG_SPEC_NOW;
+  else flags[list[i]] &= ~SLQ_FLAG_SPEC_NOW;
 }
 
 // Ordered stream compaction of one flag bit: out = ascending list of the i < n with flags[i] & mask, the bit is

@@ -9,19 +9,22 @@ from noc_b200 import problems as pb
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=[(0, 0, 0), (1, 1, 0), (0, 0, 1)],
-                ids=["default-schedule", "fixed-shapes+deferred-backtracking", "dfma-sweeps"])
+@pytest.fixture(scope="module", params=[(0, 0, 0, 0), (1, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1)],
+                ids=["default-schedule", "fixed-shapes+deferred-backtracking", "dfma-sweeps", "no-speculative-line-search"])
 def solver(request):
     """Every test of this module runs under both SLQ schedules — the default (balanced wave plan, the line search settled
     before the next sweep) and round 1's fixed launch shapes with the line search's backtracking round deferred beside
     the next sweep (NOC_OPT_NO_WAVE_PLAN, NOC_OPT_DEFERRED_BACKTRACK) — and on both families of backward-pass kernels: the
     tensor-core ones (default: short n=12 work lists on k_ric12_wpi, n=24 on k_ric24_mma, both fed by step-record kernels)
-    and, with NOC_OPT_NO_TENSOR_SWEEP, the DFMA kernels k_ric12 / k_ric24.  Neither ever changes a result."""
+    and, with NOC_OPT_NO_TENSOR_SWEEP, the DFMA kernels k_ric12 / k_ric24; and with the line search of the instances that
+    backtracked last time run speculatively beside the others' first trial (default) or not
+    (NOC_OPT_NO_SPECULATIVE_BACKTRACK).  None of this ever changes a result."""
     from noc_b200 import capi
     s = capi.Solver(0)
     s.set_option(capi.OPT_NO_WAVE_PLAN, request.param[0])
     s.set_option(capi.OPT_DEFERRED_BACKTRACK, request.param[1])
     s.set_option(capi.OPT_NO_TENSOR_SWEEP, request.param[2])
+    s.set_option(capi.OPT_NO_SPECULATIVE_BACKTRACK, request.param[3])
     yield s
     s.close()
 
