@@ -1033,7 +1033,7 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
       {
         const long long total = (long long)rc_ * (p->N + 1);
         LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-        k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fs);
+        k_slq_stage_cost<MODEL><<<(unsigned)std::min<long long>((total + 127) / 128, 16LL * ctx->sm_count), 128, wbytes, ctx->stream>>>(fs);
       }
       fs.count = spec_count;
       {
@@ -1059,7 +1059,7 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
       {
         const long long total = (long long)list_count * (p->N + 1);
         LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-        k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fa);
+        k_slq_stage_cost<MODEL><<<(unsigned)std::min<long long>((total + 127) / 128, 16LL * ctx->sm_count), 128, wbytes, ctx->stream>>>(fa);
       }
       NOC_CUDA(ctx, cudaGetLastError());
       {
@@ -1113,7 +1113,7 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
           {
             const long long total = (long long)rc_ * (p->N + 1);
             LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-            k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fa);
+            k_slq_stage_cost<MODEL><<<(unsigned)std::min<long long>((total + 127) / 128, 16LL * ctx->sm_count), 128, wbytes, ctx->stream>>>(fa);
           }
           fa.count = list_count;
           {
@@ -1146,7 +1146,7 @@ int slq_chunk(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const double*
             {
               const long long total = (long long)rc_ * (p->N + 1);
               LaunchScope ls(ctx, NOC_KERNEL_FORWARD);
-              k_slq_stage_cost<MODEL><<<(unsigned)((total + 127) / 128), 128, wbytes, ctx->stream>>>(fa);
+              k_slq_stage_cost<MODEL><<<(unsigned)std::min<long long>((total + 127) / 128, 16LL * ctx->sm_count), 128, wbytes, ctx->stream>>>(fa);
             }
             NOC_CUDA(ctx, cudaGetLastError());
             fa.count = list_count;
@@ -1672,6 +1672,9 @@ int noc_slq_solve_warm(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, cons
   if (p->reg_schedule != NOC_REG_X10 && p->reg_schedule != NOC_REG_ADAPTIVE) return fail(ctx, NOC_ERR_BAD_ARG, "unknown reg_schedule");
   if (batch > 0x7fffffffLL) return fail(ctx, NOC_ERR_BAD_ARG, "batch too large for 32-bit work lists");
   if (batch == 0) return NOC_OK;
+  // device buffers are used in place, by 16-byte accesses (cp.async, bulk copies, vector loads); host buffers are staged
+  for (const void* q : {(const void*)xgoal, (const void*)u_init, (const void*)x, (const void*)u, (const void*)K})
+    if (q && is_device_ptr(q) && misaligned16(q)) return fail(ctx, NOC_ERR_BAD_ARG, "device xgoal / u_init / x / u / K must be 16-byte aligned");
   return p->model == NOC_MODEL_QUAD12
              ? slq_impl<0>(ctx, p, batch, x0, xgoal, QRQf, u_init, x, u, K, cost, iters, alpha_idx, status)
              : slq_impl<1>(ctx, p, batch, x0, xgoal, QRQf, u_init, x, u, K, cost, iters, alpha_idx, status);

@@ -332,31 +332,36 @@ __global__ void __launch_bounds__(128) k_slq_stage_cost(const SlqFwdArgs a) {
   constexpr int n = model::Dims<MODEL>::n, m = model::Dims<MODEL>::m;
   extern __shared__ __align__(16) double sw[];
   CostW<MODEL> w;
-  load_weights<MODEL>(sw, a.qrqf, w);
+  load_weights<MODEL>(sw, a.qrqf, w);   // once per CTA: the grid is capped and every thread strides over the points
   const int N = a.N;
-  const long long tw = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (tw >= (long long)a.count * (N + 1)) return;
-  const int item = (int)(tw / (N + 1));
-  const int k = (int)(tw - (long long)item * (N + 1));
   const bool cand = a.cand_J > 0;
-  const long long b = a.idx[cand ? item / a.cand_J : item];
-  if (!cand && a.trial == 0 && a.bstatus[b] != 0) return;
-  if (!cand && (a.flags[b] & SLQ_FLAG_SPEC_NOW)) return;
-  double x[n], xg[n], u[m];
-  const double* xp = cand ? a.xc + ((size_t)item * (N + 1) + k) * n : a.x + ((size_t)b * (N + 1) + k) * n;
+  const long long total = (long long)a.count * (N + 1);
+  for (long long tw = (long long)blockIdx.x * blockDim.x + threadIdx.x; tw < total; tw += (long long)gridDim.x * blockDim.x) {
+    const int item = (int)(tw / (N + 1));
+    const int k = (int)(tw - (long long)item * (N + 1));
+    const long long b = a.idx[cand ? item / a.cand_J : item];
+    if (!cand && a.trial == 0 && a.bstatus[b] != 0) continue;
+    if (!cand && (a.flags[b] & SLQ_FLAG_SPEC_NOW)) continue;
+    double x[n], xg[n], u[m];
+    const double* xp = cand ? a.xc + ((size_t)item * (N + 1) + k) * n : a.x + ((size_t)b * (N + 1) + k) * n;
+    const double* gp = a.xgoal + (size_t)b * n;
 #pragma unroll
-  for (int i = 0; i < n; ++i) { x[i] = xp[i]; xg[i] = a.xgoal[b * n + i]; }
-  double c;
-  if (k < N) {
-    const double* up = cand ? a.uc + ((size_t)item * N + k) * m : a.u + ((size_t)b * N + k) * m;
+    for (int i = 0; i < n; i += 2) {   // (16-byte loads: rows of n doubles, n even, buffers 16-byte aligned)
+      const double2 v = *reinterpret_cast<const double2*>(xp + i), gq = __ldg(reinterpret_cast<const double2*>(gp + i));
+      x[i] = v.x; x[i + 1] = v.y; xg[i] = gq.x; xg[i + 1] = gq.y;
+    }
+    double c;
+    if (k < N) {
+      const double* up = cand ? a.uc + ((size_t)item * N + k) * m : a.u + ((size_t)b * N + k) * m;
 #pragma unroll
-    for (int j = 0; j < m; ++j) u[j] = up[j];
-    c = w.stage(x, u, xg);
-  } else {
-    c = w.terminal(x, xg);
+      for (int j = 0; j < m; j += 2) { const double2 v = *reinterpret_cast<const double2*>(up + j); u[j] = v.x; u[j + 1] = v.y; }
+      c = w.stage(x, u, xg);
+    } else {
+      c = w.terminal(x, xg);
+    }
+    if (cand) a.lcc[(size_t)item * (N + 1) + k] = c;
+    else a.lc[(size_t)b * (N + 1) + k] = c;
   }
-  if (cand) a.lcc[(size_t)item * (N + 1) + k] = c;
-  else a.lc[(size_t)b * (N + 1) + k] = c;
 }
 
 // (3) per instance: J = sum of the stage costs in ascending k (the oracle's order), Armijo test, bookkeeping,
