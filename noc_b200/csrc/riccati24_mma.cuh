@@ -14,11 +14,14 @@
 //   H' = W' + F'^T G'    the ten upper 8x8 tiles of 32 x 32: 60 DMMAs.  The A fragments of F'^T are the B fragments of F'
 //                        (same registers); G' goes through a shared-memory buffer, column tile by column tile, because a
 //                        DMMA's C layout is not its B layout.
-//   L D L^T of Huu (8x8) redundantly in every lane, the 24 gain columns (lanes 8..31) and the feed-forward (lanes 0..7)
-//                        back-substituted in ONE pass of the same code,
+//   L D L^T of Huu (8x8) distributed over the warp (m24_ldl_pivot: the lanes hold Huu as the C fragments of H' tile (0,0)),
+//                        the 24 gain columns (lanes 8..31) and the feed-forward (lanes 0..7) back-substituted in ONE
+//                        pass of the same code,
 //   P' = Hxx + Hux^T K   the six upper tiles of 24 x 24, k = 8: 12 DMMAs (chain over the input index from Hxx: §2.3 step 5).
-//   RIC_AFFINE extras (h = W e + F^T Vx, Vx', dV1 / dV2, mu, the input box) are per-lane DFMA chains over the lane's own
-//   column, issued between the DMMAs.
+//   RIC_AFFINE (the SLQ backward pass): everything of a step that does not depend on the recursion — the Jacobian entries,
+//   h0 = W e, ubar — arrives as a 912-byte step record from k_prep24 (PREP); h = h0 + F^T Vx, Vx', dV1 / dV2 are per-lane
+//   DFMA chains over the lane's own column, issued between the DMMAs; the input box is a warp-cooperative QP (m24_box_qp).
+//   RIC_DARE: the fixed-point iteration on one LTI record whose fragments stay in registers.
 // Tile store: every 8x8 tile in shared memory keeps element (r, c) at r*8 + (c ^ 4*((r>>1)&1)) — C-fragment stores
 // (16-byte pairs), A-fragment loads of either half (rows g, columns 4h+t) and transposed loads (rows 4h+t, column g) are
 // all bank-conflict free.  P is kept as its six upper tiles; an A fragment below the diagonal reads its mirror image.
