@@ -188,6 +188,31 @@ def test_slq_waypoints_bitexact(oracle, solver):
     assert len(set(out["iters"].tolist())) > 1           # instances leave the work list at different iterations
 
 
+@pytest.mark.parametrize("batch,N", [(1, 1), (1, 2), (3, 3), (5, 17)])
+def test_slq_tiny_horizons_and_batches(oracle, solver, batch, N):
+    """Edge shapes through the warp-per-instance backward pass (k_prep12 + k_ric12_wpi: step records, double-buffered bulk
+    copies, the first / last step of a sweep): horizons of one to three steps, single instances."""
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(batch, seed=70 + N); xg = pb.sample_goals(batch, seed=71 + N)
+    _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=8)
+
+
+def test_slq_list_crosses_the_short_list_threshold(oracle, solver):
+    """A batch above twelve instances per SM whose work list shrinks below it during the solve: the backward pass moves
+    from k_ric12<RIC_AFFINE> (eight instances per warp) to k_ric12_wpi (one per warp) between iterations, and the
+    line search of the instances that backtracked runs speculatively beside the others — same bits throughout."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    batch, N = 12 * sms + 40, 12
+    Q, R, Qf = pb.default_weights(); qr = pb.pack_qrqf(Q, R, Qf)
+    rng = np.random.default_rng(12)
+    x0 = pb.sample_x0(batch, seed=124)
+    x0[: batch // 8, 6:8] = rng.uniform(-0.9, 0.9, (batch // 8, 2))     # some aggressive starts: backtracking
+    xg = pb.sample_goals(batch, seed=16)
+    out = _slq_compare(oracle, solver, batch, N, x0, xg, qr, max_iter=12)
+    assert len(set(out["iters"].tolist())) > 2 and np.any(out["aidx"] > 0)
+
+
 def test_slq_backtracking_and_max_iter(oracle, solver):
     """Aggressive starts force alpha < 1; a small max_iter leaves some instances at MAX_ITER."""
     batch, N = 24, 40

@@ -135,6 +135,29 @@ def test_slq_dual24_bitexact(oracle, solver, kw):
         assert np.any(np.all(K == 0.0, axis=-1))
 
 
+@pytest.mark.parametrize("batch,N,box", [(1, 1, False), (2, 2, True), (3, 3, False), (5, 9, True)])
+def test_slq_dual24_tiny_horizons_and_batches(oracle, solver, batch, N, box):
+    """Edge shapes through k_prep24 + k_ric24_mma<RIC_AFFINE> (step records, double-buffered bulk copies, the first / last
+    step of a sweep) and their DFMA partner: horizons of one to three steps, single instances, with and without the box."""
+    from noc_b200 import capi
+    Q, R, Qf = pb.default_weights(M)
+    qr = pb.pack_qrqf(Q, R, Qf)
+    x0 = pb.sample_x0(batch, seed=80 + N, model=M)
+    xg = pb.sample_goals(batch, seed=81 + N, model=M)
+    kw = dict(u_min=1.0, u_max=3.5) if box else {}
+    prob = capi.problem(M, N, max_iter=6, **kw)
+    x = np.empty((batch, N + 1, 24)); u = np.empty((batch, N, 8)); K = np.empty((batch, N, 8, 24))
+    cost = np.empty(batch); iters = np.zeros(batch, dtype=np.int32); status = np.full(batch, -1, dtype=np.int32)
+    aidx = np.full((batch, prob.max_iter), -7, dtype=np.int32)
+    solver.slq_solve_batch(prob, batch, x0, xg, qr, x=x, u=u, K=K, cost=cost, iters=iters, alpha_idx=aidx, status=status)
+    opts = oracle.slq_opts(M, N, max_iter=prob.max_iter, u_min=prob.u_min, u_max=prob.u_max, reg0=prob.reg0,
+                           reg_schedule=prob.reg_schedule)
+    ref = oracle.slq_batch(opts, x0, xg, qr, want_traj=True, want_K=True)
+    assert np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"])
+    assert np.array_equal(aidx, ref["alpha_idx"]) and np.array_equal(cost, ref["cost"])
+    assert np.array_equal(x, ref["x"]) and np.array_equal(u, ref["u"]) and np.array_equal(K, ref["K"])
+
+
 def test_lqr24_multiwarp_config_bitexact(oracle, solver):
     """Batches above 2 x 2 x SM-count use the 8-warp CTA configuration of k_ric24 (smaller ones one warp per CTA)."""
     from noc_b200 import capi
