@@ -261,8 +261,13 @@ __device__ __forceinline__ bool m24_ldl_masked(const double* U, unsigned clmask,
   __syncwarp();
   return bad;
 }
+// qr / fmask: 1/D of the last masked factorisation the QP computed (its L is in Ls) and the clamped set it belongs to
+// (~0u: none, or it failed) — when the QP stops on that very set, which is the rule once the active set has settled, the
+// caller's gain solves reuse it instead of factoring again.
 __device__ __forceinline__ void m24_box_qp(const double* U, const double (&g)[8], const double (&lo)[8], const double (&hi)[8],
-                                           double (&xio)[8], unsigned& clmask, double* ws, double* Ls, int lane) {
+                                           double (&xio)[8], unsigned& clmask, double* ws, double* Ls, int lane,
+                                           double (&qr)[8], unsigned& fmask) {
+  fmask = ~0u;
   double* x = ws;
   double* r = ws + 8;
   double* xc = ws + 16;
@@ -298,8 +303,10 @@ __device__ __forceinline__ void m24_box_qp(const double* U, const double (&g)[8]
     int nfree;
     clmask = clamped_set(grad, nfree, gn);
     if (nfree == 0 || gn < R12_QP_GTOL * (1.0 + gmax)) { finish(); return; }
-    double qr[8];
-    if (m24_ldl_masked(U, clmask, qr, Ls, lane)) { finish(); return; }
+    if (fmask != clmask) {   // (an iteration on the clamped set of the previous one keeps its factorisation)
+      if (m24_ldl_masked(U, clmask, qr, Ls, lane)) { fmask = ~0u; finish(); return; }
+      fmask = clmask;
+    }
     double rhs[8], dx[8];
 #pragma unroll
     for (int a = 0; a < 8; ++a) rhs[a] = ((clmask >> a) & 1u) ? 0.0 : grad[a];
@@ -708,11 +715,11 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
           }
           if (!inside) {
             double* ws = base + O_QP;
-            unsigned clmask = 0;
-            m24_box_qp(Us, hur, lo, hi, kf, clmask, ws, Ls, lane);
+            unsigned clmask = 0, fmask = ~0u;
+            m24_box_qp(Us, hur, lo, hi, kf, clmask, ws, Ls, lane, ldr, fmask);
 #pragma unroll
             for (int c = 0; c < 8; ++c) cl[c] = ((clmask >> c) & 1u) != 0;
-            failed |= m24_ldl_masked(Us, clmask, ldr, Ls, lane);
+            if (fmask != clmask) failed |= m24_ldl_masked(Us, clmask, ldr, Ls, lane);   // (else: Ls / ldr already hold this factorisation)
             double rhs[8];
 #pragma unroll
             for (int c = 0; c < 8; ++c) rhs[c] = cl[c] ? 0.0 : hux[c];
