@@ -215,8 +215,8 @@ int noc_lqr_solve_along(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, 
  *   AB [batch][n*n+n*m] one LTI record per instance; QR [n*n+m*m] shared.
  *   Iterates the sweep step from P = Q until max|P'-P| < tol * max|P'| or max_iter.
  *   P [batch][n*n], K [batch][m*n], iters [batch], status [batch] (MAX_ITER if not converged)
- *   Any 1 <= n <= 24, 1 <= m <= 8 (NOC_MODEL_LTV_USER); (12,4) runs the tuned kernel, everything else the
- *   thread-per-instance one.                                                                         */
+ *   Any 1 <= n <= 24, 1 <= m <= 8 (NOC_MODEL_LTV_USER); (12,4) and (24,8) with A_THEN_B records run tuned kernels
+ *   (k_ric12<RIC_DARE>; k_ric24_mma<RIC_DARE> on the FP64 tensor cores), everything else the thread-per-instance one.   */
 int noc_dare_solve_batch(noc_ctx* ctx, const noc_problem_t* prob, int64_t batch, const double* AB,
                          const double* QR, double* P, double* K, int32_t* iters, int32_t* status);
 
