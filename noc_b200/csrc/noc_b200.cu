@@ -373,6 +373,19 @@ int launch_ric12_mma_cfg(noc_ctx* ctx, const Ric12Args& a) {
   NOC_CUDA(ctx, cudaGetLastError());
   return NOC_OK;
 }
+// per-instance weights (a.W = the QRQf array, a.w_stride = 304): W' fragments from L2 per instance-step
+int launch_ric12_mma_perw(noc_ctx* ctx, const Ric12Args& a) {
+  auto kern = k_ric12_mma<4, 2, false, true>;
+  const size_t smem = ric12_mma_smem_bytes<false>(4);
+  int rc = configure_kernel(ctx, (const void*)kern, smem, true);
+  if (rc) return rc;
+  {
+    LaunchScope ls(ctx, NOC_KERNEL_RICCATI);
+    kern<<<(unsigned)((a.batch + 31) / 32), 128, smem, ctx->stream>>>(a);
+  }
+  NOC_CUDA(ctx, cudaGetLastError());
+  return NOC_OK;
+}
 int launch_ric12_mma(noc_ctx* ctx, const Ric12Args& a) {
   switch (ctx->opt[NOC_OPT_TENSOR_SWEEP_VARIANT]) {
     case 1: return launch_ric12_mma_cfg<8, 1, false>(ctx, a);   // + phase interlock of scheduler mates (3.06 ms)
@@ -608,8 +621,15 @@ int lqr12_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, const doub
 int lqr_batch_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, bool generic, const double* dAB,
                      const double* dQ, int qr_per_instance, const double* dx0, double* dK, double* dK0, double* dP0,
                      double* dcost, int32_t* dstatus) {
-  if ((p->flags & NOC_FLAG_TIME_PARALLEL) && (generic || p->n != 12))
+  if ((p->flags & NOC_FLAG_TIME_PARALLEL) && (generic || qr_per_instance || p->n != 12))
     return fail(ctx, NOC_ERR_UNSUPPORTED, "NOC_FLAG_TIME_PARALLEL: n=12, m=4 with shared weights only");
+  if (qr_per_instance && !generic) {   // (12,4), A_THEN_B records: the tensor-core sweep reads each instance's own Q | R | Qf
+    Ric12Args a{};
+    a.AB = dAB; a.W = dQ; a.w_stride = 2 * 12 * 12 + 4 * 4; a.x0 = dx0;
+    a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
+    a.batch = batch; a.N = p->N;
+    return launch_ric12_mma_perw(ctx, a);
+  }
   if (generic) {
     RicGenArgs g{};
     g.AB = dAB; g.QRQf = dQ; g.x0 = dx0; g.K = dK; g.K0 = dK0; g.P0 = dP0; g.cost = dcost; g.status = dstatus;
@@ -1456,10 +1476,12 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   PendingGuard pending_guard(ctx);
   if (!AB || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "AB and QRQf are required");
   if (batch == 0) return NOC_OK;
-  // per-instance weights run on the thread-per-instance kernel whatever the shape: the tuned kernels keep one W / Qf
-  // per CTA in shared memory (a per-instance copy would halve their occupancy)
+  // per-instance weights: (12,4) with A_THEN_B records runs on k_ric12_mma<PERW> (W' fragments from L2 per instance-step);
+  // every other shape / layout on the thread-per-instance kernel (the other tuned kernels keep one W / Qf per CTA)
   const bool n24 = (p->n == 24 && p->m == 8);
-  const bool generic = qr_per_instance || (!(p->n == 12 && p->m == 4) && !n24);
+  const bool perw12 = qr_per_instance && p->n == 12 && p->m == 4 && p->layout == NOC_LAYOUT_A_THEN_B &&
+                      !(is_device_ptr(QRQf) && misaligned16(QRQf)) && !ctx->opt[NOC_OPT_NO_TENSOR_SWEEP];
+  const bool generic = (qr_per_instance && !perw12) || (!(p->n == 12 && p->m == 4) && !n24);
   if (generic && (p->n < 1 || p->n > RG_NMAX || p->m < 1 || p->m > RG_MMAX))
     return fail(ctx, NOC_ERR_UNSUPPORTED, "LTV sweep: 1 <= n <= 24 and 1 <= m <= 8 (tuned kernels: (12,4), (24,8))");
   if (misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned (TMA bulk copies)");

@@ -94,7 +94,12 @@ __device__ __forceinline__ void rm_store_upper(double* Ps, const double* h, int 
     if (i <= j) Ps[i * 12 + j] = h[i];
 }
 
-template <int WARPS, int MIN_CTAS, bool DIRECT>
+// PERW: per-instance weights.  a.W is then the caller's QRQf array ([batch][Q 144 | R 16 | Qf 144], a.w_stride doubles
+// apart) and every instance-step reads the C fragments of its own W' from L2 (three 16-byte loads per lane, requested two
+// pipeline slots — about forty DMMAs — before the H' product that starts from them; the eight instances' fragments would
+// take 96 registers, their tiles 12 KB of shared memory per warp).  Only the entries the spec reads are touched: Q[i][j]
+// for i <= j, R[a][b] for b <= a, Qf[i][j] for i <= j, exactly like k_build_w for the shared weights.
+template <int WARPS, int MIN_CTAS, bool DIRECT, bool PERW = false>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12Args a) {
   extern __shared__ __align__(128) double smem[];
   constexpr bool PAIRED = (WARPS == 8) && !DIRECT;
@@ -169,17 +174,33 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
   const int hs = g * 8 + 2 * t;                                                                // + 64*tile
   // C fragments of W' = W permuted (constant over the sweep): tiles (0,0), (0,1), (1,1)
   double wc[3][2];
-  {
+  if (!PERW) {
     const int tr[3] = {0, 0, 8}, tc[3] = {0, 8, 8};
 #pragma unroll
     for (int T = 0; T < 3; ++T)
 #pragma unroll
       for (int e = 0; e < 2; ++e) wc[T][e] = a.W[rm_perm(tr[T] + g) * 16 + rm_perm(tc[T] + 2 * t + e)];
   }
+  // PERW: the same fragments out of an instance's Q | R block, as 16-byte pairs.  Tile (0,0), element (g, 2t+e): both
+  // positions u (g < 4, t < 2): R[3-g][3-2t-e], a descending pair; both x: Q[g-4][2t-4+e]; mixed: zero.  Tile (0,1),
+  // element (g, 8+2t+e): Q[g-4][4+2t+e] for g >= 4, else zero.  Tile (1,1): Q[4+g][4+2t+e].
+  const bool w_uu = g < 4 && t < 2, w_on0 = (g < 4) == (t < 2), w_on1 = g >= 4;
+  const int w_off0 = w_uu ? 144 + (3 - g) * 4 + (2 - 2 * t) : (g - 4) * 12 + 2 * t - 4;
+  const int w_off1 = (g - 4) * 12 + 4 + 2 * t, w_off2 = (4 + g) * 12 + 4 + 2 * t;
+  double2 wq[2][3];        // ring over the instances of the tensor pipeline (raw pairs; the u-u pair is swapped on use)
+  auto load_w = [&](int q) {
+    const double* Wq = a.W + (size_t)(wlast + (q < nvalid ? q : nvalid - 1)) * (size_t)a.w_stride;
+    wq[q & 1][0] = wq[q & 1][1] = make_double2(0.0, 0.0);
+    if (w_on0) wq[q & 1][0] = __ldg(reinterpret_cast<const double2*>(Wq + w_off0));
+    if (w_on1) wq[q & 1][1] = __ldg(reinterpret_cast<const double2*>(Wq + w_off1));
+    wq[q & 1][2] = __ldg(reinterpret_cast<const double2*>(Wq + w_off2));
+  };
+  if (PERW) { load_w(0); load_w(1); }
 
   if (lane < RM_ZPAD) Gb[2 * RM_GBUF + lane] = 0.0;
   // P <- Qf
-  for (int e = t; e < 144; e += 4) Ps[e] = a.Qf[e];
+  const double* Qf_own = PERW ? a.W + (size_t)b * (size_t)a.w_stride + 160 : a.Qf;
+  for (int e = t; e < 144; e += 4) Ps[e] = Qf_own[e];
   for (int e = 144 + t; e < 192; e += 4) Ps[e] = 0.0;
 
   bool failed = false;
@@ -292,8 +313,16 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric12_mma(const Ric12A
 #pragma unroll
           for (int T = 0; T < 3; ++T) sts128(PHp + 64 * T + hs, hacc[T][0], hacc[T][1]);
         }
+        if (PERW) {
+          const double2 v0 = wq[(q - 1) & 1][0], v1 = wq[(q - 1) & 1][1], v2 = wq[(q - 1) & 1][2];
+          hacc[0][0] = w_uu ? v0.y : v0.x; hacc[0][1] = w_uu ? v0.x : v0.y;
+          hacc[1][0] = v1.x; hacc[1][1] = v1.y;
+          hacc[2][0] = v2.x; hacc[2][1] = v2.y;
+          load_w((q + 1) % 8);   // into the ring slot just read; slots 7 and 8 request instances 0 and 1 of the next step
+        } else {
 #pragma unroll
-        for (int T = 0; T < 3; ++T) { hacc[T][0] = wc[T][0]; hacc[T][1] = wc[T][1]; }
+          for (int T = 0; T < 3; ++T) { hacc[T][0] = wc[T][0]; hacc[T][1] = wc[T][1]; }
+        }
 #pragma unroll
         for (int ki = 0; ki < 3; ++ki) {
           rm_dmma(hacc[0][0], hacc[0][1], fb[(q - 1) % 4][ki][0], gb[(q - 1) & 1][ki][0]);   // tile (0,0)

@@ -280,7 +280,7 @@ def test_generic_dimensions_not_pd(oracle, solver):
 @pytest.mark.parametrize("n,m", [(12, 4), (24, 8), (5, 2)])
 def test_per_instance_weights_bitexact(oracle, solver, n, m):
     """qr_per_instance=1: every instance brings its own Q | R | Qf block; each must equal the oracle run with that
-    instance's weights (also for the tuned shapes, which then take the thread-per-instance kernel)."""
+    instance's weights ((12,4): k_ric12_mma<PERW>; the other shapes take the thread-per-instance kernel)."""
     from noc_b200 import capi
     rng = np.random.default_rng(500 + n)
     batch, N = 7, 12
@@ -304,6 +304,56 @@ def test_per_instance_weights_bitexact(oracle, solver, n, m):
         assert status[b] == ref["status"][0] == 0
         assert np.array_equal(K[b], ref["K"][0]) and np.array_equal(K0[b], ref["K0"][0])
         assert np.array_equal(P0[b], ref["P0"][0]) and cost[b] == ref["cost"][0]
+
+
+@pytest.mark.parametrize("batch,N", [(1, 1), (33, 3), (1003, 40), (2 * 148 * 32 + 13, 9)])
+def test_per_instance_weights_tensor_sweep_bitexact(oracle, solver, batch, N):
+    """(12,4) with A_THEN_B records and qr_per_instance=1 runs on k_ric12_mma<PERW> (W' fragments per instance-step from
+    the caller's QRQf array): ragged last warp, more than one wave, device-resident weights; bit-identical to the oracle
+    run per instance, to the thread-per-instance kernel (NOC_OPT_NO_TENSOR_SWEEP), and — with the UNUSED triangles of
+    Q, R, Qf overwritten by NaN — still the same (only Q[i][j], i <= j, R[a][b], b <= a, Qf[i][j], i <= j are read)."""
+    from noc_b200 import capi
+    import torch
+    n, m = 12, 4
+    rng = np.random.default_rng(900 + batch)
+    A = np.eye(n)[None, None] + 0.05 * rng.standard_normal((batch, N, n, n))
+    Bm = 0.2 * rng.standard_normal((batch, N, n, m))
+    AB = np.concatenate([A.reshape(batch, N, -1), Bm.reshape(batch, N, -1)], axis=2)
+    d = rng.uniform(0.5, 5.0, (batch, n)); M = 0.1 * rng.standard_normal((batch, n, n))
+    Q = np.einsum("bij,bkj->bik", M, M) + d[:, :, None] * np.eye(n)
+    L = 0.05 * rng.standard_normal((batch, m, m))
+    R = np.einsum("bij,bkj->bik", L, L) + rng.uniform(0.05, 1.0, (batch, m))[:, :, None] * np.eye(m)
+    Qf = 10.0 * Q + np.eye(n)
+    qr = np.concatenate([Q.reshape(batch, -1), R.reshape(batch, -1), Qf.reshape(batch, -1)], axis=1)
+    x0 = rng.standard_normal((batch, n))
+    prob = capi.problem(capi.MODEL_LTV_USER, N, n=n, m=m)
+
+    def run(qr_arg, no_tensor=0):
+        K = np.empty((batch, N, m, n)); K0 = np.empty((batch, m, n)); P0 = np.empty((batch, n, n)); cost = np.empty(batch)
+        status = np.full(batch, -1, dtype=np.int32)
+        solver.set_option(capi.OPT_NO_TENSOR_SWEEP, no_tensor)
+        try:
+            solver.lqr_solve_batch(prob, batch, AB, qr_arg, x0dev=x0, K=K, K0=K0, P0=P0, cost=cost, status=status,
+                                   qr_per_instance=True)
+        finally:
+            solver.set_option(capi.OPT_NO_TENSOR_SWEEP, 0)
+        return K, K0, P0, cost, status
+
+    got = run(qr)
+    assert np.all(got[4] == 0)
+    ref = oracle.lqr_batch(n, m, N, AB, qr, x0dev=x0, qr_per_instance=True)
+    for a, key in zip(got, ("K", "K0", "P0", "cost", "status")):
+        assert np.array_equal(a, ref[key]), key
+    if batch <= 1003:
+        for a, b in zip(got, run(qr, no_tensor=1)):
+            assert np.array_equal(a, b)
+    # device-resident weights with poisoned unused triangles
+    Qp = Q.copy(); Rp = R.copy(); Qfp = Qf.copy()
+    il = np.tril_indices(n, -1); iu = np.triu_indices(m, 1)
+    Qp[:, il[0], il[1]] = np.nan; Qfp[:, il[0], il[1]] = np.nan; Rp[:, iu[0], iu[1]] = np.nan
+    qrp = torch.from_numpy(np.concatenate([Qp.reshape(batch, -1), Rp.reshape(batch, -1), Qfp.reshape(batch, -1)], axis=1)).cuda()
+    for a, b in zip(got, run(qrp)):
+        assert np.array_equal(a, b)
 
 
 @pytest.mark.parametrize("model", [0, 1])

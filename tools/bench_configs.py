@@ -282,22 +282,40 @@ class Bench:
         """Rates of k_ric_generic (VERDICT r1 #5): DARE at n=24/m=8 and the LTV sweep with per-instance weights."""
         torch, s, capi, pb = self.torch, self.s, self.capi, self.pb
         out = {}
-        # per-instance weights, (12,4), N=100
-        nb, N = (2048 if self.quick else 16384), 100
+        # per-instance weights, (12,4), N=100: k_ric12_mma<PERW> (round 1/2: the thread-per-instance kernel, 0.28 M solves/s),
+        # and the same call forced onto the thread-per-instance kernel (NOC_OPT_NO_TENSOR_SWEEP) on a smaller batch
+        nb, N = (2048 if self.quick else 65536), 100
         qr = pb.pack_qrqf(*pb.default_weights())
         x0 = pb.sample_x0(nb, seed=9); d_x0 = self.T(x0)
         d_xbar = torch.empty(nb, N + 1, 12, **self.f64); d_AB = torch.empty(nb, N, 192, **self.f64)
         pm = capi.problem(capi.MODEL_QUAD12, N, flags=capi.FLAG_ASYNC)
         s.rollout_open_loop(pm, nb, d_x0, None, d_xbar); s.linearize_batch(pm, nb, d_xbar, None, d_AB)
-        d_qrb = self.T(np.tile(qr, (nb, 1)))
+        scale = np.linspace(0.5, 2.0, nb)[:, None]                      # every instance its own weights
+        d_qrb = self.T(np.tile(qr, (nb, 1)) * scale)
+        dK = torch.empty(nb, N, 48, **self.f64)
         dK0 = torch.empty(nb, 48, **self.f64); dst = torch.empty(nb, **self.i32)
         pl = capi.problem(capi.MODEL_LTV_USER, N, flags=capi.FLAG_ASYNC)
-        fn = lambda: s.lqr_solve_batch(pl, nb, d_AB, d_qrb, K0=dK0, status=dst, qr_per_instance=True)
+        fn = lambda: s.lqr_solve_batch(pl, nb, d_AB, d_qrb, K=dK, K0=dK0, status=dst, qr_per_instance=True)
         fn()
-        ms = ev_time(torch, self.stream, fn, 3)
+        ms = ev_time(torch, self.stream, fn, 10)
+        nbg = min(nb, 8192)
+        fng = lambda: s.lqr_solve_batch(pl, nbg, d_AB, d_qrb, K=dK, K0=dK0, status=dst, qr_per_instance=True)
+        s.set_option(capi.OPT_NO_TENSOR_SWEEP, 1)
+        try:
+            fng()
+            msg = ev_time(torch, self.stream, fng, 2)
+        finally:
+            s.set_option(capi.OPT_NO_TENSOR_SWEEP, 0)
+        gbs = nb * (N * BYTES_STEP[12] + 304 * 8) / (ms * 1e-3) / 1e9
         out["per_instance_weights_n12"] = {
-            "batch": nb, "N": N, "ms": ms, "solves_per_s": nb / ms * 1e3,
-            "roofline": fp64_roofline(float(nb) * N * FLOPS_STEP[12], ms, "k_ric_generic", "batch x N x 9,045")}
+            "batch": nb, "N": N, "ms": ms, "solves_per_s": nb / ms * 1e3, "status_not_ok": int((dst != 0).sum().item()),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs(), "unit": "GB/s", "frac": gbs / hbm_peak_gbs(),
+                         "kernel": "k_ric12_mma<PERW>", "bytes_model": "batch x (N x 1920 + 2432)"},
+            "fp64": fp64_roofline(float(nb) * N * FLOPS_STEP[12], ms, "k_ric12_mma<PERW>", "batch x N x 9,045"),
+            "thread_per_instance_kernel": {"batch": nbg, "ms": msg, "solves_per_s": nbg / msg * 1e3,
+                                           "roofline": fp64_roofline(float(nbg) * N * FLOPS_STEP[12], msg, "k_ric_generic", "batch x N x 9,045")},
+            "what": "noc_lqr_solve_batch(qr_per_instance=1), A_k,B_k and the [batch][304] weights resident in HBM, all K_k written"}
+        del dK
         # DARE n=24: the dual model linearised at its hover rest configuration
         nb2 = 512 if self.quick else 4096
         o_rec = None
