@@ -175,10 +175,10 @@ void noc_problem_defaults(noc_problem_t* p, int32_t model, int32_t N);
  * Finite-horizon LTV LQR sweep for `batch` independent instances.
  *   AB        [batch][N][n*n+n*m]   A_k,B_k records (prob->layout); any 1<=n<=24, 1<=m<=8 ((12,4) and (24,8) are the tuned shapes); a device pointer
  *                                   must be 16-byte aligned (the records are fetched by TMA bulk copies)
- *   QRQf      [n*n + m*m + n*n]     Q, R, Qf shared by the batch, or [batch][...] if qr_per_instance ((12,4) with
- *                                   A_THEN_B records: the tensor-core sweep, each instance's weight fragments read per
- *                                   step; other shapes / layouts: the thread-per-instance kernel).  Read: Q[i][j] and
- *                                   Qf[i][j] for i <= j, R[a][b] for b <= a
+ *   QRQf      [n*n + m*m + n*n]     Q, R, Qf shared by the batch, or [batch][...] if qr_per_instance ((12,4) and
+ *                                   (24,8) with A_THEN_B records: the tensor-core sweeps with each instance's own
+ *                                   weight fragments; other shapes / layouts: the thread-per-instance kernel).
+ *                                   Read: Q[i][j] and Qf[i][j] for i <= j, R[a][b] for b <= a
  *   x0dev     [batch][n] or NULL    initial deviation; needed only for `cost`
  *   K         [batch][N][m*n] or NULL   feedback gains u = K x
  *   K0        [batch][m*n]   or NULL   gains of step 0 only (MPC use)

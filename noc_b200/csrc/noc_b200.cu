@@ -446,10 +446,10 @@ int launch_ric24_cfg(noc_ctx* ctx, const Ric24Args& a, int residency = 0) {
 // records or the fused linearisation, bit-identical to k_ric24.  Two CTAs of six warps per SM; work lists that do not
 // fill the GPU run as one-warp CTAs (breadth-first over the SMs) with the residency cap of the wave plan.
 constexpr int kRic24MmaWarps = 6, kRic24MmaCtas = 2;
-template <int MODE, bool FUSED, int W, int CTAS, bool BOX, bool PREP>
+template <int MODE, bool FUSED, int W, int CTAS, bool BOX, bool PREP, bool PERW = false>
 int launch_ric24_mma_cfg(noc_ctx* ctx, const Ric24Args& a, const double* prep, int residency = 0) {
-  auto kern = k_ric24_mma<MODE, FUSED, W, CTAS, BOX, PREP>;
-  const size_t need = ric24_mma_smem_bytes<MODE, FUSED, BOX, PREP>(W);
+  auto kern = k_ric24_mma<MODE, FUSED, W, CTAS, BOX, PREP, PERW>;
+  const size_t need = ric24_mma_smem_bytes<MODE, FUSED, BOX, PREP, PERW>(W);
   const size_t smem = residency > 0 ? smem_for_residency(residency, need) : need;
   int rc = configure_kernel(ctx, (const void*)kern, residency > 0 ? kSmemMaxDynamic : need, true);
   if (rc) return rc;
@@ -472,6 +472,12 @@ int launch_ric24_mma_shape(noc_ctx* ctx, const Ric24Args& a, const double* prep)
     w = (a.batch <= 8LL * ctx->sm_count) ? (int)((a.batch + ctx->sm_count - 1) / ctx->sm_count) : 0;
   if (w > 0) return launch_ric24_mma_cfg<MODE, FUSED, 1, 1, BOX, PREP>(ctx, a, prep, w);
   return launch_ric24_mma_cfg<MODE, FUSED, kRic24MmaWarps, kRic24MmaCtas, BOX, PREP>(ctx, a, prep);
+}
+// per-instance weights (a.W = the QRQf array, a.w_stride = 1216): each warp stages its instance's W' tiles
+int launch_ric24_mma_perw(noc_ctx* ctx, const Ric24Args& a) {
+  if (a.batch <= 8LL * ctx->sm_count)
+    return launch_ric24_mma_cfg<RIC_LQR, false, 1, 1, false, false, true>(ctx, a, nullptr, (int)((a.batch + ctx->sm_count - 1) / ctx->sm_count));
+  return launch_ric24_mma_cfg<RIC_LQR, false, kRic24MmaWarps, kRic24MmaCtas, false, false, true>(ctx, a, nullptr);
 }
 // `prep_buf` (RIC_AFFINE): room for batch x N x M24_PREP_DOUBLES doubles — the step records k_prep24 leaves for the sweep
 template <int MODE, bool FUSED, bool BOX>
@@ -623,6 +629,13 @@ int lqr_batch_device(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, bool g
                      double* dcost, int32_t* dstatus) {
   if ((p->flags & NOC_FLAG_TIME_PARALLEL) && (generic || qr_per_instance || p->n != 12))
     return fail(ctx, NOC_ERR_UNSUPPORTED, "NOC_FLAG_TIME_PARALLEL: n=12, m=4 with shared weights only");
+  if (qr_per_instance && !generic && p->n == 24) {   // (24,8), A_THEN_B records: each warp stages its instance's W' tiles
+    Ric24Args a{};
+    a.AB = dAB; a.W = dQ; a.w_stride = 2 * 24 * 24 + 8 * 8; a.x0 = dx0;
+    a.K = dK; a.K0 = dK0; a.P0 = dP0; a.cost = dcost; a.status = dstatus;
+    a.batch = batch; a.N = p->N;
+    return launch_ric24_mma_perw(ctx, a);
+  }
   if (qr_per_instance && !generic) {   // (12,4), A_THEN_B records: the tensor-core sweep reads each instance's own Q | R | Qf
     Ric12Args a{};
     a.AB = dAB; a.W = dQ; a.w_stride = 2 * 12 * 12 + 4 * 4; a.x0 = dx0;
@@ -1476,12 +1489,13 @@ int noc_lqr_solve_batch(noc_ctx* ctx, const noc_problem_t* p, int64_t batch, con
   PendingGuard pending_guard(ctx);
   if (!AB || !QRQf) return fail(ctx, NOC_ERR_BAD_ARG, "AB and QRQf are required");
   if (batch == 0) return NOC_OK;
-  // per-instance weights: (12,4) with A_THEN_B records runs on k_ric12_mma<PERW> (W' fragments from L2 per instance-step);
-  // every other shape / layout on the thread-per-instance kernel (the other tuned kernels keep one W / Qf per CTA)
+  // per-instance weights: (12,4) and (24,8) with A_THEN_B records run on k_ric12_mma<PERW> (W' fragments from L2 per
+  // instance-step) / k_ric24_mma<PERW> (W' tiles staged per warp); every other shape / layout on the thread-per-instance
+  // kernel (the other tuned kernels keep one W / Qf per CTA)
   const bool n24 = (p->n == 24 && p->m == 8);
-  const bool perw12 = qr_per_instance && p->n == 12 && p->m == 4 && p->layout == NOC_LAYOUT_A_THEN_B &&
-                      !(is_device_ptr(QRQf) && misaligned16(QRQf)) && !ctx->opt[NOC_OPT_NO_TENSOR_SWEEP];
-  const bool generic = (qr_per_instance && !perw12) || (!(p->n == 12 && p->m == 4) && !n24);
+  const bool perw = qr_per_instance && ((p->n == 12 && p->m == 4) || n24) && p->layout == NOC_LAYOUT_A_THEN_B &&
+                    !(is_device_ptr(QRQf) && misaligned16(QRQf)) && !ctx->opt[NOC_OPT_NO_TENSOR_SWEEP];
+  const bool generic = (qr_per_instance && !perw) || (!(p->n == 12 && p->m == 4) && !n24);
   if (generic && (p->n < 1 || p->n > RG_NMAX || p->m < 1 || p->m > RG_MMAX))
     return fail(ctx, NOC_ERR_UNSUPPORTED, "LTV sweep: 1 <= n <= 24 and 1 <= m <= 8 (tuned kernels: (12,4), (24,8))");
   if (misaligned16(AB) && is_device_ptr(AB)) return fail(ctx, NOC_ERR_BAD_ARG, "device AB must be 16-byte aligned (TMA bulk copies)");

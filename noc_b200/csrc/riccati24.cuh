@@ -42,6 +42,7 @@ struct Ric24Args {
   const double* AB;      // [batch][N][768]
   const double* W;       // [32][32] symmetric blockdiag(Q,R)
   const double* Qf;      // [24][24]
+  long long w_stride;    // k_ric24_mma<PERW>: W = the per-instance QRQf array, this many doubles (1216) between instances
   const double* x0;      // [batch][24] or nullptr
   double* K;             // [batch][N][192] or nullptr
   double* K0;            // [batch][192] or nullptr

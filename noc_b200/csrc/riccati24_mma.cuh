@@ -64,9 +64,13 @@ template <int MODE, bool FUSED, bool BOX, bool PREP = false>
 __host__ __device__ constexpr int m24_warp_doubles() {
   return PREP ? (BOX ? M24P_QP + 32 : M24P_QP) : (FUSED ? M24_XS_END : M24_XS);
 }
-template <int MODE, bool FUSED, bool BOX, bool PREP = false>
+// PERW (per-instance weights, RIC_LQR on A_THEN_B records): every warp keeps the seven W' tiles its H' products start from
+// — (0,0) and the six upper tiles of the x-x block — for its own instance; twelve warps still share an SM (221 KB)
+constexpr int M24_WT_PERW = 448;
+template <int MODE, bool FUSED, bool BOX, bool PREP = false, bool PERW = false>
 inline size_t ric24_mma_smem_bytes(int warps) {
-  return sizeof(double) * (size_t)(M24_BAR_DOUBLES + M24_WT_DOUBLES + warps * m24_warp_doubles<MODE, FUSED, BOX, PREP>());
+  return sizeof(double) * (size_t)(M24_BAR_DOUBLES + (PERW ? 0 : M24_WT_DOUBLES) +
+                                   warps * (m24_warp_doubles<MODE, FUSED, BOX, PREP>() + (PERW ? M24_WT_PERW : 0)));
 }
 
 // Two threads per (work-list slot w, step k, vehicle v) — one evaluates the Jacobian, the other h0 and ubar (different warps:
@@ -345,8 +349,9 @@ __device__ __forceinline__ void m24_box_qp(const double* U, const double (&g)[8]
   finish();
 }
 
-template <int MODE, bool FUSED, int WARPS, int MIN_CTAS, bool BOX = false, bool PREP = false>
+template <int MODE, bool FUSED, int WARPS, int MIN_CTAS, bool BOX = false, bool PREP = false, bool PERW = false>
 __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24Args a, const double* __restrict__ prep) {
+  static_assert(!PERW || (MODE == RIC_LQR && !FUSED), "per-instance weights: the LTV sweep on records from HBM");
   static_assert(MODE == RIC_LQR || MODE == RIC_AFFINE || MODE == RIC_DARE, "LQR sweep, SLQ backward pass or DARE iteration");
   static_assert(MODE != RIC_DARE || !FUSED, "RIC_DARE iterates on one LTI record from HBM");
   constexpr bool DARE = MODE == RIC_DARE;
@@ -354,15 +359,17 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   static_assert(!BOX || MODE == RIC_AFFINE, "input box: SLQ only");
   static_assert(PREP == (MODE == RIC_AFFINE), "the SLQ backward pass, and only it, takes its step records from k_prep24");
   extern __shared__ __align__(128) double smem[];
-  constexpr int WD = m24_warp_doubles<MODE, FUSED, BOX, PREP>();
+  constexpr int WD = m24_warp_doubles<MODE, FUSED, BOX, PREP>() + (PERW ? M24_WT_PERW : 0);
   constexpr bool AFF = MODE == RIC_AFFINE;
   constexpr bool BUILD = FUSED && !PREP;   // the record is evaluated in the sweep
   constexpr bool TMA = !FUSED || PREP;     // something arrives by bulk copy on the warp's mbarrier
   constexpr int O_VS = M24P_VS, O_HV = M24P_HV, O_KF = M24P_KF, O_RR = M24P_RR, O_QP = M24P_QP;
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  double* Wt = smem + M24_BAR_DOUBLES;
-  double* base = Wt + M24_WT_DOUBLES + warp * WD;
+  // shared weights: ten W' tiles per CTA; PERW: the warp's own seven tiles behind its slice (a.W = the caller's
+  // [batch][Q 576 | R 64 | Qf 576] array, a.w_stride doubles apart)
+  double* base = smem + M24_BAR_DOUBLES + (PERW ? 0 : M24_WT_DOUBLES) + warp * WD;
+  double* Wt = PERW ? base + (WD - M24_WT_PERW) : smem + M24_BAR_DOUBLES;
   double* Fs = base + M24_FS;
   double* Pt = base + M24_PT;
   double* Hu = base + M24_HU;
@@ -371,7 +378,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   const unsigned bar = smem_u32(smem) + 8u * warp;
 
   // W' = W in the permuted order, upper tiles, C-fragment order (plain row-major tiles: each lane reads its own 16 bytes)
-  for (int e = threadIdx.x; e < M24_WT_DOUBLES; e += WARPS * 32) {
+  for (int e = threadIdx.x; e < (PERW ? 0 : M24_WT_DOUBLES); e += WARPS * 32) {
     const int T = e >> 6, r = (e >> 3) & 7, c = e & 7;
     const int mi = T < 4 ? 0 : (T < 7 ? 1 : (T < 9 ? 2 : 3));
     const int nj = T - m24_t4(mi, mi) + mi;
@@ -387,6 +394,21 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
   if (w >= a.batch) return;                  // a whole warp: nothing below synchronises across warps
   const long long b = (AFF && a.idx) ? (long long)a.idx[w] : w;
   const int N = a.N;
+  const double* Wown = PERW ? a.W + (size_t)b * (size_t)a.w_stride : nullptr;
+  if (PERW) {   // the spec reads Q[i][j] for i <= j and R[a][b] for b <= a (as k_build_w does for shared weights)
+    for (int e = lane; e < M24_WT_PERW; e += 32) {
+      const int T = e >> 6, r = (e >> 3) & 7, c = e & 7;
+      const int mi = T == 0 ? 0 : (T < 4 ? 1 : (T < 6 ? 2 : 3));
+      const int nj = T == 0 ? 0 : T + 3 - m24_t4(mi, mi) + mi;
+      const int pr = m24_perm(8 * mi + r), pc = m24_perm(8 * nj + c);   // W order: [x0 .. x23 | u0 .. u7]
+      const int lo = pr < pc ? pr : pc, hi = pr < pc ? pc : pr;
+      double v = 0.0;
+      if (hi < 24) v = Wown[lo * 24 + hi];
+      else if (lo >= 24) v = Wown[576 + (hi - 24) * 8 + (lo - 24)];
+      Wt[e] = v;
+    }
+    __syncwarp();
+  }
 
   // ---- lane constants
   const int s_g = (g >> 1) & 1, s_t = (t >> 1) & 1;
@@ -504,8 +526,14 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
     for (int mi = 0; mi < 3; ++mi)
 #pragma unroll
       for (int nj = mi; nj < 3; ++nj) {
-        const double* q = a.Qf + (8 * mi + g) * 24 + 8 * nj + 2 * t;
-        sts128(Pt + m24_t3(mi, nj) * 64 + cs_off, q[0], q[1]);
+        if (PERW) {   // Qf[i][j] for i <= j only
+          const int i = 8 * mi + g, j0 = 8 * nj + 2 * t, j1 = j0 + 1;
+          const double* qf = Wown + 640;
+          sts128(Pt + m24_t3(mi, nj) * 64 + cs_off, i <= j0 ? qf[i * 24 + j0] : qf[j0 * 24 + i], i <= j1 ? qf[i * 24 + j1] : qf[j1 * 24 + i]);
+        } else {
+          const double* q = a.Qf + (8 * mi + g) * 24 + 8 * nj + 2 * t;
+          sts128(Pt + m24_t3(mi, nj) * 64 + cs_off, q[0], q[1]);
+        }
       }
     if (FUSED) {
       if (PREP) fetch_prep(N - 1);
@@ -633,7 +661,7 @@ __global__ void __launch_bounds__(WARPS * 32, MIN_CTAS) k_ric24_mma(const Ric24A
 #pragma unroll
         for (int mi = 0; mi <= nj; ++mi) {
           if (mi == 0 && nj > 0) { hacc2[0][0] = 0.0; hacc2[0][1] = 0.0; continue; }   // W is block diagonal: Hux starts from 0
-          const double2 wv = lds128(Wt + m24_t4(mi, nj) * 64 + g * 8 + 2 * t);
+          const double2 wv = lds128(Wt + (PERW ? (mi == 0 ? 0 : m24_t4(mi, nj) - 3) : m24_t4(mi, nj)) * 64 + g * 8 + 2 * t);
           hacc2[mi][0] = wv.x; hacc2[mi][1] = wv.y;
         }
 #pragma unroll

@@ -306,16 +306,18 @@ def test_per_instance_weights_bitexact(oracle, solver, n, m):
         assert np.array_equal(P0[b], ref["P0"][0]) and cost[b] == ref["cost"][0]
 
 
-@pytest.mark.parametrize("batch,N", [(1, 1), (33, 3), (1003, 40), (2 * 148 * 32 + 13, 9)])
-def test_per_instance_weights_tensor_sweep_bitexact(oracle, solver, batch, N):
-    """(12,4) with A_THEN_B records and qr_per_instance=1 runs on k_ric12_mma<PERW> (W' fragments per instance-step from
-    the caller's QRQf array): ragged last warp, more than one wave, device-resident weights; bit-identical to the oracle
+@pytest.mark.parametrize("n,m,batch,N", [(12, 4, 1, 1), (12, 4, 33, 3), (12, 4, 1003, 40), (12, 4, 2 * 148 * 32 + 13, 9),
+                                         (24, 8, 1, 1), (24, 8, 33, 3), (24, 8, 8 * 148 + 5, 6), (24, 8, 12 * 148 + 7, 4)])
+def test_per_instance_weights_tensor_sweep_bitexact(oracle, n, m, batch, N):
+    """(12,4) / (24,8) with A_THEN_B records and qr_per_instance=1 run on k_ric12_mma<PERW> (W' fragments per instance-step
+    from the caller's QRQf array) / k_ric24_mma<PERW> (the warp stages its instance's W' tiles): ragged last warp / CTA,
+    one-warp and six-warp CTAs, more than one wave, device-resident weights; bit-identical to the oracle
     run per instance, to the thread-per-instance kernel (NOC_OPT_NO_TENSOR_SWEEP), and — with the UNUSED triangles of
     Q, R, Qf overwritten by NaN — still the same (only Q[i][j], i <= j, R[a][b], b <= a, Qf[i][j], i <= j are read)."""
     from noc_b200 import capi
     import torch
-    n, m = 12, 4
-    rng = np.random.default_rng(900 + batch)
+    solver = capi.Solver(0)          # (its own context: the test toggles NOC_OPT_NO_TENSOR_SWEEP)
+    rng = np.random.default_rng(900 + batch + n)
     A = np.eye(n)[None, None] + 0.05 * rng.standard_normal((batch, N, n, n))
     Bm = 0.2 * rng.standard_normal((batch, N, n, m))
     AB = np.concatenate([A.reshape(batch, N, -1), Bm.reshape(batch, N, -1)], axis=2)
@@ -344,7 +346,7 @@ def test_per_instance_weights_tensor_sweep_bitexact(oracle, solver, batch, N):
     ref = oracle.lqr_batch(n, m, N, AB, qr, x0dev=x0, qr_per_instance=True)
     for a, key in zip(got, ("K", "K0", "P0", "cost", "status")):
         assert np.array_equal(a, ref[key]), key
-    if batch <= 1003:
+    if batch * N * n <= 1003 * 40 * 12:
         for a, b in zip(got, run(qr, no_tensor=1)):
             assert np.array_equal(a, b)
     # device-resident weights with poisoned unused triangles
@@ -354,6 +356,7 @@ def test_per_instance_weights_tensor_sweep_bitexact(oracle, solver, batch, N):
     qrp = torch.from_numpy(np.concatenate([Qp.reshape(batch, -1), Rp.reshape(batch, -1), Qfp.reshape(batch, -1)], axis=1)).cuda()
     for a, b in zip(got, run(qrp)):
         assert np.array_equal(a, b)
+    solver.close()
 
 
 @pytest.mark.parametrize("model", [0, 1])

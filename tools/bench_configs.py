@@ -275,6 +275,24 @@ class Bench:
             else: blk["gains_bit_identical_to_tensor"] = bool(torch.equal(ref, kk))
             out[name] = blk
         s.set_option(capi.OPT_NO_TENSOR_SWEEP, 0)
+        # per-instance weights: k_ric24_mma<PERW> (each warp stages its instance's W' tiles); the thread-per-instance
+        # kernel, which ran this call before, on a small batch beside it
+        qrb = (qr.reshape(1, -1) * torch.linspace(0.5, 2.0, nb, **self.f64).reshape(-1, 1)).contiguous()
+        f3 = lambda: s.lqr_solve_batch(pl, nb, AB, qrb, x0dev=x0, K=K, K0=K0, cost=cost, status=st, qr_per_instance=True)
+        f3(); _, p3 = self.profiled(f3, 3)
+        ms = p3["riccati"]["ms"]
+        nbg = min(nb, 512)
+        f4 = lambda: s.lqr_solve_batch(pl, nbg, AB, qrb, x0dev=x0, K=K, K0=K0, cost=cost, status=st, qr_per_instance=True)
+        s.set_option(capi.OPT_NO_TENSOR_SWEEP, 1)
+        try:
+            f4(); msg = ev_time(torch, self.stream, f4, 1)
+        finally:
+            s.set_option(capi.OPT_NO_TENSOR_SWEEP, 0)
+        out["per_instance_weights"] = {
+            "ltv_kernel_ms": ms, "ltv_solves_per_s": nb / ms * 1e3, "status_not_ok": int((st[:nb] != 0).sum().item()),
+            "ltv_roofline": fp64_roofline(float(nb) * N * FLOPS_STEP[24], ms, "k_ric24_mma<RIC_LQR, PERW>",
+                                          "batch x N x 71,595 (dense symmetric count)"),
+            "thread_per_instance_kernel": {"batch": nbg, "ms": msg, "solves_per_s": nbg / msg * 1e3}}
         return out
 
     # ------------------------------------------------------------------------------------------- thread-per-instance kernel
