@@ -109,6 +109,14 @@ class BatchedLqr {
     ctx_->check(noc_lqr_solve_batch(ctx_->handle(), &p, batch, AB, weights_.qrqf.data(), 0, x0dev, K, K0, P0, cost,
                                     status));
   }
+  // the same with one Q | R | Qf block per instance: weights[batch][n*n + m*m + n*n] (host or device).  (12,4) and (24,8)
+  // with A_THEN_B records run on the tensor-core sweeps; other shapes on the thread-per-instance kernel.
+  void solveWithInstanceWeights(int64_t batch, const double* AB, const double* weights, const double* x0dev, double* K,
+                                double* K0, double* P0, double* cost, int32_t* status) {
+    noc_problem_t p = prob_;
+    p.model = NOC_MODEL_LTV_USER;
+    ctx_->check(noc_lqr_solve_batch(ctx_->handle(), &p, batch, AB, weights, 1, x0dev, K, K0, P0, cost, status));
+  }
   // built-in model: x0 -> hover-thrust nominal -> linearise -> sweep
   void solveFromInitialStates(int64_t batch, const double* x0, double* K, double* K0, double* P0, double* cost,
                               int32_t* status) {

@@ -171,6 +171,25 @@ int main() {
     for (double v : u) in_box = in_box && v >= 0.0 && v <= 4.0;
     CHECK(in_box);
   }
+  for (int model = 0; model < 2; ++model) {  // one Q | R | Qf block per instance: the PERW tensor-core sweeps (n=12 and n=24)
+    const int64_t B = 37;
+    const int N = 11, n = model ? 24 : 12, m = model ? 8 : 4, rec = n * n + n * m, qlen = 2 * n * n + m * m;
+    const Weights wm = Weights::quadrotorDefault(model ? 2 : 1);
+    std::vector<double> x0((size_t)B * n);
+    for (auto& v : x0) v = urand(-0.3, 0.3);
+    std::vector<double> AB((size_t)B * N * rec), qr((size_t)B * qlen);
+    noc_oracle_make_ab_batch(model ? NOC_O_MODEL_DUAL24 : NOC_O_MODEL_QUAD12, N, 0.02, B, x0.data(), 0, AB.data(), 0);
+    for (int64_t b = 0; b < B; ++b)
+      for (int e = 0; e < qlen; ++e) qr[(size_t)b * qlen + e] = wm.qrqf[e] * (0.5 + 0.04 * (double)b);
+    std::vector<double> K((size_t)B * N * m * n), K0((size_t)B * m * n), P0((size_t)B * n * n), cost(B);
+    std::vector<double> rK(K.size()), rK0(K0.size()), rP0(P0.size()), rcost(B);
+    std::vector<int32_t> st(B, -1), rst(B, -1);
+    BatchedLqr lqr(ctx, N, model ? NOC_MODEL_DUAL24 : NOC_MODEL_QUAD12);
+    lqr.solveWithInstanceWeights(B, AB.data(), qr.data(), x0.data(), K.data(), K0.data(), P0.data(), cost.data(), st.data());
+    noc_oracle_lqr_batch(n, m, N, B, AB.data(), 0, qr.data(), 1, x0.data(), rK.data(), rK0.data(), rP0.data(), rcost.data(),
+                         rst.data(), 0);
+    CHECK(same(K, rK) && same(K0, rK0) && same(P0, rP0) && same(cost, rcost) && st == rst);
+  }
   {  // errors surface as exceptions with the library's message
     BatchedLqr lqr(ctx, 10);
     bool threw = false;
