@@ -117,14 +117,17 @@ struct LdlReg {
       for (int l = 0; l < i; ++l) s = fmad(-L[i][l], y[l], s);
       y[i] = s;
     }
-    // back substitution on n_i = -z_i (exactly the oracle's chain with every sign flipped)
+    // back substitution on z, negated at the end like the oracle (a chain on -z_i flips the sign of exact zeros)
+    double z[M];
 #pragma unroll
     for (int i = M - 1; i >= 0; --i) {
-      double s = (-y[i]) * r[i];
+      double s = y[i] * r[i];
 #pragma unroll
-      for (int l = i + 1; l < M; ++l) s = fmad(-L[l][i], out[l], s);
-      out[i] = s;
+      for (int l = i + 1; l < M; ++l) s = fmad(-L[l][i], z[l], s);
+      z[i] = s;
     }
+#pragma unroll
+    for (int i = 0; i < M; ++i) out[i] = -z[i];
   }
 };
 

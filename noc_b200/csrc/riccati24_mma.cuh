@@ -222,13 +222,16 @@ __device__ __forceinline__ void m24_solve_neg(const double* Ls, const double (&r
     for (int l = 0; l < i; ++l) sacc = fmad(-Lr[i][l], y[l], sacc);
     y[i] = sacc;
   }
+  double z[M];   // negated at the end like the oracle (a chain on -z_i flips the sign of exact zeros)
 #pragma unroll
   for (int i = M - 1; i >= 0; --i) {
-    double sacc = (-y[i]) * r[i];
+    double sacc = y[i] * r[i];
 #pragma unroll
-    for (int l = i + 1; l < M; ++l) sacc = fmad(-Lr[l][i], out[l], sacc);
-    out[i] = sacc;
+    for (int l = i + 1; l < M; ++l) sacc = fmad(-Lr[l][i], z[l], sacc);
+    z[i] = sacc;
   }
+#pragma unroll
+  for (int i = 0; i < M; ++i) out[i] = -z[i];
 }
 
 // ---- input box, warp-cooperative restatement of box_qp_gen<8> for one instance per warp: the same

@@ -188,6 +188,13 @@ int main() {
     lqr.solveWithInstanceWeights(B, AB.data(), qr.data(), x0.data(), K.data(), K0.data(), P0.data(), cost.data(), st.data());
     noc_oracle_lqr_batch(n, m, N, B, AB.data(), 0, qr.data(), 1, x0.data(), rK.data(), rK0.data(), rP0.data(), rcost.data(),
                          rst.data(), 0);
+    if (!(same(K, rK) && same(K0, rK0) && same(P0, rP0) && same(cost, rcost) && st == rst)) {
+      std::printf("per-instance weights, model %d: K %d K0 %d P0 %d cost %d status %d\n", model, (int)same(K, rK), (int)same(K0, rK0),
+                  (int)same(P0, rP0), (int)same(cost, rcost), (int)(st == rst));
+      for (size_t i = 0; i < K.size(); ++i)
+        if (std::memcmp(&K[i], &rK[i], 8)) { std::printf("  first K mismatch at %zu (instance %zu, step %zu): %.17g vs %.17g\n", i, i / ((size_t)N * m * n), (i / ((size_t)m * n)) % N, K[i], rK[i]); break; }
+      for (int64_t b = 0; b < B; ++b) if (st[b] != rst[b]) { std::printf("  status[%lld] = %d vs %d\n", (long long)b, st[b], rst[b]); break; }
+    }
     CHECK(same(K, rK) && same(K0, rK0) && same(P0, rP0) && same(cost, rcost) && st == rst);
   }
   {  // errors surface as exceptions with the library's message
