@@ -8,6 +8,13 @@ import numpy as np
 from noc_b200 import capi, problems as pb
 from oracle import pyoracle as oracle
 
+def same_bits(a, b):
+    """float64 arrays: equal bit patterns (so the sign of an exact zero counts); NaNs in the same places count as equal"""
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and bool(np.all(na == nb)) and bool(np.all((a.view(np.int64) == b.view(np.int64)) | na))
+
+
 def run(cases=60, seed=1, verbose=True):
     rng = np.random.default_rng(seed)
     s = capi.Solver(0)
@@ -47,8 +54,8 @@ def run(cases=60, seed=1, verbose=True):
         ref = oracle.slq_batch(o, x0, xg, qr, want_traj=True, want_K=True)
         ok_inst = ref["status"] != 4      # (REG_FAIL leaves its gains unspecified)
         same = (np.array_equal(status, ref["status"]) and np.array_equal(iters, ref["iters"]) and np.array_equal(aidx, ref["alpha_idx"])
-                and np.array_equal(cost, ref["cost"], equal_nan=True) and np.array_equal(x, ref["x"], equal_nan=True)
-                and np.array_equal(u, ref["u"], equal_nan=True) and np.array_equal(K[ok_inst], ref["K"][ok_inst], equal_nan=True))
+                and same_bits(cost, ref["cost"]) and same_bits(x, ref["x"]) and same_bits(u, ref["u"])
+                and same_bits(K[ok_inst], ref["K"][ok_inst]))
         for k_, v_ in zip(*np.unique(ref["status"], return_counts=True)): seen["status"][int(k_)] = seen["status"].get(int(k_), 0) + int(v_)
         seen["backtracked"] += int((ref["alpha_idx"] > 0).any(axis=1).sum()); seen["ls_repeat"] += int((ref["alpha_idx"] == -2).any(axis=1).sum())
         seen["boxed"] += batch * int("u_min" in kw); seen["adaptive"] += batch * int("reg_schedule" in kw); seen["instances"] += batch
@@ -56,7 +63,10 @@ def run(cases=60, seed=1, verbose=True):
             bad += 1
             print(json.dumps({"case": c, "model": model, "N": N, "batch": batch, "kw": {k: float(v) for k, v in kw.items()}, "opts": opts,
                               "status": np.unique(status).tolist(), "ref_status": np.unique(ref["status"]).tolist(),
-                              "iters_eq": bool(np.array_equal(iters, ref["iters"])), "aidx_eq": bool(np.array_equal(aidx, ref["alpha_idx"]))}), flush=True)
+                              "iters_eq": bool(np.array_equal(iters, ref["iters"])), "aidx_eq": bool(np.array_equal(aidx, ref["alpha_idx"])),
+                              "cost_bits": same_bits(cost, ref["cost"]), "x_bits": same_bits(x, ref["x"]), "u_bits": same_bits(u, ref["u"]),
+                              "K_bits": same_bits(K[ok_inst], ref["K"][ok_inst]),
+                              "K_values": bool(np.array_equal(K[ok_inst], ref["K"][ok_inst], equal_nan=True))}), flush=True)
     s.close()
     out = {"cases": cases, "mismatches": bad, "seconds": round(time.time() - t0, 1), "covered": seen}
     if verbose: print(json.dumps(out))
