@@ -29,6 +29,12 @@ __device__ __forceinline__ void stg128_cs(double* p, double a, double b) {
   __stcs(reinterpret_cast<double2*>(p), make_double2(a, b));
 }
 
+// -x by flipping the sign bit on the integer pipe (a DADD with a negated operand would take an FP64 issue slot; the gain
+// solves negate their results last)
+__device__ __forceinline__ double neg_bits(double x) {
+  return __hiloint2double(__double2hiint(x) ^ (int)0x80000000, __double2loint(x));
+}
+
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // Adaptive Levenberg-Marquardt schedule of SLQ (oracle: reg_increase / reg_decrease): delta0 = 2,

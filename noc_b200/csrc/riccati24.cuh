@@ -127,7 +127,7 @@ struct LdlReg {
       z[i] = s;
     }
 #pragma unroll
-    for (int i = 0; i < M; ++i) out[i] = -z[i];
+    for (int i = 0; i < M; ++i) out[i] = neg_bits(z[i]);
   }
 };
 

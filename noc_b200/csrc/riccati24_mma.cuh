@@ -231,7 +231,7 @@ __device__ __forceinline__ void m24_solve_neg(const double* Ls, const double (&r
     z[i] = sacc;
   }
 #pragma unroll
-  for (int i = 0; i < M; ++i) out[i] = -z[i];
+  for (int i = 0; i < M; ++i) out[i] = neg_bits(z[i]);
 }
 
 // ---- input box, warp-cooperative restatement of box_qp_gen<8> for one instance per warp: the same
