@@ -55,6 +55,20 @@ def main():
                         cost=sb["cost"], iters=sb["iters"], alpha_idx=sb["alpha_idx"], status=sb["status"],
                         x=sb["x"], u=sb["u"])
 
+    # hover nominals with one Q | R | Qf block per instance (n=12 and n=24): gains with exact zeros — the oracle writes
+    # them as -0.0, and the fixtures keep the sign (tests compare bit patterns)
+    for model, name, N in ((0, "n12", 8), (1, "n24", 5)):
+        n, m = pb.dims(model)
+        batch = 4
+        xh = pb.hover_state(batch, model=model)
+        xh[2:] = pb.sample_x0(batch, seed=20261021, model=model)[2:]
+        ABh = oracle.make_ab_batch(model, N, pb.DT, xh)
+        qrb = np.tile(pb.pack_qrqf(*pb.default_weights(model)), (batch, 1)) * np.array([0.5, 1.0, 1.5, 2.0])[:, None]
+        rh = oracle.lqr_batch(n, m, N, ABh, qrb, x0dev=xh, qr_per_instance=True)
+        assert np.signbit(rh["K"][rh["K"] == 0.0]).any()
+        np.savez_compressed(os.path.join(OUT, f"lqr_hover_perw_{name}.npz"), x0=xh, qrqf=qrb, N=N, AB=ABh, K=rh["K"], K0=rh["K0"],
+                            P0=rh["P0"], cost=rh["cost"], status=rh["status"])
+
     # model: one step, one linearisation at a generic state (both models)
     for model, name in ((0, "quad12"), (1, "dual24")):
         x = pb.sample_x0(1, seed=7, model=model)[0]
