@@ -48,3 +48,25 @@ def test_jacobian_sparsity_predicates_cover_the_emitters():
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", src, "-o", exe])
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and "SPARSITY OK" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_facade_host_layer_is_clean_under_asan_and_ubsan():
+    """The C++ host layer and its test driver built with -fsanitize=address,undefined against the (uninstrumented)
+    product library: every buffer the facade hands to the C-ABI is an exact-size std::vector, so an out-of-bounds host
+    write by the library's copy-back, or UB in the header-only facade, is reported.  (compute-sanitizer is closed on the
+    GPU pool; this is the host-side tool that is left.)"""
+    _build()
+    exe = EXE + "_san"
+    src = os.path.join(ROOT, "tests", "cpp", "facade_test.cpp")
+    cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-I",
+           os.path.join(ROOT, "include"), src, "-o", exe, "-L", os.path.join(ROOT, "noc_b200"), "-lnoc_b200", "-L",
+           os.path.join(ROOT, "oracle"), "-lnoc_oracle", "-Wl,-rpath," + os.path.join(ROOT, "noc_b200"),
+           "-Wl,-rpath," + os.path.join(ROOT, "oracle"), "-Wl,-rpath,/usr/local/cuda/lib64", "-pthread"]
+    subprocess.check_call(cmd)
+    env = dict(os.environ, ASAN_OPTIONS="protect_shadow_gap=0:detect_leaks=0:abort_on_error=0",
+               UBSAN_OPTIONS="print_stacktrace=1")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900, env=env)
+    out = r.stdout + r.stderr
+    assert r.returncode == 0 and "FACADE OK" in out, out[-4000:]
+    assert "ERROR: AddressSanitizer" not in out and "runtime error" not in out, out[-4000:]
