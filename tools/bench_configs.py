@@ -297,7 +297,9 @@ class Bench:
 
     # ------------------------------------------------------------------------------------------- thread-per-instance kernel
     def generic(self):
-        """Rates of k_ric_generic (VERDICT r1 #5): DARE at n=24/m=8 and the LTV sweep with per-instance weights."""
+        """The two calls that ran on the thread-per-instance kernel k_ric_generic in round 1, on the kernels
+        that took them over — the LTV sweep with per-instance weights (k_ric12_mma<PERW>) and DARE at n=24/m=8
+        (k_ric24_mma<RIC_DARE>) — each with k_ric_generic's rate on a smaller batch beside it.  (The block keeps its name.)"""
         torch, s, capi, pb = self.torch, self.s, self.capi, self.pb
         out = {}
         # per-instance weights, (12,4), N=100: k_ric12_mma<PERW> (round 1/2: the thread-per-instance kernel, 0.28 M solves/s),
